@@ -1,0 +1,1252 @@
+// C-ABI layer of the B200 ART resampler path (include/esp_audio_b200.h).
+//
+// Host logic only: parameter validation with the reference's conventions (NULL / false
+// on failure, the same stderr lines), planning (plan.cpp), device-buffer management and
+// kernel launches.  No CPU compute path exists: without a usable CUDA device every
+// computing entry point fails with ESPB_ERR_CUDA.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <atomic>
+#include <string>
+#include <vector>
+
+#include "../../include/esp_audio_b200.h"
+#include "kernels.hpp"
+#include "plan.hpp"
+
+using namespace espb;
+
+// ------------------------------------------------------------------------------------
+// errors, counters
+// ------------------------------------------------------------------------------------
+static thread_local std::string g_last_error;
+static std::atomic<uint64_t> g_launches{0};
+
+namespace espb {
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+}  // namespace espb
+
+static int fail(int code, const char *what, const char *detail = nullptr) {
+  g_last_error = what;
+  if (detail) {
+    g_last_error += ": ";
+    g_last_error += detail;
+  }
+  return code;
+}
+static int cuda_fail(cudaError_t e, const char *what) { return fail(ESPB_ERR_CUDA, what, cudaGetErrorString(e)); }
+
+#define CU_TRY(expr, what)        \
+  do {                            \
+    cudaError_t e__ = (expr);     \
+    if (e__ != cudaSuccess)       \
+      return cuda_fail(e__, what); \
+  } while (0)
+
+static inline cudaStream_t as_stream(void *s) { return reinterpret_cast<cudaStream_t>(s); }
+
+static long env_long(const char *name, long dflt) {
+  const char *v = getenv(name);
+  return (v && *v) ? strtol(v, nullptr, 10) : dflt;
+}
+
+extern "C" {
+
+const char *espb_last_error(void) { return g_last_error.c_str(); }
+int espb_abi_version(void) { return ESPB_ABI_VERSION; }
+uint64_t espb_launch_count(void) { return g_launches.load(); }
+
+// ------------------------------------------------------------------------------------
+// device + buffers
+// ------------------------------------------------------------------------------------
+int espb_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+int espb_set_device(int device) {
+  CU_TRY(cudaSetDevice(device), "cudaSetDevice");
+  return ESPB_OK;
+}
+int espb_device_info(int *sm_count, int *cc_major, int *cc_minor, size_t *total_mem, char *name, int name_len) {
+  int dev = 0;
+  CU_TRY(cudaGetDevice(&dev), "cudaGetDevice");
+  cudaDeviceProp prop;
+  CU_TRY(cudaGetDeviceProperties(&prop, dev), "cudaGetDeviceProperties");
+  if (sm_count)
+    *sm_count = prop.multiProcessorCount;
+  if (cc_major)
+    *cc_major = prop.major;
+  if (cc_minor)
+    *cc_minor = prop.minor;
+  if (total_mem)
+    *total_mem = prop.totalGlobalMem;
+  if (name && name_len > 0) {
+    strncpy(name, prop.name, name_len - 1);
+    name[name_len - 1] = 0;
+  }
+  return ESPB_OK;
+}
+void *espb_malloc(size_t bytes) {
+  void *p = nullptr;
+  cudaError_t e = cudaMalloc(&p, bytes ? bytes : 1);
+  if (e != cudaSuccess) {
+    cuda_fail(e, "cudaMalloc");
+    return nullptr;
+  }
+  return p;
+}
+void espb_free(void *dptr) {
+  if (dptr)
+    cudaFree(dptr);
+}
+void *espb_malloc_host(size_t bytes) {
+  void *p = nullptr;
+  cudaError_t e = cudaMallocHost(&p, bytes ? bytes : 1);
+  if (e != cudaSuccess) {
+    cuda_fail(e, "cudaMallocHost");
+    return nullptr;
+  }
+  return p;
+}
+void espb_free_host(void *hptr) {
+  if (hptr)
+    cudaFreeHost(hptr);
+}
+int espb_memcpy_h2d(void *dst, const void *src, size_t bytes, void *stream) {
+  CU_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, as_stream(stream)), "cudaMemcpyAsync h2d");
+  return ESPB_OK;
+}
+int espb_memcpy_d2h(void *dst, const void *src, size_t bytes, void *stream) {
+  CU_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, as_stream(stream)), "cudaMemcpyAsync d2h");
+  return ESPB_OK;
+}
+int espb_memset(void *dst, int value, size_t bytes, void *stream) {
+  CU_TRY(cudaMemsetAsync(dst, value, bytes, as_stream(stream)), "cudaMemsetAsync");
+  return ESPB_OK;
+}
+void *espb_stream_create(void) {
+  cudaStream_t s = nullptr;
+  cudaError_t e = cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking);
+  if (e != cudaSuccess) {
+    cuda_fail(e, "cudaStreamCreate");
+    return nullptr;
+  }
+  return s;
+}
+void espb_stream_destroy(void *stream) {
+  if (stream)
+    cudaStreamDestroy(as_stream(stream));
+}
+int espb_stream_sync(void *stream) {
+  CU_TRY(cudaStreamSynchronize(as_stream(stream)), "cudaStreamSynchronize");
+  return ESPB_OK;
+}
+int espb_device_sync(void) {
+  CU_TRY(cudaDeviceSynchronize(), "cudaDeviceSynchronize");
+  return ESPB_OK;
+}
+void *espb_event_create(void) {
+  cudaEvent_t ev = nullptr;
+  cudaError_t e = cudaEventCreate(&ev);
+  if (e != cudaSuccess) {
+    cuda_fail(e, "cudaEventCreate");
+    return nullptr;
+  }
+  return ev;
+}
+void espb_event_destroy(void *ev) {
+  if (ev)
+    cudaEventDestroy(reinterpret_cast<cudaEvent_t>(ev));
+}
+int espb_event_record(void *ev, void *stream) {
+  CU_TRY(cudaEventRecord(reinterpret_cast<cudaEvent_t>(ev), as_stream(stream)), "cudaEventRecord");
+  return ESPB_OK;
+}
+int espb_event_elapsed_ms(void *start, void *stop, float *ms) {
+  CU_TRY(cudaEventSynchronize(reinterpret_cast<cudaEvent_t>(stop)), "cudaEventSynchronize");
+  CU_TRY(cudaEventElapsedTime(ms, reinterpret_cast<cudaEvent_t>(start), reinterpret_cast<cudaEvent_t>(stop)),
+         "cudaEventElapsedTime");
+  return ESPB_OK;
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------
+// small RAII-free device buffer helper
+// ------------------------------------------------------------------------------------
+namespace {
+
+struct DevBuf {
+  void *p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t bytes) {
+    if (bytes <= cap)
+      return cudaSuccess;
+    if (p)
+      cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e == cudaSuccess)
+      cap = bytes;
+    return e;
+  }
+  void release() {
+    if (p)
+      cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+  template <typename T>
+  T *as() const {
+    return static_cast<T *>(p);
+  }
+};
+
+struct ScheduleKey {
+  uint32_t offset_bits = 0, ratio_bits = 0;
+  int index = -1, n_in = -1, n_out = -1;
+  bool operator==(const ScheduleKey &o) const {
+    return offset_bits == o.offset_bits && ratio_bits == o.ratio_bits && index == o.index && n_in == o.n_in &&
+           n_out == o.n_out;
+  }
+};
+
+inline uint32_t f2u(float f) {
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  return u;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------
+// host pipelining helper shared by the ART batch and the wrapper
+// ------------------------------------------------------------------------------------
+namespace {
+
+struct HostPipe {
+  static const int kStreams = 3;
+  cudaStream_t s[kStreams] = {nullptr, nullptr, nullptr};
+  cudaEvent_t ready = nullptr;
+  bool ok = false;
+  cudaError_t init() {
+    if (ok)
+      return cudaSuccess;
+    for (int i = 0; i < kStreams; ++i) {
+      cudaError_t e = cudaStreamCreateWithFlags(&s[i], cudaStreamNonBlocking);
+      if (e != cudaSuccess)
+        return e;
+    }
+    cudaError_t e = cudaEventCreateWithFlags(&ready, cudaEventDisableTiming);
+    if (e != cudaSuccess)
+      return e;
+    ok = true;
+    return cudaSuccess;
+  }
+  void destroy() {
+    for (int i = 0; i < kStreams; ++i)
+      if (s[i])
+        cudaStreamDestroy(s[i]);
+    if (ready)
+      cudaEventDestroy(ready);
+    ok = false;
+  }
+};
+
+int pick_slab_streams(int num_streams) {
+  long forced = env_long("ESPB_HOST_SLABS", 0);
+  long slabs = forced > 0 ? forced : 8;
+  if (slabs > num_streams)
+    slabs = num_streams;
+  return (int) ((num_streams + slabs - 1) / slabs);
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------
+// ART resampler batch
+// ------------------------------------------------------------------------------------
+struct EspbResampleBatch {
+  int num_streams = 0, channels = 0;
+  ArtGeometry geo{};
+  float lowpass = 1.0f;
+  ArtState state{};
+  int mode = ESPB_MODE_FAST;
+  int bpp = 8;  // output blocks (warps) per pass
+  std::vector<float> bank_host;
+  DevBuf bank, hist[2];
+  int hist_cur = 0;
+  // per-call plan, cached by (state, n_in, n_out, ratio)
+  Schedule sched;
+  PassPlan plan;
+  ScheduleKey key;
+  bool plan_on_device = false;  // tables uploaded
+  int g_resident_first = -1, g_resident_end = -1;  // chunk range currently expanded in G
+  DevBuf d_outs, d_chunks, d_pcb, d_G;
+  size_t g_budget_bytes = (size_t) 1 << 30;
+  // device staging + CUDA streams of the host-buffer entry point
+  DevBuf stage_in, stage_out;
+  HostPipe pipe;
+  int n_series() const { return num_streams * channels; }
+};
+
+namespace {
+
+// Build (or reuse) the schedule + pass plan for this call and upload the tables.
+int prepare_call(EspbResampleBatch *c, int n_in, int n_out, float ratio, cudaStream_t stream) {
+  ScheduleKey k;
+  k.offset_bits = f2u(c->state.offset);
+  k.ratio_bits = f2u(ratio);
+  k.index = c->state.index;
+  k.n_in = n_in;
+  k.n_out = n_out;
+  if (c->plan_on_device && k == c->key)
+    return ESPB_OK;
+  c->plan_on_device = false;
+  c->g_resident_first = c->g_resident_end = -1;
+  build_schedule(c->geo, c->state, n_in, n_out, ratio, c->sched);
+  build_pass_plan(c->sched, c->geo.taps, c->bpp, c->plan);
+  c->key = k;
+  if (c->sched.generated == 0) {
+    c->plan_on_device = true;
+    return ESPB_OK;
+  }
+  CU_TRY(c->d_outs.reserve(c->sched.outs.size() * sizeof(OutEntry)), "cudaMalloc schedule");
+  CU_TRY(c->d_chunks.reserve(c->plan.chunks.size() * sizeof(ChunkEntry)), "cudaMalloc chunks");
+  CU_TRY(c->d_pcb.reserve(c->plan.pass_chunk_begin.size() * sizeof(int32_t)), "cudaMalloc passes");
+  CU_TRY(cudaMemcpyAsync(c->d_outs.p, c->sched.outs.data(), c->sched.outs.size() * sizeof(OutEntry),
+                         cudaMemcpyHostToDevice, stream),
+         "upload schedule");
+  CU_TRY(cudaMemcpyAsync(c->d_chunks.p, c->plan.chunks.data(), c->plan.chunks.size() * sizeof(ChunkEntry),
+                         cudaMemcpyHostToDevice, stream),
+         "upload chunks");
+  CU_TRY(cudaMemcpyAsync(c->d_pcb.p, c->plan.pass_chunk_begin.data(),
+                         c->plan.pass_chunk_begin.size() * sizeof(int32_t), cudaMemcpyHostToDevice, stream),
+         "upload passes");
+  c->plan_on_device = true;
+  return ESPB_OK;
+}
+
+// Number of passes per time slab so that the expanded coefficients fit the G budget.
+int passes_per_slab(const EspbResampleBatch *c) {
+  const int n_passes = c->plan.n_passes();
+  const size_t chunk_bytes = g_chunk_floats(c->bpp) * sizeof(float);
+  const size_t total = c->plan.chunks.size() * chunk_bytes;
+  if (total <= c->g_budget_bytes || n_passes <= 1)
+    return n_passes;
+  const double avg = (double) total / n_passes;
+  int pps = (int) ((double) c->g_budget_bytes / avg);
+  return pps < 1 ? 1 : pps;
+}
+
+// Make chunks [first, end) resident in G.
+int ensure_g(EspbResampleBatch *c, int chunk_first, int chunk_end, cudaStream_t stream) {
+  if (c->g_resident_first == chunk_first && c->g_resident_end == chunk_end)
+    return ESPB_OK;
+  const size_t chunk_floats = g_chunk_floats(c->bpp);
+  CU_TRY(c->d_G.reserve((size_t) (chunk_end - chunk_first) * chunk_floats * sizeof(float)), "cudaMalloc G");
+  CU_TRY(launch_expand(c->bank.as<float>(), c->d_outs.as<OutEntry>(), c->d_chunks.as<ChunkEntry>(),
+                       c->d_G.as<float>(), chunk_first, chunk_end - chunk_first, (int) c->sched.generated,
+                       c->geo.taps, c->bpp, stream),
+         "expand kernel");
+  c->g_resident_first = chunk_first;
+  c->g_resident_end = chunk_end;
+  return ESPB_OK;
+}
+
+int pick_passes_per_cta(const EspbResampleBatch *c, int n_series, int n_passes) {
+  long forced = env_long("ESPB_PPC", 0);
+  if (forced > 0)
+    return (int) forced;
+  int sms = 148;
+  int dev = 0;
+  if (cudaGetDevice(&dev) == cudaSuccess)
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const long groups = (n_series + kSeriesPerRow - 1) / kSeriesPerRow;
+  const long slots = (long) sms * 2;  // resident CTAs
+  // aim for >= 8 waves of CTAs so the tail stays small, but never less than 1 pass per CTA
+  long ppc = (groups * n_passes) / (slots * 8);
+  if (ppc < 1)
+    ppc = 1;
+  if (ppc > 64)
+    ppc = 64;
+  (void) c;
+  return (int) ppc;
+}
+
+// Resample + history update for series [series_first, series_first + n_series) of the batch.
+int run_series_range(EspbResampleBatch *c, int series_first, int n_series, const float *in, const EspbLayout &il,
+                     float *out, const EspbLayout &ol, int n_in, cudaStream_t stream, bool g_preexpanded) {
+  const int taps = c->geo.taps;
+  const float *hist_old = c->hist[c->hist_cur].as<float>() + (size_t) series_first * taps;
+  float *hist_new = c->hist[1 - c->hist_cur].as<float>() + (size_t) series_first * taps;
+  if (c->sched.generated > 0) {
+    ResampleParams p{};
+    p.in = in;
+    p.in_ss = il.stream_stride;
+    p.in_cs = il.channel_stride;
+    p.in_fs = il.frame_stride;
+    p.out = out;
+    p.out_ss = ol.stream_stride;
+    p.out_cs = ol.channel_stride;
+    p.out_fs = ol.frame_stride;
+    p.hist = hist_old;
+    p.chunks = c->d_chunks.as<ChunkEntry>();
+    p.pass_chunk_begin = c->d_pcb.as<int32_t>();
+    p.outs = c->d_outs.as<OutEntry>();
+    p.n_series = n_series;
+    p.channels = c->channels;
+    p.n_in = n_in;
+    p.n_out = (int) c->sched.generated;
+    p.taps = taps;
+    const int n_passes = c->plan.n_passes();
+    const int pps = passes_per_slab(c);
+    for (int pf = 0; pf < n_passes; pf += pps) {
+      const int pe = pf + pps < n_passes ? pf + pps : n_passes;
+      const int cf = c->plan.pass_chunk_begin[pf], ce = c->plan.pass_chunk_begin[pe];
+      if (!g_preexpanded || pps < n_passes) {
+        int rc = ensure_g(c, cf, ce, stream);
+        if (rc != ESPB_OK)
+          return rc;
+      }
+      p.G = c->d_G.as<float>();
+      p.g_chunk_base = cf;
+      p.pass_first = pf;
+      p.pass_end = pe;
+      p.passes_per_cta = pick_passes_per_cta(c, n_series, pe - pf);
+      CU_TRY(launch_resample(p, c->bpp, c->mode == ESPB_MODE_EXACT, stream), "resample kernel");
+    }
+  }
+  if (c->sched.used > 0)
+    CU_TRY(launch_history(in, il.stream_stride, il.channel_stride, il.frame_stride, hist_old, hist_new, n_series,
+                          c->channels, taps, (int) c->sched.used, stream),
+           "history kernel");
+  return ESPB_OK;
+}
+
+void finish_call(EspbResampleBatch *c) {
+  if (c->sched.used > 0)
+    c->hist_cur = 1 - c->hist_cur;
+  c->state = c->sched.end;
+}
+
+}  // namespace
+
+extern "C" {
+
+EspbResampleBatch *espb_resampleInit(int num_streams, int numChannels, int numTaps, int numFilters,
+                                     float lowpassRatio, int flags) {
+  if (!normalise_init(numTaps, numFilters, &lowpassRatio, &flags)) {
+    fail(ESPB_ERR_ARG, "resampleInit: invalid taps/filters");
+    return nullptr;
+  }
+  if (num_streams <= 0 || numChannels <= 0) {
+    fail(ESPB_ERR_ARG, "resampleInit: num_streams and numChannels must be positive");
+    return nullptr;
+  }
+  if (espb_device_count() <= 0) {
+    fail(ESPB_ERR_CUDA, "resampleInit: no CUDA device (this library has no CPU path)");
+    return nullptr;
+  }
+  EspbResampleBatch *c = new EspbResampleBatch();
+  c->num_streams = num_streams;
+  c->channels = numChannels;
+  c->geo = ArtGeometry{numTaps, numFilters, flags};
+  c->lowpass = lowpassRatio;
+  c->state = initial_state(numTaps);
+  long bpp = env_long("ESPB_BPP", 8);
+  c->bpp = (bpp == 4) ? 4 : 8;
+  long gb = env_long("ESPB_G_MBYTES", 0);
+  if (gb > 0)
+    c->g_budget_bytes = (size_t) gb << 20;
+  build_filter_bank(c->geo, lowpassRatio, c->bank_host);
+  const size_t bank_bytes = c->bank_host.size() * sizeof(float);
+  const size_t hist_bytes = (size_t) c->n_series() * numTaps * sizeof(float);
+  cudaError_t e = c->bank.reserve(bank_bytes);
+  if (e == cudaSuccess)
+    e = c->hist[0].reserve(hist_bytes);
+  if (e == cudaSuccess)
+    e = c->hist[1].reserve(hist_bytes);
+  if (e == cudaSuccess)
+    e = cudaMemcpy(c->bank.p, c->bank_host.data(), bank_bytes, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess)
+    e = cudaMemset(c->hist[0].p, 0, hist_bytes);
+  if (e == cudaSuccess)
+    e = cudaMemset(c->hist[1].p, 0, hist_bytes);
+  if (e != cudaSuccess) {
+    cuda_fail(e, "resampleInit: device allocation");
+    espb_resampleFree(c);
+    return nullptr;
+  }
+  return c;
+}
+
+void espb_resampleFree(EspbResampleBatch *c) {
+  if (!c)
+    return;
+  c->bank.release();
+  c->hist[0].release();
+  c->hist[1].release();
+  c->d_outs.release();
+  c->d_chunks.release();
+  c->d_pcb.release();
+  c->d_G.release();
+  c->stage_in.release();
+  c->stage_out.release();
+  c->pipe.destroy();
+  delete c;
+}
+
+int espb_resampleReset(EspbResampleBatch *c, void *stream) {
+  if (!c)
+    return fail(ESPB_ERR_ARG, "resampleReset: NULL context");
+  CU_TRY(cudaMemsetAsync(c->hist[c->hist_cur].p, 0, (size_t) c->n_series() * c->geo.taps * sizeof(float),
+                         as_stream(stream)),
+         "resampleReset");
+  c->state = initial_state(c->geo.taps);
+  return ESPB_OK;
+}
+
+void espb_resampleAdvancePosition(EspbResampleBatch *c, float delta) {
+  if (delta < 0.0f)
+    fprintf(stderr, "resampleAdvancePosition() can only advance forward!\n");
+  else
+    c->state.offset += delta;
+}
+
+float espb_resampleGetPosition(EspbResampleBatch *c) { return position_of(c->geo, c->state); }
+
+unsigned int espb_resampleGetRequiredSamples(EspbResampleBatch *c, int numOutputFrames, float ratio) {
+  return required_samples(c->geo, c->state, numOutputFrames, ratio);
+}
+unsigned int espb_resampleGetExpectedOutput(EspbResampleBatch *c, int numInputFrames, float ratio) {
+  return expected_output(c->geo, c->state, numInputFrames, ratio);
+}
+
+int espb_resampleSetMode(EspbResampleBatch *c, int mode) {
+  if (!c || (mode != ESPB_MODE_FAST && mode != ESPB_MODE_EXACT))
+    return fail(ESPB_ERR_ARG, "resampleSetMode: bad mode");
+  c->mode = mode;
+  return ESPB_OK;
+}
+
+int espb_resampleGetFlags(EspbResampleBatch *c) { return c->geo.flags; }
+void espb_resampleGetState(EspbResampleBatch *c, float *outputOffset, int *inputIndex) {
+  *outputOffset = c->state.offset;
+  *inputIndex = c->state.index;
+}
+int espb_resampleCopyFilters(EspbResampleBatch *c, float *host_dst) {
+  // read back from the device copy: what the kernels actually use
+  CU_TRY(cudaMemcpy(host_dst, c->bank.p, c->bank_host.size() * sizeof(float), cudaMemcpyDeviceToHost),
+         "resampleCopyFilters");
+  return ESPB_OK;
+}
+
+EspbResampleResult espb_resampleProcessLayout(EspbResampleBatch *c, const float *in, const EspbLayout *il,
+                                              int numInputFrames, float *out, const EspbLayout *ol,
+                                              int numOutputFrames, float ratio, void *stream) {
+  EspbResampleResult res = {0, 0};
+  if (!c || !il || !ol) {
+    fail(ESPB_ERR_ARG, "resampleProcess: NULL argument");
+    return res;
+  }
+  if (numInputFrames < 0)
+    numInputFrames = 0;
+  if (prepare_call(c, numInputFrames, numOutputFrames, ratio, as_stream(stream)) != ESPB_OK)
+    return res;
+  if (run_series_range(c, 0, c->n_series(), in, *il, out, *ol, numInputFrames, as_stream(stream), false) != ESPB_OK)
+    return res;
+  res.input_used = c->sched.used;
+  res.output_generated = c->sched.generated;
+  finish_call(c);
+  g_last_error.clear();
+  return res;
+}
+
+EspbResampleResult espb_resampleProcessInterleaved(EspbResampleBatch *c, const float *in, int64_t in_stream_stride,
+                                                   int numInputFrames, float *out, int64_t out_stream_stride,
+                                                   int numOutputFrames, float ratio, void *stream) {
+  if (!c) {
+    fail(ESPB_ERR_ARG, "resampleProcessInterleaved: NULL context");
+    return EspbResampleResult{0, 0};
+  }
+  EspbLayout il = {in_stream_stride, 1, c->channels}, ol = {out_stream_stride, 1, c->channels};
+  return espb_resampleProcessLayout(c, in, &il, numInputFrames, out, &ol, numOutputFrames, ratio, stream);
+}
+
+EspbResampleResult espb_resampleProcess(EspbResampleBatch *c, const float *in, int64_t in_stream_stride,
+                                        int64_t in_channel_stride, int numInputFrames, float *out,
+                                        int64_t out_stream_stride, int64_t out_channel_stride, int numOutputFrames,
+                                        float ratio, void *stream) {
+  EspbLayout il = {in_stream_stride, in_channel_stride, 1}, ol = {out_stream_stride, out_channel_stride, 1};
+  return espb_resampleProcessLayout(c, in, &il, numInputFrames, out, &ol, numOutputFrames, ratio, stream);
+}
+
+// Host-buffer variant: rows of `in`/`out` are host memory (pinned for full PCIe speed).
+// Streams are cut into slabs; slab i copies in, resamples and copies out on CUDA stream
+// i % 3 so that H2D, compute and D2H of neighbouring slabs overlap.  Synchronous.
+EspbResampleResult espb_resampleProcessInterleavedHost(EspbResampleBatch *c, const float *in,
+                                                       int64_t in_stream_stride, int numInputFrames, float *out,
+                                                       int64_t out_stream_stride, int numOutputFrames, float ratio);
+
+}  // extern "C"
+
+extern "C" {
+
+EspbResampleResult espb_resampleProcessInterleavedHost(EspbResampleBatch *c, const float *in,
+                                                       int64_t in_stream_stride, int numInputFrames, float *out,
+                                                       int64_t out_stream_stride, int numOutputFrames, float ratio) {
+  EspbResampleResult res = {0, 0};
+  if (!c) {
+    fail(ESPB_ERR_ARG, "resampleProcessInterleavedHost: NULL context");
+    return res;
+  }
+  if (numInputFrames < 0)
+    numInputFrames = 0;
+  EspbResampleBatch *hs = c;
+  cudaError_t e = hs->pipe.init();
+  if (e != cudaSuccess) {
+    cuda_fail(e, "host pipeline streams");
+    return res;
+  }
+  const int ch = c->channels;
+  const size_t in_row = (size_t) numInputFrames * ch, out_cap_row = (size_t) (numOutputFrames > 0 ? numOutputFrames : 0) * ch;
+  if (hs->stage_in.reserve((in_row ? in_row : 1) * c->num_streams * sizeof(float)) != cudaSuccess ||
+      hs->stage_out.reserve((out_cap_row ? out_cap_row : 1) * c->num_streams * sizeof(float)) != cudaSuccess) {
+    fail(ESPB_ERR_NOMEM, "host stage device buffers");
+    return res;
+  }
+  cudaStream_t s0 = hs->pipe.s[0];
+  if (prepare_call(c, numInputFrames, numOutputFrames, ratio, s0) != ESPB_OK)
+    return res;
+  const size_t out_row = (size_t) c->sched.generated * ch;
+  const bool single_slab_g = passes_per_slab(c) >= c->plan.n_passes();
+  if (c->sched.generated > 0 && single_slab_g) {
+    if (ensure_g(c, 0, (int) c->plan.chunks.size(), s0) != ESPB_OK)
+      return res;
+  }
+  cudaEventRecord(hs->pipe.ready, s0);
+  const int per = pick_slab_streams(c->num_streams);
+  EspbLayout il = {(int64_t) in_row, 1, ch}, ol = {(int64_t) out_cap_row, 1, ch};
+  int slab = 0;
+  for (int st0 = 0; st0 < c->num_streams; st0 += per, ++slab) {
+    const int ns = st0 + per <= c->num_streams ? per : c->num_streams - st0;
+    cudaStream_t s = single_slab_g ? hs->pipe.s[slab % HostPipe::kStreams] : s0;
+    cudaStreamWaitEvent(s, hs->pipe.ready, 0);
+    float *din = hs->stage_in.as<float>() + (size_t) st0 * in_row;
+    float *dout = hs->stage_out.as<float>() + (size_t) st0 * out_cap_row;
+    if (in_row) {
+      e = cudaMemcpy2DAsync(din, in_row * sizeof(float), in + (size_t) st0 * in_stream_stride,
+                            (size_t) in_stream_stride * sizeof(float), in_row * sizeof(float), ns,
+                            cudaMemcpyHostToDevice, s);
+      if (e != cudaSuccess) {
+        cuda_fail(e, "h2d");
+        return res;
+      }
+    }
+    if (run_series_range(c, st0 * ch, ns * ch, din, il, dout, ol, numInputFrames, s, single_slab_g) != ESPB_OK)
+      return res;
+    if (out_row) {
+      e = cudaMemcpy2DAsync(out + (size_t) st0 * out_stream_stride, (size_t) out_stream_stride * sizeof(float), dout,
+                            out_cap_row * sizeof(float), out_row * sizeof(float), ns, cudaMemcpyDeviceToHost, s);
+      if (e != cudaSuccess) {
+        cuda_fail(e, "d2h");
+        return res;
+      }
+    }
+  }
+  for (int i = 0; i < HostPipe::kStreams; ++i) {
+    e = cudaStreamSynchronize(hs->pipe.s[i]);
+    if (e != cudaSuccess) {
+      cuda_fail(e, "host pipeline sync");
+      return res;
+    }
+  }
+  res.input_used = c->sched.used;
+  res.output_generated = c->sched.generated;
+  finish_call(c);
+  g_last_error.clear();
+  return res;
+}
+
+// ------------------------------------------------------------------------------------
+// art_biquad
+// ------------------------------------------------------------------------------------
+void espb_biquad_lowpass(EspbBiquadCoefficients *f, double frequency) {
+  design_lowpass(reinterpret_cast<BiquadCoeffs *>(f), frequency);
+}
+void espb_biquad_highpass(EspbBiquadCoefficients *f, double frequency) {
+  design_highpass(reinterpret_cast<BiquadCoeffs *>(f), frequency);
+}
+
+}  // extern "C"
+
+struct EspbBiquadBatch {
+  int num_series = 0, num_sections = 0;
+  BiquadParams params{};
+  DevBuf state;
+};
+
+extern "C" {
+
+EspbBiquadBatch *espb_biquad_init(int num_series, int num_sections, const EspbBiquadCoefficients *coeffs,
+                                  float gain) {
+  if (num_series <= 0 || num_sections < 1 || num_sections > 4 || !coeffs) {
+    fail(ESPB_ERR_ARG, "biquad_init: bad arguments (1..4 sections)");
+    return nullptr;
+  }
+  if (espb_device_count() <= 0) {
+    fail(ESPB_ERR_CUDA, "biquad_init: no CUDA device (this library has no CPU path)");
+    return nullptr;
+  }
+  EspbBiquadBatch *f = new EspbBiquadBatch();
+  f->num_series = num_series;
+  f->num_sections = num_sections;
+  // art_biquad.cpp:43-51
+  f->params.a0 = coeffs->a0 * gain;
+  f->params.a1 = coeffs->a1 * gain;
+  f->params.a2 = coeffs->a2 * gain;
+  f->params.b1 = coeffs->b1;
+  f->params.b2 = coeffs->b2;
+  f->params.first_order = (coeffs->a2 == 0.0f && coeffs->b2 == 0.0f);
+  const size_t bytes = (size_t) num_series * num_sections * 4 * sizeof(float);
+  cudaError_t e = f->state.reserve(bytes);
+  if (e == cudaSuccess)
+    e = cudaMemset(f->state.p, 0, bytes);
+  if (e != cudaSuccess) {
+    cuda_fail(e, "biquad_init: device allocation");
+    f->state.release();
+    delete f;
+    return nullptr;
+  }
+  return f;
+}
+
+void espb_biquad_free(EspbBiquadBatch *f) {
+  if (!f)
+    return;
+  f->state.release();
+  delete f;
+}
+
+int espb_biquad_reset(EspbBiquadBatch *f, void *stream) {
+  if (!f)
+    return fail(ESPB_ERR_ARG, "biquad_reset: NULL");
+  CU_TRY(cudaMemsetAsync(f->state.p, 0, (size_t) f->num_series * f->num_sections * 4 * sizeof(float),
+                         as_stream(stream)),
+         "biquad_reset");
+  return ESPB_OK;
+}
+
+int espb_biquad_apply_buffer(EspbBiquadBatch *f, float *buf, const EspbLayout *layout, int channels, int num_samples,
+                             void *stream) {
+  if (!f || !layout || channels <= 0)
+    return fail(ESPB_ERR_ARG, "biquad_apply_buffer: bad arguments");
+  CU_TRY(launch_biquad(buf, layout->stream_stride, layout->channel_stride, layout->frame_stride, channels,
+                       f->num_series, f->num_sections, num_samples, f->params, f->state.as<float>(),
+                       as_stream(stream)),
+         "biquad kernel");
+  return ESPB_OK;
+}
+
+int espb_biquad_get_state(EspbBiquadBatch *f, float *host_dst) {
+  CU_TRY(cudaMemcpy(host_dst, f->state.p, (size_t) f->num_series * f->num_sections * 4 * sizeof(float),
+                    cudaMemcpyDeviceToHost),
+         "biquad_get_state");
+  return ESPB_OK;
+}
+
+// ------------------------------------------------------------------------------------
+// quantization_utils
+// ------------------------------------------------------------------------------------
+static int check_bits(uint8_t bits, const char *who) {
+  if (bits < 1 || bits > 32)
+    return fail(ESPB_ERR_ARG, who, "bits must be 1..32");
+  return ESPB_OK;
+}
+
+int espb_quantized_to_float_rows(const uint8_t *in, int64_t in_row_stride_bytes, float *out,
+                                 int64_t out_row_stride_floats, int rows, uint32_t row_samples, uint8_t input_bits,
+                                 float gain_db, void *stream) {
+  if (check_bits(input_bits, "quantized_to_float") != ESPB_OK)
+    return ESPB_ERR_ARG;
+  CU_TRY(launch_q2f(in, in_row_stride_bytes, out, out_row_stride_floats, rows, row_samples, input_bits,
+                    q2f_gain_factor(input_bits, gain_db), as_stream(stream)),
+         "q2f kernel");
+  return ESPB_OK;
+}
+
+int espb_float_to_quantized_rows(const float *in, int64_t in_row_stride_floats, uint8_t *out,
+                                 int64_t out_row_stride_bytes, int rows, uint32_t row_samples, uint8_t output_bits,
+                                 uint32_t *clipped_per_row_dev, void *stream) {
+  if (check_bits(output_bits, "float_to_quantized") != ESPB_OK)
+    return ESPB_ERR_ARG;
+  CU_TRY(launch_f2q(in, in_row_stride_floats, out, out_row_stride_bytes, rows, row_samples, output_bits,
+                    clipped_per_row_dev, true, as_stream(stream)),
+         "f2q kernel");
+  return ESPB_OK;
+}
+
+// A flat buffer is cut into rows of 2^22 samples so that 32-bit indexing inside the kernel is safe.
+static const uint64_t kFlatRow = (uint64_t) 1 << 22;
+
+int espb_quantized_to_float(const uint8_t *in, float *out, uint64_t num_samples, uint8_t input_bits, float gain_db,
+                            void *stream) {
+  if (check_bits(input_bits, "quantized_to_float") != ESPB_OK)
+    return ESPB_ERR_ARG;
+  const int nbytes = (input_bits + 7) / 8;
+  const float k = q2f_gain_factor(input_bits, gain_db);
+  const uint64_t full = num_samples / kFlatRow, rem = num_samples % kFlatRow;
+  for (uint64_t r0 = 0; r0 < full; r0 += 32768) {
+    const int rows = (int) (full - r0 < 32768 ? full - r0 : 32768);
+    CU_TRY(launch_q2f(in + r0 * kFlatRow * nbytes, (int64_t) kFlatRow * nbytes, out + r0 * kFlatRow,
+                      (int64_t) kFlatRow, rows, (uint32_t) kFlatRow, input_bits, k, as_stream(stream)),
+           "q2f kernel");
+  }
+  if (rem)
+    CU_TRY(launch_q2f(in + full * kFlatRow * nbytes, 0, out + full * kFlatRow, 0, 1, (uint32_t) rem, input_bits, k,
+                      as_stream(stream)),
+           "q2f kernel");
+  return ESPB_OK;
+}
+
+int espb_float_to_quantized(const float *in, uint8_t *out, uint64_t num_samples, uint8_t output_bits,
+                            uint32_t *clipped_dev, void *stream) {
+  if (check_bits(output_bits, "float_to_quantized") != ESPB_OK)
+    return ESPB_ERR_ARG;
+  const int nbytes = (output_bits + 7) / 8;
+  const uint64_t full = num_samples / kFlatRow, rem = num_samples % kFlatRow;
+  for (uint64_t r0 = 0; r0 < full; r0 += 32768) {
+    const int rows = (int) (full - r0 < 32768 ? full - r0 : 32768);
+    CU_TRY(launch_f2q(in + r0 * kFlatRow, (int64_t) kFlatRow, out + r0 * kFlatRow * nbytes,
+                      (int64_t) kFlatRow * nbytes, rows, (uint32_t) kFlatRow, output_bits, clipped_dev, false,
+                      as_stream(stream)),
+           "f2q kernel");
+  }
+  if (rem)
+    CU_TRY(launch_f2q(in + full * kFlatRow, 0, out + full * kFlatRow * nbytes, 0, 1, (uint32_t) rem, output_bits,
+                      clipped_dev, false, as_stream(stream)),
+           "f2q kernel");
+  return ESPB_OK;
+}
+
+uint32_t espb_float_to_quantized_sync(const float *in, uint8_t *out, uint64_t num_samples, uint8_t output_bits,
+                                      void *stream) {
+  uint32_t *d = nullptr, h = 0;
+  if (cudaMalloc(&d, sizeof(uint32_t)) != cudaSuccess) {
+    fail(ESPB_ERR_NOMEM, "float_to_quantized: counter");
+    return 0;
+  }
+  cudaMemsetAsync(d, 0, sizeof(uint32_t), as_stream(stream));
+  if (espb_float_to_quantized(in, out, num_samples, output_bits, d, stream) == ESPB_OK) {
+    cudaMemcpyAsync(&h, d, sizeof(uint32_t), cudaMemcpyDeviceToHost, as_stream(stream));
+    cudaError_t e = cudaStreamSynchronize(as_stream(stream));
+    if (e != cudaSuccess)
+      cuda_fail(e, "float_to_quantized sync");
+  }
+  cudaFree(d);
+  return h;
+}
+
+// ------------------------------------------------------------------------------------
+// host-side planning (no device)
+// ------------------------------------------------------------------------------------
+int espb_plan_filter_bank(int numTaps, int numFilters, float lowpassRatio, int flags, float *host_dst,
+                          int *effective_flags) {
+  if (!normalise_init(numTaps, numFilters, &lowpassRatio, &flags))
+    return fail(ESPB_ERR_ARG, "plan_filter_bank: invalid taps/filters");
+  std::vector<float> bank;
+  build_filter_bank(ArtGeometry{numTaps, numFilters, flags}, lowpassRatio, bank);
+  if (host_dst)
+    memcpy(host_dst, bank.data(), bank.size() * sizeof(float));
+  if (effective_flags)
+    *effective_flags = flags;
+  return ESPB_OK;
+}
+
+int espb_plan_schedule(int numTaps, int numFilters, int flags, float outputOffset, int inputIndex,
+                       int numInputFrames, int numOutputFrames, float ratio, unsigned int *input_used,
+                       unsigned int *output_generated, float *end_outputOffset, int *end_inputIndex,
+                       int32_t *window_start, int32_t *phase, float *weight, int32_t *kind) {
+  if ((numTaps & 3) || numTaps <= 0 || numTaps > 1024 || numFilters < 2 || numFilters > 1024)
+    return fail(ESPB_ERR_ARG, "plan_schedule: invalid taps/filters");
+  Schedule s;
+  build_schedule(ArtGeometry{numTaps, numFilters, flags}, ArtState{outputOffset, inputIndex}, numInputFrames,
+                 numOutputFrames, ratio, s);
+  if (input_used)
+    *input_used = s.used;
+  if (output_generated)
+    *output_generated = s.generated;
+  if (end_outputOffset)
+    *end_outputOffset = s.end.offset;
+  if (end_inputIndex)
+    *end_inputIndex = s.end.index;
+  for (size_t i = 0; i < s.outs.size(); ++i) {
+    if (window_start)
+      window_start[i] = s.outs[i].ws;
+    if (phase)
+      phase[i] = s.outs[i].phase;
+    if (weight)
+      weight[i] = s.outs[i].w;
+    if (kind)
+      kind[i] = s.outs[i].kind;
+  }
+  return ESPB_OK;
+}
+
+int espb_plan_policy(const EspbResamplerConfiguration *config, EspbBiquadCoefficients *coeffs, float *sample_ratio,
+                     float *art_lowpass, int *art_flags) {
+  if (!config)
+    return fail(ESPB_ERR_ARG, "plan_policy: NULL");
+  WrapperPolicy p;
+  decide_policy(config->source_sample_rate, config->target_sample_rate, config->number_of_taps,
+                config->use_pre_or_post_filter != 0, config->subsample_interpolate != 0, &p);
+  if (coeffs)
+    memcpy(coeffs, &p.coeffs, sizeof(EspbBiquadCoefficients));
+  if (sample_ratio)
+    *sample_ratio = p.sample_ratio;
+  if (art_lowpass)
+    *art_lowpass = p.art_lowpass;
+  if (art_flags) {  // resampleInit would normalise the flags the same way
+    float lp = p.art_lowpass;
+    int fl = p.art_flags;
+    if (lp > 0.0f && lp < 1.0f)
+      fl |= kFlagLowpass;
+    else
+      fl &= ~kFlagLowpass;
+    *art_flags = p.resampling ? fl : 0;
+  }
+  return p.pre ? 1 : (p.post ? 2 : 0);
+}
+
+// ------------------------------------------------------------------------------------
+// utilities
+// ------------------------------------------------------------------------------------
+int espb_checksum_u32(const void *buf, uint64_t num_words, uint64_t *sum_dev, void *stream) {
+  CU_TRY(launch_checksum(static_cast<const uint32_t *>(buf), num_words,
+                         reinterpret_cast<unsigned long long *>(sum_dev), as_stream(stream)),
+         "checksum kernel");
+  return ESPB_OK;
+}
+
+int espb_measure_fp32_fma_peak(double *tflops, double *sm_clock_mhz_estimate) {
+  if (!tflops)
+    return fail(ESPB_ERR_ARG, "measure_fp32_fma_peak: NULL");
+  CU_TRY(run_fma_probe(tflops, sm_clock_mhz_estimate), "fma probe");
+  return ESPB_OK;
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------
+// resampler::Resampler, batched
+// ------------------------------------------------------------------------------------
+struct EspbResampler {
+  int num_streams = 0;
+  size_t in_samples = 0, out_samples = 0;  // per-stream float scratch sizes (reference ctor arguments)
+  EspbResamplerConfiguration cfg{};
+  WrapperPolicy policy;
+  EspbResampleBatch *art = nullptr;
+  EspbBiquadBatch *lowpass = nullptr;
+  DevBuf fin, fout, clipped, pcm_in, pcm_out;
+  uint32_t *clipped_host = nullptr;  // pinned
+  HostPipe pipe;
+};
+
+namespace {
+
+struct WrapperCall {
+  size_t todo = 0, used = 0, generated = 0;
+};
+
+// Steps of Resampler::resample (resampler.cpp:100-160) for stream rows [s0, s0+ns).
+int wrapper_run_range(EspbResampler *r, int s0, int ns, const uint8_t *d_in, int64_t in_stride_bytes, uint8_t *d_out,
+                      int64_t out_stride_bytes, const WrapperCall &wc, size_t out_free, float gain_db,
+                      cudaStream_t stream, bool g_preexpanded) {
+  const int ch = r->cfg.channels;
+  float *fin = r->fin.as<float>() + (size_t) s0 * r->in_samples;
+  float *fout = r->fout.as<float>() + (size_t) s0 * r->out_samples;
+  uint32_t *clip = r->clipped.as<uint32_t>() + s0;
+  const uint8_t *in = d_in + (size_t) s0 * in_stride_bytes;
+  uint8_t *out = d_out + (size_t) s0 * out_stride_bytes;
+  CU_TRY(cudaMemsetAsync(clip, 0, ns * sizeof(uint32_t), stream), "clip counters");
+  const bool rs = r->policy.resampling;
+  // :112-119 quantized_to_float into the float input (or, without resampling, output) buffer
+  CU_TRY(launch_q2f(in, in_stride_bytes, rs ? fin : fout, (int64_t) (rs ? r->in_samples : r->out_samples), ns,
+                    (uint32_t) (wc.todo * ch), r->cfg.source_bits_per_sample,
+                    q2f_gain_factor(r->cfg.source_bits_per_sample, gain_db), stream),
+         "q2f kernel");
+  if (rs) {
+    EspbLayout il = {(int64_t) r->in_samples, 1, ch}, ol = {(int64_t) r->out_samples, 1, ch};
+    EspbBiquadBatch *lp = r->lowpass;
+    if (r->policy.pre && wc.todo)  // :126-133
+      CU_TRY(launch_biquad(fin, il.stream_stride, 1, ch, ch, ns * ch, lp->num_sections, (int) wc.todo, lp->params,
+                           lp->state.as<float>() + (size_t) s0 * ch * lp->num_sections * 4, stream),
+             "biquad kernel");
+    int rc = run_series_range(r->art, s0 * ch, ns * ch, fin, il, fout, ol, (int) wc.todo, stream, g_preexpanded);
+    if (rc != ESPB_OK)
+      return rc;
+    if (r->policy.post && wc.generated)  // :142-149
+      CU_TRY(launch_biquad(fout, ol.stream_stride, 1, ch, ch, ns * ch, lp->num_sections, (int) wc.generated,
+                           lp->params, lp->state.as<float>() + (size_t) s0 * ch * lp->num_sections * 4, stream),
+             "biquad kernel");
+  }
+  (void) out_free;
+  // :152-153 float_to_quantized + clip count
+  CU_TRY(launch_f2q(fout, (int64_t) r->out_samples, out, out_stride_bytes, ns, (uint32_t) (wc.generated * ch),
+                    r->cfg.target_bits_per_sample, clip, true, stream),
+         "f2q kernel");
+  return ESPB_OK;
+}
+
+// The host-known part of the call: frames_to_process and the schedule.
+int wrapper_plan(EspbResampler *r, size_t avail, size_t out_free, cudaStream_t stream, WrapperCall *wc) {
+  size_t todo = avail;
+  if (r->policy.resampling) {  // :104-107
+    const size_t need = espb_resampleGetRequiredSamples(r->art, (int) out_free, r->policy.sample_ratio);
+    if (need < todo)
+      todo = need;
+  } else if (out_free < todo) {
+    todo = out_free;
+  }
+  const size_t ch = r->cfg.channels;
+  if (todo * ch > (r->policy.resampling ? r->in_samples : r->out_samples))
+    return fail(ESPB_ERR_ARG, "resample: frames exceed the float buffer size given at construction");
+  wc->todo = todo;
+  wc->used = todo;
+  wc->generated = todo;
+  if (r->policy.resampling) {
+    int rc = prepare_call(r->art, (int) todo, (int) out_free, r->policy.sample_ratio, stream);
+    if (rc != ESPB_OK)
+      return rc;
+    wc->used = r->art->sched.used;
+    wc->generated = r->art->sched.generated;
+    if (wc->generated * ch > r->out_samples)
+      return fail(ESPB_ERR_ARG, "resample: output exceeds the float buffer size given at construction");
+  }
+  return ESPB_OK;
+}
+
+EspbResamplerResults wrapper_finish(EspbResampler *r, const WrapperCall &wc, uint32_t *clipped_per_stream_host) {
+  EspbResamplerResults res{};
+  uint64_t total = 0;
+  for (int s = 0; s < r->num_streams; ++s)
+    total += r->clipped_host[s];
+  if (clipped_per_stream_host)
+    memcpy(clipped_per_stream_host, r->clipped_host, r->num_streams * sizeof(uint32_t));
+  res.frames_used = wc.used;
+  res.frames_generated = wc.generated;
+  res.predicted_frames_used = wc.todo;
+  res.clipped_samples = total;
+  if (r->policy.resampling)
+    finish_call(r->art);
+  g_last_error.clear();
+  return res;
+}
+
+}  // namespace
+
+extern "C" {
+
+EspbResampler *espb_resampler_create(int num_streams, size_t input_buffer_samples, size_t output_buffer_samples,
+                                     const EspbResamplerConfiguration *config) {
+  if (!config || num_streams <= 0 || config->channels == 0) {
+    fail(ESPB_ERR_ARG, "resampler_create: bad arguments");
+    return nullptr;
+  }
+  if (espb_device_count() <= 0) {
+    fail(ESPB_ERR_CUDA, "resampler_create: no CUDA device (this library has no CPU path)");
+    return nullptr;
+  }
+  EspbResampler *r = new EspbResampler();
+  r->num_streams = num_streams;
+  r->cfg = *config;
+  // round the per-stream scratch rows up to 4 floats so rows stay 16-byte aligned
+  r->in_samples = (input_buffer_samples + 3) & ~(size_t) 3;
+  r->out_samples = (output_buffer_samples + 3) & ~(size_t) 3;
+  decide_policy(config->source_sample_rate, config->target_sample_rate, config->number_of_taps,
+                config->use_pre_or_post_filter != 0, config->subsample_interpolate != 0, &r->policy);
+  cudaError_t e = r->fin.reserve((r->in_samples ? r->in_samples : 4) * num_streams * sizeof(float));
+  if (e == cudaSuccess)
+    e = r->fout.reserve((r->out_samples ? r->out_samples : 4) * num_streams * sizeof(float));
+  if (e == cudaSuccess)
+    e = r->clipped.reserve(num_streams * sizeof(uint32_t));
+  if (e == cudaSuccess)
+    e = cudaMallocHost(&r->clipped_host, num_streams * sizeof(uint32_t));
+  if (e != cudaSuccess) {
+    cuda_fail(e, "resampler_create: device allocation");
+    espb_resampler_free(r);
+    return nullptr;
+  }
+  if (r->policy.resampling) {
+    r->art = espb_resampleInit(num_streams, config->channels, config->number_of_taps, config->number_of_filters,
+                               r->policy.art_lowpass, r->policy.art_flags);
+    if (!r->art) {
+      espb_resampler_free(r);
+      return nullptr;
+    }
+    espb_resampleAdvancePosition(r->art, config->number_of_taps / 2.0f);  // resampler.cpp:94
+    if (r->policy.pre || r->policy.post) {
+      r->lowpass = espb_biquad_init(num_streams * config->channels, 2,
+                                    reinterpret_cast<const EspbBiquadCoefficients *>(&r->policy.coeffs), 1.0f);
+      if (!r->lowpass) {
+        espb_resampler_free(r);
+        return nullptr;
+      }
+    }
+  }
+  return r;
+}
+
+void espb_resampler_free(EspbResampler *r) {
+  if (!r)
+    return;
+  if (r->art)
+    espb_resampleFree(r->art);
+  if (r->lowpass)
+    espb_biquad_free(r->lowpass);
+  r->fin.release();
+  r->fout.release();
+  r->clipped.release();
+  r->pcm_in.release();
+  r->pcm_out.release();
+  if (r->clipped_host)
+    cudaFreeHost(r->clipped_host);
+  r->pipe.destroy();
+  delete r;
+}
+
+int espb_resampler_set_mode(EspbResampler *r, int mode) {
+  if (!r)
+    return fail(ESPB_ERR_ARG, "resampler_set_mode: NULL");
+  return r->art ? espb_resampleSetMode(r->art, mode) : ESPB_OK;
+}
+
+int espb_resampler_policy(EspbResampler *r, EspbBiquadCoefficients *coeffs, float *sample_ratio, float *art_lowpass,
+                          int *art_flags) {
+  if (coeffs)
+    memcpy(coeffs, &r->policy.coeffs, sizeof(EspbBiquadCoefficients));
+  if (sample_ratio)
+    *sample_ratio = r->policy.sample_ratio;
+  if (art_lowpass)
+    *art_lowpass = r->policy.art_lowpass;
+  if (art_flags)
+    *art_flags = r->art ? r->art->geo.flags : 0;
+  return r->policy.pre ? 1 : (r->policy.post ? 2 : 0);
+}
+
+EspbResamplerResults espb_resampler_resample(EspbResampler *r, const uint8_t *in, int64_t in_stride_bytes,
+                                             uint8_t *out, int64_t out_stride_bytes, size_t input_frames_available,
+                                             size_t output_frames_free, float gain_db,
+                                             uint32_t *clipped_per_stream_host, void *stream) {
+  EspbResamplerResults none{};
+  if (!r) {
+    fail(ESPB_ERR_ARG, "resample: NULL");
+    return none;
+  }
+  cudaStream_t s = as_stream(stream);
+  WrapperCall wc;
+  if (wrapper_plan(r, input_frames_available, output_frames_free, s, &wc) != ESPB_OK)
+    return none;
+  if (wrapper_run_range(r, 0, r->num_streams, in, in_stride_bytes, out, out_stride_bytes, wc, output_frames_free,
+                        gain_db, s, false) != ESPB_OK)
+    return none;
+  cudaError_t e = cudaMemcpyAsync(r->clipped_host, r->clipped.p, r->num_streams * sizeof(uint32_t),
+                                  cudaMemcpyDeviceToHost, s);
+  if (e == cudaSuccess)
+    e = cudaStreamSynchronize(s);
+  if (e != cudaSuccess) {
+    cuda_fail(e, "resample: sync");
+    return none;
+  }
+  return wrapper_finish(r, wc, clipped_per_stream_host);
+}
+
+EspbResamplerResults espb_resampler_resample_host(EspbResampler *r, const uint8_t *in, int64_t in_stride_bytes,
+                                                  uint8_t *out, int64_t out_stride_bytes,
+                                                  size_t input_frames_available, size_t output_frames_free,
+                                                  float gain_db, uint32_t *clipped_per_stream_host) {
+  EspbResamplerResults none{};
+  if (!r) {
+    fail(ESPB_ERR_ARG, "resample_host: NULL");
+    return none;
+  }
+  cudaError_t e = r->pipe.init();
+  if (e != cudaSuccess) {
+    cuda_fail(e, "host pipeline streams");
+    return none;
+  }
+  cudaStream_t s0 = r->pipe.s[0];
+  WrapperCall wc;
+  if (wrapper_plan(r, input_frames_available, output_frames_free, s0, &wc) != ESPB_OK)
+    return none;
+  const int ch = r->cfg.channels;
+  const size_t in_bytes = wc.todo * ch * ((r->cfg.source_bits_per_sample + 7) / 8);
+  const size_t out_bytes = wc.generated * ch * ((r->cfg.target_bits_per_sample + 7) / 8);
+  const size_t in_pitch = (in_bytes + 15) & ~(size_t) 15, out_pitch = (out_bytes + 15) & ~(size_t) 15;
+  if (r->pcm_in.reserve((in_pitch ? in_pitch : 16) * r->num_streams) != cudaSuccess ||
+      r->pcm_out.reserve((out_pitch ? out_pitch : 16) * r->num_streams) != cudaSuccess) {
+    fail(ESPB_ERR_NOMEM, "resample_host: device staging");
+    return none;
+  }
+  bool single_slab_g = true;
+  if (r->policy.resampling && wc.generated > 0) {
+    single_slab_g = passes_per_slab(r->art) >= r->art->plan.n_passes();
+    if (single_slab_g && ensure_g(r->art, 0, (int) r->art->plan.chunks.size(), s0) != ESPB_OK)
+      return none;
+  }
+  cudaEventRecord(r->pipe.ready, s0);
+  const int per = pick_slab_streams(r->num_streams);
+  int slab = 0;
+  for (int st0 = 0; st0 < r->num_streams; st0 += per, ++slab) {
+    const int ns = st0 + per <= r->num_streams ? per : r->num_streams - st0;
+    cudaStream_t s = single_slab_g ? r->pipe.s[slab % HostPipe::kStreams] : s0;
+    cudaStreamWaitEvent(s, r->pipe.ready, 0);
+    if (in_bytes) {
+      e = cudaMemcpy2DAsync(r->pcm_in.as<uint8_t>() + (size_t) st0 * in_pitch, in_pitch,
+                            in + (size_t) st0 * in_stride_bytes, (size_t) in_stride_bytes, in_bytes, ns,
+                            cudaMemcpyHostToDevice, s);
+      if (e != cudaSuccess) {
+        cuda_fail(e, "h2d");
+        return none;
+      }
+    }
+    // the range helper offsets rows by s0 itself: pass the bases
+    if (wrapper_run_range(r, st0, ns, r->pcm_in.as<uint8_t>(), (int64_t) in_pitch, r->pcm_out.as<uint8_t>(),
+                          (int64_t) out_pitch, wc, output_frames_free, gain_db, s, single_slab_g) != ESPB_OK)
+      return none;
+    if (out_bytes) {
+      e = cudaMemcpy2DAsync(out + (size_t) st0 * out_stride_bytes, (size_t) out_stride_bytes,
+                            r->pcm_out.as<uint8_t>() + (size_t) st0 * out_pitch, out_pitch, out_bytes, ns,
+                            cudaMemcpyDeviceToHost, s);
+      if (e != cudaSuccess) {
+        cuda_fail(e, "d2h");
+        return none;
+      }
+    }
+    e = cudaMemcpyAsync(r->clipped_host + st0, r->clipped.as<uint32_t>() + st0, ns * sizeof(uint32_t),
+                        cudaMemcpyDeviceToHost, s);
+    if (e != cudaSuccess) {
+      cuda_fail(e, "d2h clip counts");
+      return none;
+    }
+  }
+  for (int i = 0; i < HostPipe::kStreams; ++i) {
+    e = cudaStreamSynchronize(r->pipe.s[i]);
+    if (e != cudaSuccess) {
+      cuda_fail(e, "host pipeline sync");
+      return none;
+    }
+  }
+  return wrapper_finish(r, wc, clipped_per_stream_host);
+}
+
+}  // extern "C"

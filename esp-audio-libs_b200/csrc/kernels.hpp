@@ -1,0 +1,54 @@
+// Launch wrappers for the sm_100a kernels (internal; the public boundary is include/esp_audio_b200.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#include "common.hpp"
+
+namespace espb {
+
+void count_launch();  // bumps the process-wide kernel-launch counter (api.cu)
+
+struct ResampleParams {
+  const float *in;
+  int64_t in_ss, in_cs, in_fs;  // stream / channel / frame strides, floats
+  float *out;
+  int64_t out_ss, out_cs, out_fs;
+  const float *hist;  // [n_series][taps] frames consumed before this call
+  const float *G;     // expanded coefficients, chunk-major, starting at chunk g_chunk_base
+  const ChunkEntry *chunks;
+  const int32_t *pass_chunk_begin;
+  const OutEntry *outs;
+  int n_series, channels, n_in, n_out, taps;
+  int pass_first, pass_end, passes_per_cta, g_chunk_base;
+};
+
+size_t resample_smem_bytes(int bpp);
+size_t g_chunk_floats(int bpp);
+cudaError_t launch_expand(const float *bank, const OutEntry *outs, const ChunkEntry *chunks, float *G,
+                          int chunk_first, int n_chunks, int n_out, int taps, int bpp, cudaStream_t stream);
+cudaError_t launch_resample(const ResampleParams &p, int bpp, bool exact, cudaStream_t stream);
+cudaError_t launch_history(const float *in, int64_t in_ss, int64_t in_cs, int64_t in_fs, const float *hist_old,
+                           float *hist_new, int n_series, int channels, int taps, int used, cudaStream_t stream);
+
+// quantization_utils
+cudaError_t launch_q2f(const uint8_t *in, int64_t in_row_bytes, float *out, int64_t out_row_floats, int rows,
+                       uint32_t row_samples, int bits, float gain_factor, cudaStream_t stream);
+cudaError_t launch_f2q(const float *in, int64_t in_row_floats, uint8_t *out, int64_t out_row_bytes, int rows,
+                       uint32_t row_samples, int bits, uint32_t *clipped, bool clipped_per_row, cudaStream_t stream);
+
+// art_biquad
+struct BiquadParams {
+  float a0, a1, a2, b1, b2;
+  int first_order;
+};
+cudaError_t launch_biquad(float *buf, int64_t ss, int64_t cs, int64_t fs, int channels, int n_series, int n_sections,
+                          int n_samples, BiquadParams c, float *state /* [series][section][4] */,
+                          cudaStream_t stream);
+
+// utilities
+cudaError_t launch_checksum(const uint32_t *words, uint64_t n, unsigned long long *sum_dev, cudaStream_t stream);
+cudaError_t run_fma_probe(double *tflops, double *clock_mhz);
+
+}  // namespace espb

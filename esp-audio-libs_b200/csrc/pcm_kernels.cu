@@ -1,0 +1,262 @@
+// quantization_utils on the device: packed little-endian PCM <-> float.
+//
+// Reference: src/quantization_utils.cpp:6-48 (quantized_to_float) and :50-94
+// (float_to_quantized).  Integer/byte work, HBM-bound: each thread converts four
+// samples per step with 32-bit word loads/stores (4*nbytes bytes of PCM, one 128-bit
+// float access); a scalar byte path covers unaligned buffers and row tails.
+// Bit-exact with the reference for finite inputs (float->int32 of out-of-range values
+// is undefined behaviour in the reference; here it saturates).
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "kernels.hpp"
+
+namespace espb {
+
+namespace {
+
+// ---- decode: little-endian bytes -> the reference's int32 `value` -----------------
+template <int NBYTES>
+__device__ __forceinline__ int32_t decode_bytes(const uint8_t *p) {
+  if (NBYTES == 1)
+    return (int32_t) p[0] - 128;  // :14
+  if (NBYTES == 2)
+    return (int32_t) (int16_t) ((uint32_t) p[0] | ((uint32_t) p[1] << 8));  // :21-23
+  if (NBYTES == 3)
+    return (int32_t) ((uint32_t) p[0] | ((uint32_t) p[1] << 8)) + (int32_t) (int8_t) p[2] * 65536;  // :30-33
+  // :40-44 — byte 2 is sign-extended as well as byte 3 (reference quirk, reproduced)
+  uint32_t v = (uint32_t) p[0] | ((uint32_t) p[1] << 8);
+  v += (uint32_t) ((int32_t) (int8_t) p[2] * 65536);
+  v += (uint32_t) p[3] << 24;
+  return (int32_t) v;
+}
+
+// four samples from NBYTES 32-bit words
+template <int NBYTES>
+__device__ __forceinline__ void decode_words(const uint32_t *w, int32_t v[4]) {
+  if (NBYTES == 1) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      v[i] = (int32_t) ((w[0] >> (8 * i)) & 0xffu) - 128;
+  } else if (NBYTES == 2) {
+    v[0] = (int32_t) (int16_t) (w[0] & 0xffffu);
+    v[1] = (int32_t) (int16_t) (w[0] >> 16);
+    v[2] = (int32_t) (int16_t) (w[1] & 0xffffu);
+    v[3] = (int32_t) (int16_t) (w[1] >> 16);
+  } else if (NBYTES == 3) {
+    const uint32_t s0 = w[0] & 0xffffffu;
+    const uint32_t s1 = (w[0] >> 24) | ((w[1] & 0xffffu) << 8);
+    const uint32_t s2 = (w[1] >> 16) | ((w[2] & 0xffu) << 16);
+    const uint32_t s3 = w[2] >> 8;
+    v[0] = (int32_t) (s0 << 8) >> 8;
+    v[1] = (int32_t) (s1 << 8) >> 8;
+    v[2] = (int32_t) (s2 << 8) >> 8;
+    v[3] = (int32_t) (s3 << 8) >> 8;
+  } else {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)  // sign-extending byte 2 subtracts 2^24 when it is >= 0x80
+      v[i] = (int32_t) (w[i] - ((w[i] & 0x00800000u) << 1));
+  }
+}
+
+template <int NBYTES>
+__global__ void __launch_bounds__(256)
+    espb_q2f_kernel(const uint8_t *__restrict__ in, int64_t in_row_bytes, float *__restrict__ out,
+                    int64_t out_row_floats, uint32_t n, float k, int vec_ok) {
+  const uint8_t *irow = in + (int64_t) blockIdx.y * in_row_bytes;
+  float *orow = out + (int64_t) blockIdx.y * out_row_floats;
+  const uint32_t groups = vec_ok ? n / 4 : 0;
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t g = blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += stride) {
+    const uint32_t *wp = reinterpret_cast<const uint32_t *>(irow) + (size_t) g * NBYTES;
+    uint32_t w[NBYTES];
+#pragma unroll
+    for (int i = 0; i < NBYTES; ++i)
+      w[i] = __ldg(wp + i);
+    int32_t v[4];
+    decode_words<NBYTES>(w, v);
+    float4 f;
+    f.x = __fmul_rn(__int2float_rn(v[0]), k);
+    f.y = __fmul_rn(__int2float_rn(v[1]), k);
+    f.z = __fmul_rn(__int2float_rn(v[2]), k);
+    f.w = __fmul_rn(__int2float_rn(v[3]), k);
+    reinterpret_cast<float4 *>(orow)[g] = f;
+  }
+  for (uint32_t i = groups * 4 + blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    orow[i] = __fmul_rn(__int2float_rn(decode_bytes<NBYTES>(irow + (size_t) i * NBYTES)), k);
+}
+
+// ---- encode ------------------------------------------------------------------------
+struct F2QConst {
+  float scalar;
+  int32_t offset, hi, lo;
+  int shift, bits;
+};
+
+__device__ __forceinline__ int32_t quantise_one(float x, const F2QConst &c, uint32_t &clipped) {
+  int32_t v = __float2int_rd(__fadd_rn(__fmul_rn(x, c.scalar), 0.5f));  // :61 floorf(x*scalar + 0.5f)
+  if (c.bits < 32) {                                                    // :62-69
+    if (v > c.hi) {
+      ++clipped;
+      v = c.hi;
+    } else if (v < c.lo) {
+      ++clipped;
+      v = c.lo;
+    }
+  } else {  // :70-78
+    if (x >= 1.0f) {
+      ++clipped;
+      v = c.hi;
+    } else if (x < -1.0f) {
+      ++clipped;
+      v = c.lo;
+    }
+  }
+  return (int32_t) ((uint32_t) v << c.shift) + c.offset;  // :80
+}
+
+template <int NBYTES>
+__device__ __forceinline__ void encode_words(const int32_t v[4], uint32_t *w) {
+  if (NBYTES == 1) {
+    w[0] = ((uint32_t) v[0] & 0xffu) | (((uint32_t) v[1] & 0xffu) << 8) | (((uint32_t) v[2] & 0xffu) << 16) |
+           ((uint32_t) v[3] << 24);
+  } else if (NBYTES == 2) {
+    w[0] = ((uint32_t) v[0] & 0xffffu) | ((uint32_t) v[1] << 16);
+    w[1] = ((uint32_t) v[2] & 0xffffu) | ((uint32_t) v[3] << 16);
+  } else if (NBYTES == 3) {
+    const uint32_t a = (uint32_t) v[0] & 0xffffffu, b = (uint32_t) v[1] & 0xffffffu,
+                   c = (uint32_t) v[2] & 0xffffffu, d = (uint32_t) v[3] & 0xffffffu;
+    w[0] = a | (b << 24);
+    w[1] = (b >> 8) | (c << 16);
+    w[2] = (c >> 16) | (d << 8);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      w[i] = (uint32_t) v[i];
+  }
+}
+
+template <int NBYTES>
+__global__ void __launch_bounds__(256)
+    espb_f2q_kernel(const float *__restrict__ in, int64_t in_row_floats, uint8_t *__restrict__ out,
+                    int64_t out_row_bytes, uint32_t n, F2QConst c, uint32_t *__restrict__ clipped_out,
+                    int clipped_per_row, int vec_ok) {
+  const float *irow = in + (int64_t) blockIdx.y * in_row_floats;
+  uint8_t *orow = out + (int64_t) blockIdx.y * out_row_bytes;
+  const uint32_t groups = vec_ok ? n / 4 : 0;
+  const uint32_t stride = gridDim.x * blockDim.x;
+  uint32_t clipped = 0;
+  for (uint32_t g = blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += stride) {
+    const float4 f = __ldg(reinterpret_cast<const float4 *>(irow) + g);
+    int32_t v[4];
+    v[0] = quantise_one(f.x, c, clipped);
+    v[1] = quantise_one(f.y, c, clipped);
+    v[2] = quantise_one(f.z, c, clipped);
+    v[3] = quantise_one(f.w, c, clipped);
+    uint32_t w[NBYTES];
+    encode_words<NBYTES>(v, w);
+    uint32_t *wp = reinterpret_cast<uint32_t *>(orow) + (size_t) g * NBYTES;
+#pragma unroll
+    for (int i = 0; i < NBYTES; ++i)
+      wp[i] = w[i];
+  }
+  for (uint32_t i = groups * 4 + blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const int32_t v = quantise_one(irow[i], c, clipped);
+    uint8_t *bp = orow + (size_t) i * NBYTES;
+#pragma unroll
+    for (int b = 0; b < NBYTES; ++b)
+      bp[b] = (uint8_t) ((uint32_t) v >> (8 * b));  // :80-90
+  }
+  // clip count: warp shuffle reduction, one atomic per warp
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1)
+    clipped += __shfl_xor_sync(0xffffffffu, clipped, d);
+  if ((threadIdx.x & 31) == 0 && clipped && clipped_out)
+    atomicAdd(clipped_out + (clipped_per_row ? blockIdx.y : 0), clipped);
+}
+
+inline unsigned grid_x_for(uint32_t n, int rows) {
+  // enough CTAs to cover the row once at 4 samples/thread, capped so rows*grid stays sane
+  uint64_t want = ((uint64_t) n / 4 + 255) / 256;
+  if (want < 1)
+    want = 1;
+  const uint64_t cap = rows >= 148 * 8 ? 4 : (148 * 16 + rows - 1) / rows;
+  if (want > cap)
+    want = cap;
+  return (unsigned) want;
+}
+
+}  // namespace
+
+cudaError_t launch_q2f(const uint8_t *in, int64_t in_row_bytes, float *out, int64_t out_row_floats, int rows,
+                       uint32_t row_samples, int bits, float gain_factor, cudaStream_t stream) {
+  if (rows <= 0 || row_samples == 0)
+    return cudaSuccess;
+  const int nbytes = (bits + 7) / 8;
+  const int vec_ok = ((uintptr_t) in % 4 == 0) && (in_row_bytes % 4 == 0 || rows == 1) &&
+                     ((uintptr_t) out % 16 == 0) && (out_row_floats % 4 == 0 || rows == 1);
+  dim3 grid(grid_x_for(row_samples, rows), rows);
+  switch (nbytes) {
+    case 1:
+      espb_q2f_kernel<1><<<grid, 256, 0, stream>>>(in, in_row_bytes, out, out_row_floats, row_samples, gain_factor,
+                                                  vec_ok);
+      break;
+    case 2:
+      espb_q2f_kernel<2><<<grid, 256, 0, stream>>>(in, in_row_bytes, out, out_row_floats, row_samples, gain_factor,
+                                                  vec_ok);
+      break;
+    case 3:
+      espb_q2f_kernel<3><<<grid, 256, 0, stream>>>(in, in_row_bytes, out, out_row_floats, row_samples, gain_factor,
+                                                  vec_ok);
+      break;
+    case 4:
+      espb_q2f_kernel<4><<<grid, 256, 0, stream>>>(in, in_row_bytes, out, out_row_floats, row_samples, gain_factor,
+                                                  vec_ok);
+      break;
+    default:
+      return cudaErrorInvalidValue;
+  }
+  count_launch();
+  return cudaGetLastError();
+}
+
+cudaError_t launch_f2q(const float *in, int64_t in_row_floats, uint8_t *out, int64_t out_row_bytes, int rows,
+                       uint32_t row_samples, int bits, uint32_t *clipped, bool clipped_per_row, cudaStream_t stream) {
+  if (rows <= 0 || row_samples == 0)
+    return cudaSuccess;
+  const int nbytes = (bits + 7) / 8;
+  F2QConst c;
+  c.bits = bits;
+  c.scalar = (float) ((uint64_t) 1 << bits) / 2.0f;  // :52
+  c.offset = (bits <= 8) ? 128 : 0;                   // :53
+  c.hi = (int32_t) ((1u << (bits - 1)) - 1u);         // :54
+  c.lo = ~c.hi;                                       // :55
+  c.shift = (32 - bits) % 8;                          // :56
+  const int vec_ok = ((uintptr_t) out % 4 == 0) && (out_row_bytes % 4 == 0 || rows == 1) &&
+                     ((uintptr_t) in % 16 == 0) && (in_row_floats % 4 == 0 || rows == 1);
+  dim3 grid(grid_x_for(row_samples, rows), rows);
+  switch (nbytes) {
+    case 1:
+      espb_f2q_kernel<1><<<grid, 256, 0, stream>>>(in, in_row_floats, out, out_row_bytes, row_samples, c, clipped,
+                                                  clipped_per_row, vec_ok);
+      break;
+    case 2:
+      espb_f2q_kernel<2><<<grid, 256, 0, stream>>>(in, in_row_floats, out, out_row_bytes, row_samples, c, clipped,
+                                                  clipped_per_row, vec_ok);
+      break;
+    case 3:
+      espb_f2q_kernel<3><<<grid, 256, 0, stream>>>(in, in_row_floats, out, out_row_bytes, row_samples, c, clipped,
+                                                  clipped_per_row, vec_ok);
+      break;
+    case 4:
+      espb_f2q_kernel<4><<<grid, 256, 0, stream>>>(in, in_row_floats, out, out_row_bytes, row_samples, c, clipped,
+                                                  clipped_per_row, vec_ok);
+      break;
+    default:
+      return cudaErrorInvalidValue;
+  }
+  count_launch();
+  return cudaGetLastError();
+}
+
+}  // namespace espb

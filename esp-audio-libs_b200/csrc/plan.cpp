@@ -1,0 +1,253 @@
+// Host-side planning (see plan.hpp).  Compiled with -ffp-contract=off: the reference
+// arithmetic is un-fused FP32 and the bank/schedule must match it bit for bit.
+#include "plan.hpp"
+
+#include <math.h>
+#include <stdio.h>
+
+namespace espb {
+
+bool normalise_init(int taps, int filters, float *lowpass, int *flags) {
+  if (*lowpass > 0.0f && *lowpass < 1.0f)
+    *flags |= kFlagLowpass;
+  else {
+    *flags &= ~kFlagLowpass;
+    *lowpass = 1.0f;
+  }
+  if ((taps & 3) || taps <= 0 || taps > 1024) {
+    fprintf(stderr, "must 4-1024 filter taps, and a multiple of 4!\n");
+    return false;
+  }
+  if (filters < 2 || filters > 1024) {
+    fprintf(stderr, "must be 2-1024 filters!\n");
+    return false;
+  }
+  return true;
+}
+
+namespace {
+
+// Window value at normalised distance `r` (pi at the window edge).
+inline float window_at(float r, bool blackman_harris) {
+  if (blackman_harris)
+    return 0.35875f + 0.48829f * cosf(r) + 0.14128f * cosf(2 * r) + 0.01168f * cosf(3 * r);
+  return 0.5f * (1.0f + cosf(r));
+}
+
+// One phase of the bank.  raw[] receives the un-normalised taps; row[] the final ones.
+void build_phase(float *row, float *raw, int taps, bool bh, float fraction, float lowpass) {
+  const int half = taps / 2;
+  const double pi = 3.14159265358979323846;
+  float total = 0.0f;
+  for (int t = 0; t < taps; ++t) {
+    const float rel = (float) (half - 1) + fraction - (float) t;
+    const float dist = (float) (fabs((double) rel) * pi);
+    float v = 1.0f;
+    if (dist != 0.0f) {
+      const float arg = dist * lowpass;
+      v = sinf(arg) / arg;
+      v *= window_at(dist / (float) half, bh);
+    }
+    raw[t] = v;
+    total += v;
+  }
+  // unity DC gain; rounding error of each scaled tap is fed to the next one, visiting
+  // taps centre-out: half, half-1, half+1, half-2, ...
+  const float scale = 1.0f / total;
+  float carry = 0.0f;
+  int t = half;
+  for (int visited = 0; visited < taps; ++visited) {
+    raw[t] *= scale;
+    row[t] = raw[t] - carry;
+    carry += row[t] - raw[t];
+    t = taps - t - (t >= half ? 1 : 0);
+  }
+}
+
+}  // namespace
+
+void build_filter_bank(const ArtGeometry &g, float lowpass, std::vector<float> &bank) {
+  bank.assign((size_t) (g.filters + 1) * g.taps, 0.0f);
+  std::vector<float> raw(g.taps);
+  for (int i = 0; i <= g.filters; ++i)
+    build_phase(bank.data() + (size_t) i * g.taps, raw.data(), g.taps, (g.flags & kFlagBlackmanHarris) != 0,
+                (float) i / (float) g.filters, lowpass);
+}
+
+ArtState initial_state(int taps) { return ArtState{(float) (taps / 2), taps}; }
+
+float position_of(const ArtGeometry &g, ArtState st) { return st.offset + ((float) g.taps / 2.0f) - (float) st.index; }
+
+namespace {
+
+// The signal-independent core of the reference loop.  `emit(offset, base)` is called for
+// every output with the pre-increment offset and the accumulated ring rebase.
+template <typename Emit>
+inline void run_machine(const ArtGeometry &g, ArtState &st, int n_in, int n_out, float ratio, bool stop_on_input,
+                        bool stop_on_output, unsigned *used, unsigned *generated, Emit emit) {
+  const int half = g.taps / 2, ring = g.taps * 16, drop = ring - g.taps;
+  const float step = 1.0f / ratio;
+  float off = st.offset;
+  int idx = st.index;
+  long long base = 0;
+  unsigned u = 0, gcount = 0;
+  for (;;) {
+    if (stop_on_output && n_out <= 0)
+      break;
+    if (off >= (float) (idx - half)) {
+      if (stop_on_input && n_in <= 0)
+        break;
+      if (idx == ring) {
+        off -= (float) drop;
+        idx -= drop;
+        base += drop;
+      }
+      ++idx;
+      ++u;
+      --n_in;
+    } else {
+      emit(off, base);
+      off += step;
+      ++gcount;
+      --n_out;
+    }
+  }
+  st.offset = off;
+  st.index = idx;
+  *used = u;
+  *generated = gcount;
+}
+
+}  // namespace
+
+void build_schedule(const ArtGeometry &g, ArtState start, int n_in, int n_out, float ratio, Schedule &s) {
+  s.outs.clear();
+  if (n_out > 0)
+    s.outs.reserve((size_t) n_out < (size_t) 1 << 24 ? n_out : 1 << 24);
+  const int half = g.taps / 2, idx0 = start.index;
+  const bool lowpass = (g.flags & kFlagLowpass) != 0, interp = (g.flags & kFlagInterpolate) != 0;
+  const float nf = (float) g.filters;
+  ArtState st = start;
+  run_machine(g, st, n_in, n_out, ratio, true, true, &s.used, &s.generated, [&](float off, long long base) {
+    const float fl = floorf(off);
+    float frac = off - fl;
+    OutEntry e;
+    e.ws = (int32_t) (base + (long long) (int) fl - half + 1 - idx0);
+    e.phase = 0;
+    e.w = 0.0f;
+    if (frac == 0.0f && !lowpass) {
+      e.kind = kKindPass;
+    } else if (!interp) {
+      e.kind = kKindSingle;
+      e.phase = (int) floorf(frac * nf + 0.5f);
+    } else {
+      frac *= nf;
+      const int i = (int) floorf(frac);
+      frac -= (float) i;
+      e.phase = i;
+      e.w = frac;
+      e.kind = (frac == 0.0f && !lowpass) ? kKindSingle : kKindBlend;
+    }
+    s.outs.push_back(e);
+  });
+  s.end = st;
+}
+
+unsigned required_samples(const ArtGeometry &g, ArtState st, int n_out, float ratio) {
+  unsigned used, gen;
+  run_machine(g, st, 0, n_out, ratio, false, true, &used, &gen, [](float, long long) {});
+  return used;
+}
+
+unsigned expected_output(const ArtGeometry &g, ArtState st, int n_in, float ratio) {
+  unsigned used, gen;
+  run_machine(g, st, n_in, 0, ratio, true, false, &used, &gen, [](float, long long) {});
+  return gen;
+}
+
+void build_pass_plan(const Schedule &s, int taps, int blocks_per_pass, PassPlan &p) {
+  const int opp = blocks_per_pass * kOutputsPerBlock;
+  const int n = (int) s.outs.size();
+  p.outputs_per_pass = opp;
+  p.chunks.clear();
+  p.pass_chunk_begin.clear();
+  p.pass_chunk_begin.push_back(0);
+  for (int first = 0, pass = 0; first < n; first += opp, ++pass) {
+    const int last = (first + opp < n ? first + opp : n) - 1;
+    const int j0 = s.outs[first].ws, j1 = s.outs[last].ws + taps;
+    for (int j = j0; j < j1; j += kChunkRows)
+      p.chunks.push_back(ChunkEntry{j, pass});
+    p.pass_chunk_begin.push_back((int32_t) p.chunks.size());
+  }
+}
+
+void design_lowpass(BiquadCoeffs *c, double frequency) {
+  const double pi = 3.14159265358979323846;
+  const double q = sqrt(0.5), k = tan(pi * frequency);
+  const double norm = 1.0 / (1.0 + k / q + k * k);
+  c->a0 = (float) (k * k * norm);
+  c->a1 = 2 * c->a0;
+  c->a2 = c->a0;
+  c->b1 = (float) (2.0 * (k * k - 1.0) * norm);
+  c->b2 = (float) ((1.0 - k / q + k * k) * norm);
+}
+
+void design_highpass(BiquadCoeffs *c, double frequency) {
+  const double pi = 3.14159265358979323846;
+  const double q = sqrt(0.5), k = tan(pi * frequency);
+  const double norm = 1.0 / (1.0 + k / q + k * k);
+  c->a0 = (float) norm;
+  c->a1 = (float) (-2.0 * norm);
+  c->a2 = c->a0;
+  c->b1 = (float) (2.0 * (k * k - 1.0) * norm);
+  c->b2 = (float) ((1.0 - k / q + k * k) * norm);
+}
+
+void decide_policy(float src_rate, float dst_rate, int taps, bool use_filter, bool interpolate, WrapperPolicy *p) {
+  *p = WrapperPolicy{};
+  if (src_rate == dst_rate)
+    return;
+  p->resampling = true;
+  const int flags = interpolate ? kFlagInterpolate : 0;
+  p->sample_ratio = dst_rate / src_rate;
+  if (p->sample_ratio < 1.0f) {
+    p->lowpass_ratio -= (10.24f / (float) taps);
+    if (p->lowpass_ratio < 0.84f)
+      p->lowpass_ratio = 0.84f;
+    if (p->lowpass_ratio < p->sample_ratio)
+      p->lowpass_ratio = p->sample_ratio;
+  }
+  if (p->lowpass_ratio * p->sample_ratio < 0.98f && use_filter) {
+    const float cutoff = p->lowpass_ratio * p->sample_ratio / 2.0f;
+    design_lowpass(&p->coeffs, cutoff);
+    p->pre = true;
+  }
+  if (p->lowpass_ratio / p->sample_ratio < 0.98f && use_filter && !p->pre) {
+    const float cutoff = p->lowpass_ratio / p->sample_ratio / 2.0f;
+    design_lowpass(&p->coeffs, cutoff);
+    p->post = true;
+  }
+  if (p->sample_ratio < 1.0f) {
+    p->art_lowpass = p->sample_ratio * p->lowpass_ratio;
+    p->art_flags = flags | kFlagLowpass;
+  } else if (p->lowpass_ratio < 1.0f) {
+    p->art_lowpass = p->lowpass_ratio;
+    p->art_flags = flags | kFlagLowpass;
+  } else {
+    p->art_lowpass = 1.0f;
+    p->art_flags = flags;
+  }
+}
+
+float q2f_gain_factor(int bits, float gain_db) {
+  const float gain = powf(10.0f, gain_db / 20.0f);
+  if (bits <= 8)
+    return gain / 128.0f;
+  if (bits <= 16)
+    return gain / 32768.0f;
+  if (bits <= 24)
+    return gain / 8388608.0f;
+  return gain / 2147483648.0f;
+}
+
+}  // namespace espb

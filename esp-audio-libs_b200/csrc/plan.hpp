@@ -1,0 +1,75 @@
+// Host-side planning for the B200 ART resampler path: everything that is
+// signal-independent is computed here once per call and shared by all streams.
+#pragma once
+#include <vector>
+
+#include "common.hpp"
+
+namespace espb {
+
+constexpr int kFlagInterpolate = 0x1, kFlagBlackmanHarris = 0x2, kFlagLowpass = 0x4;
+
+// Position state of a context (include/art_resampler.h:25-29: outputOffset, inputIndex).
+struct ArtState {
+  float offset;
+  int index;
+};
+
+struct ArtGeometry {
+  int taps, filters, flags;
+};
+
+// resampleInit's parameter normalisation (art_resampler.cpp:82-97).  Returns false (after
+// printing the reference's stderr line) for invalid taps / filters.
+bool normalise_init(int taps, int filters, float *lowpass, int *flags);
+
+// The (filters+1) x taps windowed-sinc bank, bit-identical to init_filter
+// (art_resampler.cpp:379-419); needs the same libm (glibc sinf/cosf) as the reference.
+void build_filter_bank(const ArtGeometry &g, float lowpass, std::vector<float> &bank);
+
+ArtState initial_state(int taps);  // art_resampler.cpp:135-136
+
+struct Schedule {
+  std::vector<OutEntry> outs;
+  unsigned used = 0, generated = 0;
+  ArtState end{};
+};
+
+// Data-free run of the resampleProcess state machine (art_resampler.cpp:172-199 /
+// :213-240) that records, per output, the window start / phase / weight / kind.
+void build_schedule(const ArtGeometry &g, ArtState start, int n_in, int n_out, float ratio, Schedule &s);
+
+unsigned required_samples(const ArtGeometry &g, ArtState st, int n_out, float ratio);  // :257-279
+unsigned expected_output(const ArtGeometry &g, ArtState st, int n_in, float ratio);    // :281-306
+float position_of(const ArtGeometry &g, ArtState st);                                   // :348
+
+// Pass / chunk tables for the kernel: pass p covers outputs [p*opp, (p+1)*opp) and
+// sweeps input rows [ws(first), ws(last)+taps) in chunks of kChunkRows.
+struct PassPlan {
+  int outputs_per_pass = 0;
+  std::vector<ChunkEntry> chunks;
+  std::vector<int32_t> pass_chunk_begin;  // n_passes + 1 prefix
+  int n_passes() const { return (int) pass_chunk_begin.size() - 1; }
+};
+void build_pass_plan(const Schedule &s, int taps, int blocks_per_pass, PassPlan &p);
+
+// art_biquad.cpp:16-38 (design in double, stored as float).
+struct BiquadCoeffs {
+  float a0, a1, a2, b1, b2;
+};
+void design_lowpass(BiquadCoeffs *c, double frequency);
+void design_highpass(BiquadCoeffs *c, double frequency);
+
+// Resampler::initialize policy (resampler.cpp:38-94).
+struct WrapperPolicy {
+  bool resampling = false, pre = false, post = false;
+  float sample_ratio = 1.0f, lowpass_ratio = 1.0f, art_lowpass = 1.0f;
+  int art_flags = 0;
+  BiquadCoeffs coeffs{};
+};
+void decide_policy(float src_rate, float dst_rate, int taps, bool use_filter, bool interpolate, WrapperPolicy *p);
+
+// quantization_utils.cpp:8,11,18,27,37 — the per-call scale factor (host powf).
+float q2f_gain_factor(int bits, float gain_db);
+
+}  // namespace espb

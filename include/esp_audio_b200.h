@@ -1,0 +1,249 @@
+/* esp_audio_b200.h — C ABI of the B200-native ART resampler path.
+ *
+ * Drop-in boundary for ONE hot path of esp-audio-libs (reference paths are relative
+ * to the reference tree): the ART polyphase sinc resampler, the art_biquad low-pass
+ * and the quantization_utils PCM conversion, batched over independent streams and
+ * executed by hand-written sm_100a kernels.  Plain pointers and sizes only; every
+ * processing call takes a CUDA stream (as void*, a cudaStream_t; NULL = default
+ * stream) and is asynchronous with respect to the host unless stated otherwise.
+ *
+ * There is no CPU fallback: every entry point that computes needs a B200-class
+ * device and fails loudly (ESPB_ERR_CUDA / NULL + message in espb_last_error())
+ * when none is usable.
+ *
+ * Batch semantics.  A batch context stands for `num_streams` independent reference
+ * contexts created with identical parameters.  All streams of a batch advance in
+ * lock-step (same frames in, same output capacity, same ratio per call), so the
+ * position schedule — which in the reference is a signal-independent FP32
+ * accumulator — is computed once per call on the host, bit-for-bit as the
+ * reference's state machine does, and shared by every stream.
+ *
+ * Buffer addressing (device memory).  A sample of (stream s, channel c, frame n) lives
+ * at   base + s*stream_stride + c*channel_stride + n*frame_stride   (units: floats).
+ *   interleaved (resampleProcessInterleaved): channel_stride = 1, frame_stride = channels
+ *   planar      (resampleProcess)           : channel_stride = frames per plane, frame_stride = 1
+ */
+#ifndef ESP_AUDIO_B200_H_
+#define ESP_AUDIO_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ESPB_ABI_VERSION 1
+
+/* flags — same bits as include/art_resampler.h:21-23 */
+#define ESPB_SUBSAMPLE_INTERPOLATE 0x1
+#define ESPB_BLACKMAN_HARRIS 0x2
+#define ESPB_INCLUDE_LOWPASS 0x4
+
+/* error codes (the reference only has NULL / false; these add the CUDA side) */
+#define ESPB_OK 0
+#define ESPB_ERR_ARG (-1)
+#define ESPB_ERR_CUDA (-2)
+#define ESPB_ERR_NOMEM (-3)
+#define ESPB_ERR_STATE (-4)
+
+/* arithmetic mode of the resampler dot products */
+#define ESPB_MODE_FAST 0  /* tap-order FFMA chain: <= 1e-6 max-abs of the reference            */
+#define ESPB_MODE_EXACT 1 /* tap-order FMUL+FADD (no contraction): bit-exact with the reference */
+
+const char *espb_last_error(void); /* thread-local message of the last failing call */
+int espb_abi_version(void);
+
+/* ---- device + buffers (the "device-buffer interface") ------------------------ */
+int espb_device_count(void);
+int espb_set_device(int device);
+int espb_device_info(int *sm_count, int *cc_major, int *cc_minor, size_t *total_mem, char *name, int name_len);
+void *espb_malloc(size_t bytes);           /* device memory, NULL on failure (like alloc_psram_fallback) */
+void espb_free(void *dptr);
+void *espb_malloc_host(size_t bytes);      /* pinned host memory */
+void espb_free_host(void *hptr);
+int espb_memcpy_h2d(void *dst, const void *src, size_t bytes, void *stream);
+int espb_memcpy_d2h(void *dst, const void *src, size_t bytes, void *stream);
+int espb_memset(void *dst, int value, size_t bytes, void *stream);
+void *espb_stream_create(void);
+void espb_stream_destroy(void *stream);
+int espb_stream_sync(void *stream);
+int espb_device_sync(void);
+/* CUDA-event timing on the launching stream */
+void *espb_event_create(void);
+void espb_event_destroy(void *ev);
+int espb_event_record(void *ev, void *stream);
+int espb_event_elapsed_ms(void *start, void *stop, float *ms); /* synchronises on `stop` */
+/* number of kernels this library has launched so far (process-wide) */
+uint64_t espb_launch_count(void);
+
+/* ---- ART resampler, batched: replaces include/art_resampler.h:35-45 ------------- */
+typedef struct EspbResampleBatch EspbResampleBatch;
+
+typedef struct { /* include/art_resampler.h:31-33 */
+  unsigned int input_used, output_generated;
+} EspbResampleResult;
+
+typedef struct {
+  int64_t stream_stride, channel_stride, frame_stride; /* in floats */
+} EspbLayout;
+
+/* resampleInit (art_resampler.cpp:78-139) for num_streams identical contexts.  Same
+ * validation and the same stderr lines; NULL on invalid taps/filters or failed alloc. */
+EspbResampleBatch *espb_resampleInit(int num_streams, int numChannels, int numTaps, int numFilters,
+                                     float lowpassRatio, int flags);
+void espb_resampleFree(EspbResampleBatch *cxt);                        /* art_resampler.cpp:353-366 */
+int espb_resampleReset(EspbResampleBatch *cxt, void *stream);          /* :144-152 */
+void espb_resampleAdvancePosition(EspbResampleBatch *cxt, float delta); /* :313-318 */
+float espb_resampleGetPosition(EspbResampleBatch *cxt);                /* :348 */
+unsigned int espb_resampleGetRequiredSamples(EspbResampleBatch *cxt, int numOutputFrames, float ratio); /* :257-279 */
+unsigned int espb_resampleGetExpectedOutput(EspbResampleBatch *cxt, int numInputFrames, float ratio);   /* :281-306 */
+int espb_resampleSetMode(EspbResampleBatch *cxt, int mode);            /* ESPB_MODE_FAST (default) / _EXACT */
+/* context introspection (tests): effective flags, state, the host-built filter bank */
+int espb_resampleGetFlags(EspbResampleBatch *cxt);
+void espb_resampleGetState(EspbResampleBatch *cxt, float *outputOffset, int *inputIndex);
+int espb_resampleCopyFilters(EspbResampleBatch *cxt, float *host_dst /* (numFilters+1)*numTaps */);
+
+/* resampleProcessInterleaved (art_resampler.cpp:208-243): every stream consumes up to
+ * numInputFrames and emits up to numOutputFrames; `in`/`out` are device pointers, rows
+ * `*_stream_stride` floats apart.  The result is the same for every stream. */
+EspbResampleResult espb_resampleProcessInterleaved(EspbResampleBatch *cxt, const float *in, int64_t in_stream_stride,
+                                                   int numInputFrames, float *out, int64_t out_stream_stride,
+                                                   int numOutputFrames, float ratio, void *stream);
+/* resampleProcess (art_resampler.cpp:167-202): planar — channel planes `*_channel_stride` floats apart. */
+EspbResampleResult espb_resampleProcess(EspbResampleBatch *cxt, const float *in, int64_t in_stream_stride,
+                                        int64_t in_channel_stride, int numInputFrames, float *out,
+                                        int64_t out_stream_stride, int64_t out_channel_stride, int numOutputFrames,
+                                        float ratio, void *stream);
+/* general form */
+EspbResampleResult espb_resampleProcessLayout(EspbResampleBatch *cxt, const float *in, const EspbLayout *in_layout,
+                                              int numInputFrames, float *out, const EspbLayout *out_layout,
+                                              int numOutputFrames, float ratio, void *stream);
+
+/* resampleProcessInterleaved with HOST buffers (pinned memory gives full PCIe speed):
+ * stream slabs are copied in, resampled and copied out on three internal CUDA streams so
+ * that H2D, compute and D2H of neighbouring slabs overlap.  Synchronous. */
+EspbResampleResult espb_resampleProcessInterleavedHost(EspbResampleBatch *cxt, const float *in,
+                                                       int64_t in_stream_stride, int numInputFrames, float *out,
+                                                       int64_t out_stream_stride, int numOutputFrames, float ratio);
+
+/* ---- art_biquad: replaces include/art_biquad.h:19-36 --------------------------- */
+typedef struct { /* include/art_biquad.h:19-21 */
+  float a0, a1, a2, b1, b2;
+} EspbBiquadCoefficients;
+
+void espb_biquad_lowpass(EspbBiquadCoefficients *filter, double frequency);  /* art_biquad.cpp:16-25 (host) */
+void espb_biquad_highpass(EspbBiquadCoefficients *filter, double frequency); /* art_biquad.cpp:29-38 (host) */
+
+/* A bank of `num_series` Biquad states (art_biquad.h:23-28) x `num_sections` cascaded
+ * sections, all sharing one coefficient set; delays live in device memory. */
+typedef struct EspbBiquadBatch EspbBiquadBatch;
+EspbBiquadBatch *espb_biquad_init(int num_series, int num_sections, const EspbBiquadCoefficients *coeffs,
+                                  float gain);                                  /* art_biquad.cpp:43-51 */
+void espb_biquad_free(EspbBiquadBatch *f);
+int espb_biquad_reset(EspbBiquadBatch *f, void *stream);
+/* biquad_apply_buffer (art_biquad.cpp:73-93) for every series: in place, sequential in
+ * time, un-fused FP32 in the reference's order (bit-exact).  Series q of the bank is
+ * (stream q / channels, channel q % channels) of the layout. */
+int espb_biquad_apply_buffer(EspbBiquadBatch *f, float *buf, const EspbLayout *layout, int channels, int num_samples,
+                             void *stream);
+int espb_biquad_get_state(EspbBiquadBatch *f, float *host_dst /* num_series*num_sections*4: in_d1,in_d2,out_d1,out_d2 */);
+
+/* ---- quantization_utils: replaces include/quantization_utils.h:15-25 ------------ */
+/* quantized_to_float (quantization_utils.cpp:6-48) on device buffers. */
+int espb_quantized_to_float(const uint8_t *in, float *out, uint64_t num_samples, uint8_t input_bits, float gain_db,
+                            void *stream);
+/* float_to_quantized (quantization_utils.cpp:50-94).  The clipped-sample count is
+ * accumulated into *clipped_dev (a device uint32 the caller zeroes), so the call stays
+ * asynchronous; espb_float_to_quantized_sync returns it like the reference does. */
+int espb_float_to_quantized(const float *in, uint8_t *out, uint64_t num_samples, uint8_t output_bits,
+                            uint32_t *clipped_dev, void *stream);
+uint32_t espb_float_to_quantized_sync(const float *in, uint8_t *out, uint64_t num_samples, uint8_t output_bits,
+                                      void *stream);
+/* row-wise variants for batches whose rows are padded: `rows` rows of `row_samples`
+ * samples, strides in bytes (input) / floats (output) and vice versa; per-row clip counts. */
+int espb_quantized_to_float_rows(const uint8_t *in, int64_t in_row_stride_bytes, float *out,
+                                 int64_t out_row_stride_floats, int rows, uint32_t row_samples, uint8_t input_bits,
+                                 float gain_db, void *stream);
+int espb_float_to_quantized_rows(const float *in, int64_t in_row_stride_floats, uint8_t *out,
+                                 int64_t out_row_stride_bytes, int rows, uint32_t row_samples, uint8_t output_bits,
+                                 uint32_t *clipped_per_row_dev, void *stream);
+
+/* ---- resampler::Resampler, batched: replaces include/resampler.h:15-80 ------------ */
+typedef struct { /* include/resampler.h:22-32 */
+  float source_sample_rate;
+  float target_sample_rate;
+  uint8_t source_bits_per_sample;
+  uint8_t target_bits_per_sample;
+  uint8_t channels;
+  uint8_t use_pre_or_post_filter; /* bool */
+  uint8_t subsample_interpolate;  /* bool */
+  uint16_t number_of_taps;
+  uint16_t number_of_filters;
+} EspbResamplerConfiguration;
+
+typedef struct { /* include/resampler.h:15-20; clipped_samples is the batch total */
+  size_t frames_used;
+  size_t frames_generated;
+  size_t predicted_frames_used;
+  uint64_t clipped_samples;
+} EspbResamplerResults;
+
+typedef struct EspbResampler EspbResampler;
+/* Resampler(input_buffer_samples, output_buffer_samples) + initialize(config)
+ * (resampler.cpp:21-98), for num_streams streams.  NULL where the reference returns false.
+ * Unlike the reference (lowpass_[2][2], include/resampler.h:64) any channel count works. */
+EspbResampler *espb_resampler_create(int num_streams, size_t input_buffer_samples, size_t output_buffer_samples,
+                                     const EspbResamplerConfiguration *config);
+void espb_resampler_free(EspbResampler *r);
+int espb_resampler_set_mode(EspbResampler *r, int mode);
+/* policy introspection: 0 none / 1 pre / 2 post; coefficients; ART low-pass and flags */
+int espb_resampler_policy(EspbResampler *r, EspbBiquadCoefficients *coeffs, float *sample_ratio, float *art_lowpass,
+                          int *art_flags);
+/* Resampler::resample (resampler.cpp:100-160) on DEVICE buffers: row s of `in` holds
+ * stream s's packed PCM (rows in_stride_bytes apart), likewise `out`.  Synchronises the
+ * stream before returning (the clip count is part of the result, as in the reference).
+ * clipped_per_stream_host may be NULL, else receives num_streams counts. */
+EspbResamplerResults espb_resampler_resample(EspbResampler *r, const uint8_t *in, int64_t in_stride_bytes,
+                                             uint8_t *out, int64_t out_stride_bytes, size_t input_frames_available,
+                                             size_t output_frames_free, float gain_db,
+                                             uint32_t *clipped_per_stream_host, void *stream);
+/* Same call with HOST buffers: stages through pinned memory, copies host->device,
+ * processes, copies device->host; stream slabs are pipelined over internal CUDA streams. */
+EspbResamplerResults espb_resampler_resample_host(EspbResampler *r, const uint8_t *in, int64_t in_stride_bytes,
+                                                  uint8_t *out, int64_t out_stride_bytes,
+                                                  size_t input_frames_available, size_t output_frames_free,
+                                                  float gain_db, uint32_t *clipped_per_stream_host);
+
+/* ---- host-side planning (no device needed) ------------------------------------------ */
+/* The signal-independent parts of the path, exposed for callers that want to size
+ * buffers ahead of time and for CPU-only verification of the host logic.
+ * espb_plan_filter_bank: the (numFilters+1) x numTaps bank of init_filter
+ * (art_resampler.cpp:379-419) after resampleInit's flag normalisation (:82-87). */
+int espb_plan_filter_bank(int numTaps, int numFilters, float lowpassRatio, int flags, float *host_dst,
+                          int *effective_flags);
+/* Data-free run of the resampleProcess state machine (art_resampler.cpp:172-199) from an
+ * explicit (outputOffset, inputIndex): counts, end state and, when the arrays are not
+ * NULL (numOutputFrames entries each), per output the window start relative to the first
+ * input frame of the call, the filter phase, the blend weight and the kind
+ * (1 pass-through, 2 single dot product, 3 blend). */
+int espb_plan_schedule(int numTaps, int numFilters, int flags, float outputOffset, int inputIndex,
+                       int numInputFrames, int numOutputFrames, float ratio, unsigned int *input_used,
+                       unsigned int *output_generated, float *end_outputOffset, int *end_inputIndex,
+                       int32_t *window_start, int32_t *phase, float *weight, int32_t *kind);
+/* Resampler::initialize's decisions (resampler.cpp:38-94) without creating anything:
+ * returns 0 none / 1 pre / 2 post filter. */
+int espb_plan_policy(const EspbResamplerConfiguration *config, EspbBiquadCoefficients *coeffs, float *sample_ratio,
+                     float *art_lowpass, int *art_flags);
+
+/* ---- batch utilities -------------------------------------------------------------- */
+/* Order-independent checksum of a float/byte buffer: wrapping 64-bit sum of the 32-bit
+ * words (bytes for the u8 variant) — what each rank contributes to the NCCL gather. */
+int espb_checksum_u32(const void *buf, uint64_t num_words, uint64_t *sum_dev, void *stream);
+/* FFMA-only probe: achieved FP32 TFLOP/s of this device right now (roofline denominator). */
+int espb_measure_fp32_fma_peak(double *tflops, double *sm_clock_mhz_estimate);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ESP_AUDIO_B200_H_ */

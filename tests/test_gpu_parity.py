@@ -1,0 +1,380 @@
+"""Parity tests proper: the CUDA path, called through the C ABI, against the CPU oracle and the
+golden fixtures from the unmodified reference.  Integer/byte work is bit-exact; the FP32
+resampler is bit-exact in exact mode and within 1e-6 max-abs full scale in fast mode
+(the tolerance BASELINE.json states); the biquad is bit-exact."""
+import numpy as np
+import pytest
+from conftest import bits_equal
+from oracle_lib import multitone, noise
+
+import esp_audio_libs_b200 as espb
+
+pytestmark = pytest.mark.gpu
+f32 = np.float32
+TOL = 1e-6  # BASELINE.json north_star: max-abs error of 1e-6 full scale for the FP32 resampler
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _device():
+    assert espb.device_count() > 0, "GPU tests need a GPU: the product has no CPU path"
+    espb.set_device(0)
+    info = espb.device_info()
+    assert info["cc"][0] == 10, f"built for sm_100a, found {info}"
+
+
+def oracle_rows(oracle, x, channels, taps, filters, lowpass, flags, adv, cap, ratio):
+    ys = []
+    res = None
+    for row in x:
+        o = oracle.resampler(channels, taps, filters, lowpass, flags)
+        if adv:
+            o.advance(adv)
+        y, u, g = o.process_interleaved(row, cap, ratio)
+        ys.append(y)
+        res = (u, g)
+    return np.stack(ys), res
+
+
+# ---------------------------------------------------------------- quantisers
+@pytest.mark.parametrize("bits", [1, 5, 8, 9, 12, 16, 17, 20, 24, 25, 31, 32])
+def test_quantisers_bit_exact(oracle, bits):
+    rng = np.random.default_rng(bits)
+    nb = (bits + 7) // 8
+    for n in (0, 1, 3, 4, 5, 1023, 4096, 100003):
+        raw = rng.integers(0, 256, size=max(n * nb, 1), dtype=np.uint8)
+        for gain in (0.0, -7.25):
+            a = espb.quantized_to_float(raw, n, bits, gain)
+            b = oracle.quantized_to_float(raw, n, bits, gain) if n else np.zeros(0, f32)
+            assert bits_equal(a, b), (bits, n, gain)
+        x = (rng.random(n) * 2.6 - 1.3).astype(f32)
+        if n >= 12:
+            x[:12] = [0, 1, -1, 0.5 / 32768, -0.5 / 32768, 1.5 / 32768, np.nextafter(f32(1), f32(0)), -1.0000001,
+                      0.99999, -0.99999, 1e-9, -1e-9]
+        qa, ca = espb.float_to_quantized(x, bits)
+        qb, cb = oracle.float_to_quantized(x, bits) if n else (np.zeros(0, np.uint8), 0)
+        assert ca == cb and bits_equal(qa, qb), (bits, n)
+
+
+def test_quantisers_golden(golden):
+    arrays, meta = golden
+    for q in meta["quant"]:
+        bits = q["bits"]
+        for gain in (0.0, -6.5):
+            assert bits_equal(espb.quantized_to_float(arrays[f"q2f_{bits}_raw"], 4096, bits, gain),
+                              arrays[f"q2f_{bits}_{gain}"])
+        out, clipped = espb.float_to_quantized(arrays[f"f2q_{bits}_x"], bits)
+        assert clipped == q["clipped"] and bits_equal(out, arrays[f"f2q_{bits}_q"])
+    out, clipped = espb.float_to_quantized(np.array([0, 1, -1, 0.5 / 32768, -0.5 / 32768, 1.5 / 32768], f32), 16)
+    assert list(out.view(np.int16)) == [0, 32767, -32768, 1, 0, 2] and clipped == 1
+    assert float(espb.quantized_to_float(np.array([0, 0, 0x80, 1], np.uint8), 1, 32)[0]) == 0.00390625
+
+
+def test_quantiser_unaligned_buffers(oracle):
+    # the reference reads byte-wise with no alignment assumption: offset device pointers by 1..3 bytes
+    rng = np.random.default_rng(12)
+    L = espb.lib()
+    for bits in (16, 24, 32):
+        nb = (bits + 7) // 8
+        n = 5001
+        raw = rng.integers(0, 256, size=n * nb + 8, dtype=np.uint8)
+        d_in = espb.DeviceBuffer.from_numpy(raw)
+        d_out = espb.DeviceBuffer((n + 4) * 4)
+        for off in (1, 2, 3):
+            assert L.espb_quantized_to_float(d_in.ptr + off, d_out.ptr + 4, n, bits, 0.0, None) == 0
+            got = d_out.download(f32)[1:n + 1]
+            assert bits_equal(got, oracle.quantized_to_float(raw[off:], n, bits, 0.0)), (bits, off)
+
+
+# ---------------------------------------------------------------- biquad
+@pytest.mark.parametrize("channels,streams", [(1, 70), (2, 37), (3, 11), (8, 5)])
+def test_biquad_bit_exact(oracle, channels, streams):
+    n = 3000
+    x = np.stack([noise(n, channels, stream=s, amp=0.9) for s in range(streams)])
+    for f, gain, sections in ((0.2274, 1.0, 2), (1.0 / 6.0, 1.0, 2), (0.441, 0.5, 1), (0.02, 1.0, 3)):
+        c = espb.biquad_lowpass(f)
+        assert bits_equal(c, oracle.biquad_lowpass(f))
+        bq = espb.BiquadBatch(streams * channels, sections, c, gain)
+        # two calls: state carries across calls exactly like the reference's Biquad struct
+        y1 = bq.apply_interleaved(x[:, : 1234 * channels], channels)
+        y2 = bq.apply_interleaved(x[:, 1234 * channels:], channels)
+        y = np.concatenate([y1, y2], axis=1)
+        for s in range(streams):
+            ref = x[s].copy()
+            for ch in range(channels):
+                for _ in range(sections):
+                    oracle.biquad(c, gain).apply_buffer(ref[ch:], channels, n=n)
+            assert bits_equal(y[s], ref), (channels, s, f)
+        bq.free()
+
+
+def test_biquad_first_order_and_highpass(oracle, golden):
+    arrays, _ = golden
+    x = arrays["biquad_x"][:2000].copy().reshape(1, -1)
+    bq = espb.BiquadBatch(1, 1, arrays["biquad_fo_c"], 1.0)
+    assert bits_equal(bq.apply_interleaved(x, 1)[0], arrays["biquad_fo_y"])
+    c = espb.biquad_highpass(0.1)
+    assert bits_equal(c, oracle.biquad_highpass(0.1))
+    xs = np.stack([noise(2500, 2, stream=s) for s in range(9)])
+    y = espb.BiquadBatch(18, 2, c, 2.0).apply_interleaved(xs, 2)
+    for s in range(9):
+        ref = xs[s].copy()
+        for ch in range(2):
+            for _ in range(2):
+                oracle.biquad(c, 2.0).apply_buffer(ref[ch:], 2, n=2500)
+        assert bits_equal(y[s], ref)
+
+
+def test_biquad_golden(golden):
+    arrays, meta = golden
+    x = arrays["biquad_x"].reshape(1, -1)
+    for k, b in enumerate(meta["biquad"]):
+        bq = espb.BiquadBatch(2, 2, arrays[f"biquad_{k}_c"], b["gain"])
+        assert bits_equal(bq.apply_interleaved(x, 2)[0], arrays[f"biquad_{k}_y"]), b
+
+
+# ---------------------------------------------------------------- resampler
+def test_resampler_golden_small_cases(golden):
+    arrays, meta = golden
+    for c in meta["small"]:
+        x = arrays[f"small_{c['name']}_x"]
+        ns = 3
+        xb = np.stack([x] * ns)
+        for mode in (espb.MODE_EXACT, espb.MODE_FAST):
+            b = espb.ResampleBatch(ns, c["channels"], c["taps"], c["filters"], c["lowpass"], c["flags"], mode=mode)
+            if c["advance"]:
+                b.advance(c["advance"])
+            y, used, gen = b.process_interleaved(xb, c["cap"], f32(c["ratio"]))
+            assert (used, gen) == (c["used"], c["generated"]), c["name"]
+            off, idx = b.state()
+            assert (float(off), idx) == (c["final_offset"], c["final_index"]) and b.position() == c["position"]
+            ref = arrays[f"small_{c['name']}_y"]
+            for s in range(ns):
+                if mode == espb.MODE_EXACT:
+                    assert bits_equal(y[s], ref), c["name"]
+                else:
+                    assert np.max(np.abs(y[s].astype(np.float64) - ref)) <= TOL, c["name"]
+            b.free()
+
+
+@pytest.mark.parametrize("case", [
+    # channels, streams, taps, filters, lowpass, flags, ratio, n_in   (series counts straddle the 128-series CTA groups)
+    (2, 70, 256, 256, 1.0, 3, f32(48000) / f32(44100), 2500),
+    (2, 65, 256, 256, float(f32(44100) / f32(48000) * f32(0.96)), 1, f32(44100) / f32(48000), 2500),
+    (1, 131, 256, 256, 1.0, 1, f32(3.0), 900),
+    (8, 17, 1024, 256, 0.45, 1, f32(44100) / f32(96000), 3000),
+    (3, 45, 32, 16, 1.0, 0, f32(1.37), 1500),
+    (1, 1, 4, 2, 1.0, 3, f32(2.5), 300),
+    (5, 30, 64, 1024, 0.7, 2, f32(0.61), 2000),
+])
+def test_resampler_vs_oracle(oracle, case):
+    ch, ns, taps, filters, lp, flags, ratio, n_in = case
+    x = np.stack([noise(n_in, ch, stream=s, amp=0.9) for s in range(ns)])
+    cap = int(n_in * float(ratio)) + 40
+    ref, (uo, go) = oracle_rows(oracle, x, ch, taps, filters, lp, flags, taps / 2, cap, ratio)
+    for mode in (espb.MODE_EXACT, espb.MODE_FAST):
+        b = espb.ResampleBatch(ns, ch, taps, filters, lp, flags, mode=mode)
+        b.advance(taps / 2)
+        assert bits_equal(b.bank(), oracle.resampler(1, taps, filters, lp, flags).bank())
+        y, used, gen = b.process_interleaved(x, cap, ratio)
+        assert (used, gen) == (uo, go)
+        if mode == espb.MODE_EXACT:
+            assert bits_equal(y, ref)
+        else:
+            assert np.max(np.abs(y.astype(np.float64) - ref)) <= TOL
+        b.free()
+
+
+def test_resampler_high_amplitude_fast_mode_tolerance(oracle):
+    # SURVEY §8a R5 stress case: amplitude 0.9 noise and multitone, T=256 and T=1024
+    for taps, ch, ratio, lp in ((256, 2, f32(48000) / f32(44100), 1.0), (1024, 2, f32(44100) / f32(96000), 0.45)):
+        x = np.stack([noise(6000, ch, stream=1, amp=0.9), multitone(6000, ch, 44100.0, stream=2, amp=0.9)])
+        cap = int(6000 * float(ratio)) + 40
+        ref, _ = oracle_rows(oracle, x, ch, taps, 256, lp, 3, taps / 2, cap, ratio)
+        b = espb.ResampleBatch(2, ch, taps, 256, lp, 3)
+        b.advance(taps / 2)
+        y, _, _ = b.process_interleaved(x, cap, ratio)
+        err = float(np.max(np.abs(y.astype(np.float64) - ref)))
+        assert err <= TOL, (taps, err)
+
+
+def test_resampler_chunked_streaming_is_bit_identical(oracle, golden):
+    arrays, meta = golden
+    m = meta["chunked"]
+    x, plan, ch = arrays["chunked_x"], arrays["chunked_plan"], m["channels"]
+    ns = 4
+    b = espb.ResampleBatch(ns, ch, m["taps"], m["filters"], 1.0, m["flags"], mode=espb.MODE_EXACT)
+    b.advance(m["advance"])
+    outs, pos = [], 0
+    for n_in, n_out, used, gen in plan:
+        seg = np.stack([x[pos * ch:(pos + int(n_in)) * ch]] * ns)
+        assert b.required(int(n_out), f32(m["ratio"])) >= 0
+        y, u, g = b.process_interleaved(seg.reshape(ns, -1), int(n_out), f32(m["ratio"]), n_in=int(n_in))
+        assert (u, g) == (used, gen)
+        outs.append(y)
+        pos += u
+    y = np.concatenate(outs, axis=1)
+    for s in range(ns):
+        assert bits_equal(y[s], arrays["chunked_y"])
+    # reset returns to the initial state and output
+    b.reset()
+    b.advance(m["advance"])
+    y2, _, _ = b.process_interleaved(np.stack([x] * ns), y.shape[1] // ch, f32(m["ratio"]))
+    assert bits_equal(y2[0], arrays["chunked_y"])
+
+
+def test_resampler_empty_and_capacity_limited_calls(oracle):
+    ch, taps = 2, 64
+    ratio = f32(1.5)
+    x = np.stack([noise(500, ch, stream=s) for s in range(3)])
+    b = espb.ResampleBatch(3, ch, taps, 64, 1.0, 3, mode=espb.MODE_EXACT)
+    o = [oracle.resampler(ch, taps, 64, 1.0, 3) for _ in range(3)]
+    # no input, no output space
+    assert b.process_interleaved(np.zeros((3, 0), f32), 0, ratio, n_in=0)[1:] == (0, 0)
+    # no input but output space: the initial half-window of silence can be emitted
+    y, u, g = b.process_interleaved(np.zeros((3, 0), f32), 100, ratio, n_in=0)
+    yo, uo, go = o[0].process_interleaved(np.zeros(0, f32), 100, ratio, n_in=0)
+    for k in (1, 2):
+        o[k].process_interleaved(np.zeros(0, f32), 100, ratio, n_in=0)
+    assert (u, g) == (uo, go) and bits_equal(y[0], yo)
+    # output capacity smaller than what the input could produce
+    y, u, g = b.process_interleaved(x, 37, ratio)
+    for k in range(3):
+        yo, uo, go = o[k].process_interleaved(x[k], 37, ratio)
+        assert (u, g) == (uo, go) and bits_equal(y[k], yo)
+    # the rest of that input after the capacity-limited call
+    y, u2, g2 = b.process_interleaved(x[:, u * ch:], 2000, ratio)
+    for k in range(3):
+        yo, uo, go = o[k].process_interleaved(x[k][u * ch:], 2000, ratio)
+        assert (u2, g2) == (uo, go) and bits_equal(y[k], yo)
+    assert b.state() == o[0].state()
+
+
+def test_resampler_planar(golden):
+    arrays, meta = golden
+    m = meta["planar"]
+    b = espb.ResampleBatch(2, m["channels"], m["taps"], m["filters"], 1.0, m["flags"], mode=espb.MODE_EXACT)
+    y, used, gen = b.process_planar(np.stack([arrays["planar_x"]] * 2), 800, f32(m["ratio"]))
+    assert (used, gen) == (m["used"], m["generated"])
+    assert bits_equal(y[0], arrays["planar_y"]) and bits_equal(y[1], arrays["planar_y"])
+
+
+def test_resampler_host_buffer_path(oracle):
+    ch, taps, ns, n_in = 2, 64, 50, 1500
+    ratio = f32(48000) / f32(44100)
+    x = np.stack([noise(n_in, ch, stream=s) for s in range(ns)])
+    cap = int(n_in * float(ratio)) + 20
+    hin = espb.PinnedBuffer(x.size, f32)
+    hin.array[:] = x.reshape(-1)
+    hout = espb.PinnedBuffer(ns * cap * ch, f32)
+    hout.array[:] = 0
+    b = espb.ResampleBatch(ns, ch, taps, 64, 1.0, 3, mode=espb.MODE_EXACT)
+    b.advance(taps / 2)
+    used, gen = b.process_interleaved_host(hin.ptr, n_in * ch, n_in, hout.ptr, cap * ch, cap, ratio)
+    ref, (uo, go) = oracle_rows(oracle, x, ch, taps, 64, 1.0, 3, taps / 2, cap, ratio)
+    assert (used, gen) == (uo, go)
+    got = hout.array.reshape(ns, cap * ch)[:, : gen * ch]
+    assert bits_equal(np.ascontiguousarray(got), ref)
+
+
+def test_invalid_init_returns_null():
+    for taps, filters in ((30, 16), (0, 16), (1028, 16), (32, 1), (32, 1025)):
+        with pytest.raises(espb.EspbError):
+            espb.ResampleBatch(1, 1, taps, filters, 1.0, 0)
+
+
+# ---------------------------------------------------------------- wrapper, end to end
+def test_wrapper_golden(golden):
+    arrays, meta = golden
+    for k, m in enumerate(meta["wrapper"]):
+        chn, nb = m["channels"], (m["src_bits"] + 7) // 8
+        ns = 3
+        r = espb.Resampler(ns, 1024 * chn, 4096 * chn, m["src_rate"], m["dst_rate"], m["src_bits"], m["dst_bits"],
+                           chn, m["use_filter"], m["interpolate"], m["taps"], m["filters"], mode=espb.MODE_EXACT)
+        raw, outs, res = arrays[f"wrap_{k}_raw"], [], []
+        for it in range(3):
+            seg = raw[it * 1024 * chn * nb:(it + 1) * 1024 * chn * nb]
+            y, rr = r.resample(np.stack([seg] * ns), 1024, m["out_free"][it], m["gain_db"], host_path=(it == 2))
+            outs.append(y)
+            res.append([rr["frames_used"], rr["frames_generated"], rr["predicted_frames_used"],
+                        int(rr["clipped_per_stream"][1])])
+            assert rr["clipped_samples"] == ns * int(rr["clipped_per_stream"][0])
+        assert np.array_equal(np.array(res, np.int64), arrays[f"wrap_{k}_res"]), m
+        y = np.concatenate(outs, axis=1)
+        for s in range(ns):
+            assert bits_equal(y[s], arrays[f"wrap_{k}_y"]), (m, s)
+        r.free()
+
+
+@pytest.mark.parametrize("cfg", [
+    # src_rate, dst_rate, src_bits, dst_bits, channels, streams  (C3- and C4-like paths)
+    (16000, 48000, 16, 16, 1, 133),
+    (96000, 44100, 24, 24, 2, 20),
+    (48000, 44100, 32, 16, 2, 40),
+])
+def test_wrapper_vs_oracle_fast_mode_within_one_lsb(oracle, cfg):
+    sr, dr, sb, db, ch, ns = cfg
+    nb = (sb + 7) // 8
+    frames = 2048
+    rng = np.random.default_rng(sr + db)
+    pcm = (rng.normal(0, 0.3, size=(ns, frames * ch)).clip(-1, 0.99999) * (2 ** (8 * nb - 1))).astype(np.int64)
+    raw = np.zeros((ns, frames * ch * nb), np.uint8)
+    for b in range(nb):
+        raw[:, b::nb] = (pcm >> (8 * b)) & 0xFF
+    cap = int(frames * dr / sr) + 64
+    for mode in (espb.MODE_EXACT, espb.MODE_FAST):
+        r = espb.Resampler(ns, frames * ch, cap * ch, sr, dr, sb, db, ch, True, True, 256, 256, mode=mode)
+        out, res = r.resample(raw, frames, cap, -1.5)
+        ob = (db + 7) // 8
+        for s in range(0, ns, 7):
+            w = oracle.wrapper(frames * ch, cap * ch, float(sr), float(dr), sb, db, ch, True, True, 256, 256)
+            yo, ro = w.resample(raw[s], frames, cap, -1.5)
+            assert res["frames_generated"] == ro["frames_generated"] and res["frames_used"] == ro["frames_used"]
+            if mode == espb.MODE_EXACT:
+                assert bits_equal(out[s], yo)
+                assert int(res["clipped_per_stream"][s]) == ro["clipped_samples"]
+            else:
+                a = _le_to_int(out[s], ob)
+                bb = _le_to_int(yo, ob)
+                assert np.max(np.abs(a - bb)) <= (1 << ((32 - db) % 8)), (cfg, s)
+        r.free()
+
+
+def _le_to_int(bytes_, nb):
+    b = bytes_.reshape(-1, nb).astype(np.int64)
+    v = np.zeros(b.shape[0], np.int64)
+    for k in range(nb):
+        v |= b[:, k] << (8 * k)
+    sign = 1 << (8 * nb - 1)
+    return (v ^ sign) - sign
+
+
+# ---------------------------------------------------------------- full-size properties (BASELINE configs[1])
+def test_full_size_batch_properties(oracle):
+    """4096 stereo streams, 256 taps, 44.1 -> 48 kHz (0.25 s each to keep the test short): every stream
+    with the same input gives the same output (a checksum of checksums), sampled streams match the
+    oracle, and the device checksum equals the host's."""
+    ns, ch, taps, n_in = 4096, 2, 256, 11025
+    ratio = f32(48000) / f32(44100)
+    base = [noise(n_in, ch, stream=s, amp=0.5) for s in range(8)]
+    x = np.stack([base[s % 8] for s in range(ns)])
+    cap = int(n_in * float(ratio)) + 16
+    b = espb.ResampleBatch(ns, ch, taps, 256, 1.0, 3)
+    b.advance(taps / 2)
+    d_in = espb.DeviceBuffer.from_numpy(x)
+    d_out = espb.DeviceBuffer(ns * cap * ch * 4)
+    d_out.zero()
+    used, gen = b.process_interleaved_dev(d_in.ptr, n_in * ch, n_in, d_out.ptr, cap * ch, cap, ratio)
+    y = d_out.download(f32).reshape(ns, cap * ch)
+    dev_sum = espb.checksum_u32(d_out.ptr, ns * cap * ch)
+    assert dev_sum == int(y.view(np.uint32).astype(np.uint64).sum() & np.uint64(0xFFFFFFFFFFFFFFFF))
+    o = oracle.resampler(ch, taps, 256, 1.0, 3)
+    o.advance(taps / 2)
+    assert gen == o.expected(n_in, ratio) and used == n_in
+    sums = y[:, : gen * ch].view(np.uint32).astype(np.uint64).sum(axis=1)
+    for s in range(8):
+        assert np.all(sums[s::8] == sums[s])  # identical inputs -> identical outputs, wherever they sit in the batch
+        oo = oracle.resampler(ch, taps, 256, 1.0, 3)
+        oo.advance(taps / 2)
+        yo, _, _ = oo.process_interleaved(base[s], cap, ratio)
+        assert np.max(np.abs(y[s, : gen * ch].astype(np.float64) - yo)) <= TOL
+    assert np.all(y[:, gen * ch:] == 0)  # nothing written past the generated frames

@@ -1,0 +1,169 @@
+"""Host-side logic of the product (no GPU): the C-ABI library loads and exports every
+declared symbol, and its planning code (filter bank, position schedule, wrapper policy)
+matches the golden fixtures made from the unmodified reference.  The schedule is
+additionally proven by replaying it in numpy with the kernel's arithmetic (one
+accumulator per dot product, taps in order, FMUL+FADD) against the golden outputs."""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+from conftest import bits_equal
+
+import esp_audio_libs_b200 as espb
+
+f32 = np.float32
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    L = espb.lib()
+    names = espb.declared_symbols()
+    assert len(names) >= 50
+    missing = [n for n in names if not hasattr(L, n)]
+    assert not missing, missing
+    assert L.espb_abi_version() == 1
+    assert os.path.basename(espb.library_path()) == "libesp_audio_b200.so"
+
+
+def test_no_cpu_fallback_fails_loudly():
+    if espb.device_count() > 0:
+        pytest.skip("a GPU is present")
+    with pytest.raises(espb.EspbError, match="no CUDA device"):
+        espb.ResampleBatch(2, 2, 64, 64, 1.0, 3)
+    with pytest.raises(espb.EspbError):
+        espb.BiquadBatch(4, 2, espb.biquad_lowpass(0.2))
+    with pytest.raises(espb.EspbError):
+        espb.Resampler(2, 1024, 4096, 44100, 48000, 16, 16, 2)
+
+
+def test_invalid_init_parameters():
+    assert espb.plan_filter_bank(30, 16, 1.0, 0) is None
+    assert espb.plan_filter_bank(0, 16, 1.0, 0) is None
+    assert espb.plan_filter_bank(1028, 16, 1.0, 0) is None
+    assert espb.plan_filter_bank(32, 1, 1.0, 0) is None
+    assert espb.plan_filter_bank(32, 1025, 1.0, 0) is None
+
+
+def test_filter_bank_matches_reference(golden):
+    arrays, meta = golden
+    for k, b in enumerate(meta["banks"]):
+        bank, eff = espb.plan_filter_bank(b["taps"], b["filters"], b["lowpass"], b["flags"])
+        assert eff == b["eff_flags"]
+        assert sha(bank) == b["sha256"], b
+        if f"bank{k}" in arrays:
+            assert bits_equal(bank, arrays[f"bank{k}"])
+
+
+def test_schedule_counts_and_state_match_reference(golden):
+    _, meta = golden
+    for c in meta["large"] + meta["small"]:
+        taps = c["taps"]
+        adv = c.get("advance", taps / 2)
+        off = f32(f32(taps // 2) + f32(adv))
+        s = espb.plan_schedule(taps, c["filters"], _eff_flags(c), off, taps, c["n_in"], c["cap"], f32(c["ratio"]),
+                               want_entries=False)
+        assert (s["used"], s["generated"]) == (c["used"], c["generated"]), c["name"]
+        assert (float(s["end_offset"]), s["end_index"]) == (c["final_offset"], c["final_index"]), c["name"]
+
+
+def _eff_flags(c):
+    fl = c["flags"]
+    return (fl | 4) if 0.0 < c["lowpass"] < 1.0 else (fl & ~4)
+
+
+def replay(bank, sched, x, channels, taps):
+    """out[n, c] from the schedule with the kernel's arithmetic: for k in taps: acc = acc + h[k]*x[ws+k]."""
+    n = sched["generated"]
+    xin = np.ascontiguousarray(x, f32).reshape(-1, channels)
+    xpad = np.concatenate([np.zeros((taps, channels), f32), xin, np.zeros((taps, channels), f32)])
+    ws = sched["ws"].astype(np.int64) + taps
+    out = np.zeros((n, channels), f32)
+    acc1 = np.zeros((n, channels), f32)
+    acc2 = np.zeros((n, channels), f32)
+    h1 = bank[sched["phase"]]
+    h2 = bank[np.minimum(sched["phase"] + 1, bank.shape[0] - 1)]
+    for k in range(taps):
+        xs = xpad[ws + k]
+        acc1 = acc1 + (h1[:, k:k + 1] * xs).astype(f32)
+        acc2 = acc2 + (h2[:, k:k + 1] * xs).astype(f32)
+    w = sched["w"][:, None]
+    blend = (acc2 * w).astype(f32) + (acc1 * (f32(1.0) - w)).astype(f32)
+    kind = sched["kind"][:, None]
+    passthrough = xpad[ws + taps // 2 - 1]
+    out = np.where(kind == 3, blend, np.where(kind == 2, acc1, passthrough)).astype(f32)
+    return out.reshape(-1)
+
+
+def test_schedule_replay_is_bit_exact(golden):
+    arrays, meta = golden
+    for c in meta["small"]:
+        taps = c["taps"]
+        bank, eff = espb.plan_filter_bank(taps, c["filters"], c["lowpass"], c["flags"])
+        off = f32(f32(taps // 2) + f32(c["advance"]))
+        s = espb.plan_schedule(taps, c["filters"], eff, off, taps, c["n_in"], c["cap"], f32(c["ratio"]))
+        y = replay(bank, s, arrays[f"small_{c['name']}_x"], c["channels"], taps)
+        assert bits_equal(y, arrays[f"small_{c['name']}_y"]), c["name"]
+        assert np.all(np.diff(s["ws"]) >= 0)
+        assert s["ws"].min() >= -taps
+
+
+def test_schedule_kinds(golden):
+    # KAT: over C1's 479880 outputs the fractional offset is exactly 0 for 93 and the blend weight 0 for 24139
+    s = espb.plan_schedule(256, 256, 3, f32(256.0), 256, 441000, 480016, f32(48000) / f32(44100))
+    assert s["generated"] == 479880
+    assert int((s["kind"] == 1).sum()) == 93
+    assert int((s["kind"] == 2).sum()) == 24139
+    # with the low-pass on there are no shortcuts
+    s = espb.plan_schedule(256, 256, 5, f32(256.0), 256, 48000, 48000, f32(44100) / f32(48000))
+    assert set(np.unique(s["kind"])) == {3}
+    # non-interpolating: nearest phase may equal numFilters
+    s = espb.plan_schedule(32, 16, 0, f32(16.0), 32, 5000, 8000, f32(1.37))
+    assert set(np.unique(s["kind"])) <= {1, 2} and s["phase"].max() == 16
+
+
+def test_required_and_expected_follow_the_oracle(oracle):
+    rng = np.random.default_rng(8)
+    for _ in range(30):
+        taps = int(rng.choice([4, 16, 64, 256, 1024]))
+        ratio = f32(rng.uniform(0.3, 3.2))
+        n = int(rng.integers(0, 5000))
+        ctx = oracle.resampler(1, taps, 32, 1.0, 3)
+        adv = float(rng.choice([0.0, taps / 2, 1.75]))
+        ctx.advance(adv)
+        off, idx = ctx.state()
+        s = espb.plan_schedule(taps, 32, 3, off, idx, n, 10 ** 7, ratio, want_entries=False)
+        assert s["generated"] == ctx.expected(n, ratio)
+        s = espb.plan_schedule(taps, 32, 3, off, idx, 10 ** 7, n, ratio, want_entries=False)
+        assert s["used"] == ctx.required(n, ratio)
+
+
+def test_wrapper_policy_matches_oracle(oracle):
+    rates = [8000, 16000, 22050, 32000, 44100, 48000, 88200, 96000]
+    for sr in rates:
+        for dr in rates:
+            for taps in (32, 256, 1024):
+                for use_f in (0, 1):
+                    w = oracle.wrapper(64, 64, float(sr), float(dr), 16, 16, 2, use_f, 1, taps, 64)
+                    a = oracle.wrapper_policy(w)
+                    b = espb.plan_policy(sr, dr, 16, 16, 2, use_f, 1, taps, 64)
+                    assert a["filter"] == b["filter"], (sr, dr, taps)
+                    assert a["sample_ratio"] == b["sample_ratio"] and a["art_lowpass"] == b["art_lowpass"]
+                    assert a["art_flags"] == b["art_flags"], (sr, dr, taps, a, b)
+                    if a["filter"] != "none":
+                        assert bits_equal(a["coeffs"], b["coeffs"])
+    # which branch each BASELINE config takes
+    assert espb.plan_policy(44100, 48000, 32, 32, 2, 1, 1, 256, 256)["filter"] == "post"
+    assert espb.plan_policy(16000, 48000, 16, 16, 1, 1, 1, 256, 256)["filter"] == "post"
+    assert espb.plan_policy(96000, 44100, 24, 24, 2, 1, 1, 1024, 256)["filter"] == "pre"
+    assert espb.plan_policy(48000, 44100, 32, 32, 2, 1, 1, 256, 256)["filter"] == "pre"
+
+
+def test_biquad_design_matches_golden(golden):
+    arrays, meta = golden
+    for k, b in enumerate(meta["biquad"]):
+        c = espb.biquad_lowpass(b["f"]) if b["kind"] == "lp" else espb.biquad_highpass(b["f"])
+        assert bits_equal(c, arrays[f"biquad_{k}_c"])
