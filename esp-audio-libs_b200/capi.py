@@ -12,6 +12,7 @@ _HEADER = os.path.join(_ROOT, "include", "esp_audio_b200.h")
 
 SUBSAMPLE_INTERPOLATE, BLACKMAN_HARRIS, INCLUDE_LOWPASS = 0x1, 0x2, 0x4
 MODE_FAST, MODE_EXACT = 0, 1
+OPT_PLAN_CACHE, OPT_KERNEL_TIMING, OPT_BLOCKS_PER_PASS = 1, 2, 3
 
 
 class EspbError(RuntimeError):
@@ -98,6 +99,8 @@ def lib():
         "espb_resampleGetRequiredSamples": (C.c_uint, [vp, i, f]),
         "espb_resampleGetExpectedOutput": (C.c_uint, [vp, i, f]),
         "espb_resampleSetMode": (i, [vp, i]),
+        "espb_resampleSetOption": (i, [vp, i, i]),
+        "espb_resampleGetKernelTime": (i, [vp, C.POINTER(f), C.POINTER(i)]),
         "espb_resampleGetFlags": (i, [vp]),
         "espb_resampleGetState": (None, [vp, C.POINTER(f), C.POINTER(i)]),
         "espb_resampleCopyFilters": (i, [vp, vp]),
@@ -302,6 +305,14 @@ class ResampleBatch:
 
     def reset(self, stream=None):
         _check(lib().espb_resampleReset(self.h, stream), "resampleReset")
+
+    def set_option(self, option, value):
+        _check(lib().espb_resampleSetOption(self.h, option, value), "resampleSetOption")
+
+    def kernel_time(self):
+        ms, n = C.c_float(0), C.c_int(0)
+        _check(lib().espb_resampleGetKernelTime(self.h, C.byref(ms), C.byref(n)), "resampleGetKernelTime")
+        return float(ms.value), int(n.value)
 
     def advance(self, delta):
         lib().espb_resampleAdvancePosition(self.h, delta)

@@ -295,6 +295,14 @@ struct EspbResampleBatch {
   // device staging + CUDA streams of the host-buffer entry point
   DevBuf stage_in, stage_out;
   HostPipe pipe;
+  // options
+  bool plan_cache = true;   // reuse schedule / tables / G when a call repeats (state, n_in, n_out, ratio)
+  bool kernel_timing = false;
+  std::vector<cudaEvent_t> ev_pool;  // pairs: [2k] before, [2k+1] after each resample-kernel launch
+  size_t ev_used = 0;
+  // the last asynchronous state change (reset) — processing on any other stream waits for it
+  cudaEvent_t state_event = nullptr;
+  bool state_event_pending = false;
   int n_series() const { return num_streams * channels; }
 };
 
@@ -302,13 +310,17 @@ namespace {
 
 // Build (or reuse) the schedule + pass plan for this call and upload the tables.
 int prepare_call(EspbResampleBatch *c, int n_in, int n_out, float ratio, cudaStream_t stream) {
+  if (c->state_event_pending) {  // order this call after an asynchronous reset issued on another stream
+    CU_TRY(cudaStreamWaitEvent(stream, c->state_event, 0), "cudaStreamWaitEvent");
+    c->state_event_pending = false;
+  }
   ScheduleKey k;
   k.offset_bits = f2u(c->state.offset);
   k.ratio_bits = f2u(ratio);
   k.index = c->state.index;
   k.n_in = n_in;
   k.n_out = n_out;
-  if (c->plan_on_device && k == c->key)
+  if (c->plan_cache && c->plan_on_device && k == c->key)
     return ESPB_OK;
   c->plan_on_device = false;
   c->g_resident_first = c->g_resident_end = -1;
@@ -362,10 +374,8 @@ int ensure_g(EspbResampleBatch *c, int chunk_first, int chunk_end, cudaStream_t 
   return ESPB_OK;
 }
 
-int pick_passes_per_cta(const EspbResampleBatch *c, int n_series, int n_passes) {
-  long forced = env_long("ESPB_PPC", 0);
-  if (forced > 0)
-    return (int) forced;
+int pick_passes_per_cta(const EspbResampleBatch *c, int n_series, int pass_first, int pass_end) {
+  const int n_passes = pass_end - pass_first;
   int sms = 148;
   int dev = 0;
   if (cudaGetDevice(&dev) == cudaSuccess)
@@ -373,12 +383,24 @@ int pick_passes_per_cta(const EspbResampleBatch *c, int n_series, int n_passes) 
   const long groups = (n_series + kSeriesPerRow - 1) / kSeriesPerRow;
   const long slots = (long) sms * 2;  // resident CTAs
   // aim for >= 8 waves of CTAs so the tail stays small, but never less than 1 pass per CTA
-  long ppc = (groups * n_passes) / (slots * 8);
+  long ppc = env_long("ESPB_PPC", 0);
+  if (ppc <= 0)
+    ppc = (groups * n_passes) / (slots * 8);
   if (ppc < 1)
     ppc = 1;
-  if (ppc > 64)
-    ppc = 64;
-  (void) c;
+  if (ppc > kMaxPassesPerCta)
+    ppc = kMaxPassesPerCta;
+  // the CTA caches its chunk table in shared memory: keep the longest run of ppc passes within it
+  int max_chunks = 1;
+  for (int ps = pass_first; ps < pass_end; ++ps) {
+    const int n = c->plan.pass_chunk_begin[ps + 1] - c->plan.pass_chunk_begin[ps];
+    if (n > max_chunks)
+      max_chunks = n;
+  }
+  if (ppc * max_chunks > kMaxChunksPerCta)
+    ppc = kMaxChunksPerCta / max_chunks;
+  if (ppc < 1)
+    ppc = 1;  // a single pass longer than the table cannot happen: taps <= 1024 gives <= 40 chunks per pass
   return (int) ppc;
 }
 
@@ -421,8 +443,21 @@ int run_series_range(EspbResampleBatch *c, int series_first, int n_series, const
       p.g_chunk_base = cf;
       p.pass_first = pf;
       p.pass_end = pe;
-      p.passes_per_cta = pick_passes_per_cta(c, n_series, pe - pf);
+      p.passes_per_cta = pick_passes_per_cta(c, n_series, pf, pe);
+      cudaEvent_t ev_after = nullptr;
+      if (c->kernel_timing) {
+        while (c->ev_pool.size() < c->ev_used + 2) {
+          cudaEvent_t ev;
+          CU_TRY(cudaEventCreate(&ev), "cudaEventCreate");
+          c->ev_pool.push_back(ev);
+        }
+        CU_TRY(cudaEventRecord(c->ev_pool[c->ev_used], stream), "cudaEventRecord");
+        ev_after = c->ev_pool[c->ev_used + 1];
+        c->ev_used += 2;
+      }
       CU_TRY(launch_resample(p, c->bpp, c->mode == ESPB_MODE_EXACT, stream), "resample kernel");
+      if (ev_after)
+        CU_TRY(cudaEventRecord(ev_after, stream), "cudaEventRecord");
     }
   }
   if (c->sched.used > 0)
@@ -502,6 +537,10 @@ void espb_resampleFree(EspbResampleBatch *c) {
   c->stage_in.release();
   c->stage_out.release();
   c->pipe.destroy();
+  for (cudaEvent_t ev : c->ev_pool)
+    cudaEventDestroy(ev);
+  if (c->state_event)
+    cudaEventDestroy(c->state_event);
   delete c;
 }
 
@@ -511,6 +550,10 @@ int espb_resampleReset(EspbResampleBatch *c, void *stream) {
   CU_TRY(cudaMemsetAsync(c->hist[c->hist_cur].p, 0, (size_t) c->n_series() * c->geo.taps * sizeof(float),
                          as_stream(stream)),
          "resampleReset");
+  if (!c->state_event)
+    CU_TRY(cudaEventCreateWithFlags(&c->state_event, cudaEventDisableTiming), "cudaEventCreate");
+  CU_TRY(cudaEventRecord(c->state_event, as_stream(stream)), "cudaEventRecord");
+  c->state_event_pending = true;
   c->state = initial_state(c->geo.taps);
   return ESPB_OK;
 }
@@ -535,6 +578,46 @@ int espb_resampleSetMode(EspbResampleBatch *c, int mode) {
   if (!c || (mode != ESPB_MODE_FAST && mode != ESPB_MODE_EXACT))
     return fail(ESPB_ERR_ARG, "resampleSetMode: bad mode");
   c->mode = mode;
+  return ESPB_OK;
+}
+
+int espb_resampleSetOption(EspbResampleBatch *c, int option, int value) {
+  if (!c)
+    return fail(ESPB_ERR_ARG, "resampleSetOption: NULL");
+  switch (option) {
+    case ESPB_OPT_PLAN_CACHE:
+      c->plan_cache = value != 0;
+      c->plan_on_device = false;
+      return ESPB_OK;
+    case ESPB_OPT_KERNEL_TIMING:
+      c->kernel_timing = value != 0;
+      c->ev_used = 0;
+      return ESPB_OK;
+    case ESPB_OPT_BLOCKS_PER_PASS:
+      if (value != 4 && value != 8)
+        return fail(ESPB_ERR_ARG, "resampleSetOption: blocks per pass must be 4 or 8");
+      c->bpp = value;
+      c->plan_on_device = false;
+      return ESPB_OK;
+    default:
+      return fail(ESPB_ERR_ARG, "resampleSetOption: unknown option");
+  }
+}
+
+int espb_resampleGetKernelTime(EspbResampleBatch *c, float *total_ms, int *launches) {
+  if (!c || !total_ms)
+    return fail(ESPB_ERR_ARG, "resampleGetKernelTime: NULL");
+  float sum = 0.0f;
+  for (size_t i = 0; i + 1 < c->ev_used; i += 2) {
+    CU_TRY(cudaEventSynchronize(c->ev_pool[i + 1]), "cudaEventSynchronize");
+    float ms = 0.0f;
+    CU_TRY(cudaEventElapsedTime(&ms, c->ev_pool[i], c->ev_pool[i + 1]), "cudaEventElapsedTime");
+    sum += ms;
+  }
+  *total_ms = sum;
+  if (launches)
+    *launches = (int) (c->ev_used / 2);
+  c->ev_used = 0;
   return ESPB_OK;
 }
 

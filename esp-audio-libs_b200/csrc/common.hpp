@@ -9,6 +9,8 @@ constexpr int kOutputsPerBlock = 8;   // NB: outputs accumulated per thread
 constexpr int kChunkRows = 32;        // CJ: input frames staged per pipeline stage
 constexpr int kSeriesPerRow = 128;    // series (stream x channel) per warp row: 32 lanes x 4
 constexpr int kGRowFloats = 2 * kOutputsPerBlock;  // 16 coefficients per (row, output block)
+constexpr int kMaxChunksPerCta = 768;  // chunk-table entries a CTA caches in shared memory
+constexpr int kMaxPassesPerCta = 64;
 
 // What the reference does for one output sample (art_resampler.cpp:421-451).
 enum OutKind : int32_t {

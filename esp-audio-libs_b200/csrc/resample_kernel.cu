@@ -38,6 +38,8 @@ constexpr int CJ = kChunkRows;        // 32
 constexpr int SGN = kSeriesPerRow;    // 128
 constexpr int XROW = SGN + 4;         // padded row: conflict-free transposing stores and 128-bit loads
 constexpr int STAGES = 3;
+constexpr int MAXC = kMaxChunksPerCta;   // chunk entries cached in shared memory per CTA
+constexpr int MAXP = kMaxPassesPerCta;   // passes per CTA
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t) __cvta_generic_to_shared(p); }
 
@@ -143,6 +145,8 @@ __global__ void __launch_bounds__(BPP * 32, (BPP <= 8 ? 2 : 1))
   float *gs = reinterpret_cast<float *>(smem_raw);               // [STAGES][CJ][BPP][16]
   float *xs = gs + STAGES * GS_STAGE;                            // [STAGES][CJ][XROW]
   uint64_t *gbar = reinterpret_cast<uint64_t *>(xs + STAGES * XS_STAGE);
+  ChunkEntry *ctab = reinterpret_cast<ChunkEntry *>(gbar + STAGES);  // [MAXC] this CTA's chunks
+  int2 *wtab = reinterpret_cast<int2 *>(ctab + MAXC);                // [MAXP][BPP] window [lo, hi) per (pass, warp)
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int series0 = blockIdx.x * SGN;
@@ -155,6 +159,20 @@ __global__ void __launch_bounds__(BPP * 32, (BPP <= 8 ? 2 : 1))
     pass_last = p.pass_end;
   const int chunk_first = p.pass_chunk_begin[pass_first], chunk_last = p.pass_chunk_begin[pass_last];
   const int n_chunks = chunk_last - chunk_first;
+
+  // ---- cache the signal-independent tables this CTA needs (no dependent global loads in the main loop)
+  for (int i = tid; i < n_chunks; i += BPP * 32)
+    ctab[i] = p.chunks[chunk_first + i];
+  for (int i = tid; i < (pass_last - pass_first) * BPP; i += BPP * 32) {
+    const int o0 = ((pass_first + i / BPP) * BPP + (i % BPP)) * NB;
+    int2 w = make_int2(0, 0);
+    if (o0 < p.n_out) {
+      const int o1 = (o0 + NB <= p.n_out ? o0 + NB : p.n_out) - 1;
+      w.x = p.outs[o0].ws;
+      w.y = p.outs[o1].ws + T;
+    }
+    wtab[i] = w;
+  }
 
   if (tid == 0) {
 #pragma unroll
@@ -181,7 +199,7 @@ __global__ void __launch_bounds__(BPP * 32, (BPP <= 8 ? 2 : 1))
   auto stage_chunk = [&](int c) {  // c relative to chunk_first
     const int st = c % STAGES;
     const int gc = chunk_first + c;
-    const int j0 = p.chunks[gc].j_start;
+    const int j0 = ctab[c].j_start;
     if (tid == 0) {
       mbar_expect_tx(&gbar[st], G_BYTES);
       tma_bulk_g2s(gs + st * GS_STAGE, p.G + (size_t) (gc - p.g_chunk_base) * GS_STAGE, G_BYTES, &gbar[st]);
@@ -248,43 +266,45 @@ __global__ void __launch_bounds__(BPP * 32, (BPP <= 8 ? 2 : 1))
       stage_chunk(c + STAGES - 1);
     cp_async_commit();
 
-    const ChunkEntry ce = p.chunks[chunk_first + c];
+    const ChunkEntry ce = ctab[c];
     if (ce.pass != cur_pass) {
       cur_pass = ce.pass;
-      const int o0 = (cur_pass * BPP + warp) * NB;
-      if (o0 < p.n_out) {
-        const int o1 = (o0 + NB <= p.n_out ? o0 + NB : p.n_out) - 1;
-        win_lo = p.outs[o0].ws;
-        win_hi = p.outs[o1].ws + T;
-      } else {
-        win_lo = 0;
-        win_hi = 0;
-      }
+      const int2 w = wtab[(cur_pass - pass_first) * BPP + warp];
+      win_lo = w.x;
+      win_hi = w.y;
     }
 
-    if (ce.j_start < win_hi && ce.j_start + CJ > win_lo) {
+    // rows of this chunk inside the warp's window, in groups of 8 (rows outside it only multiply zeros)
+    int r0 = win_lo - ce.j_start, r1 = win_hi - ce.j_start;
+    r0 = r0 < 0 ? 0 : (r0 >> 3);
+    r1 = r1 > CJ ? CJ / 8 : ((r1 + 7) >> 3);
+    {
       const float *xrow = xs + st * XS_STAGE + lane * 4;
       const float *grow = gs + st * GS_STAGE + warp * kGRowFloats;
-#pragma unroll 8
-      for (int jj = 0; jj < CJ; ++jj) {
-        const float4 xv = *reinterpret_cast<const float4 *>(xrow + jj * XROW);
-        const float4 *gp = reinterpret_cast<const float4 *>(grow + jj * BPP * kGRowFloats);
-        const float4 g0 = gp[0], g1 = gp[1], g2 = gp[2], g3 = gp[3];
-        const float x4[4] = {xv.x, xv.y, xv.z, xv.w};
-        const float g16[16] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w,
-                               g2.x, g2.y, g2.z, g2.w, g3.x, g3.y, g3.z, g3.w};
+      for (int jb = r0; jb < r1; ++jb) {
+        const float *xb = xrow + jb * 8 * XROW;
+        const float *gb = grow + jb * 8 * BPP * kGRowFloats;
 #pragma unroll
-        for (int n = 0; n < NB; ++n)
+        for (int jj = 0; jj < 8; ++jj) {
+          const float4 xv = *reinterpret_cast<const float4 *>(xb + jj * XROW);
+          const float4 *gp = reinterpret_cast<const float4 *>(gb + jj * BPP * kGRowFloats);
+          const float4 g0 = gp[0], g1 = gp[1], g2 = gp[2], g3 = gp[3];
+          const float x4[4] = {xv.x, xv.y, xv.z, xv.w};
+          const float g16[16] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w,
+                                 g2.x, g2.y, g2.z, g2.w, g3.x, g3.y, g3.z, g3.w};
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            acc[e][n][0] = mac<EXACT>(g16[2 * n], x4[e], acc[e][n][0]);
-            acc[e][n][1] = mac<EXACT>(g16[2 * n + 1], x4[e], acc[e][n][1]);
-          }
+          for (int n = 0; n < NB; ++n)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              acc[e][n][0] = mac<EXACT>(g16[2 * n], x4[e], acc[e][n][0]);
+              acc[e][n][1] = mac<EXACT>(g16[2 * n + 1], x4[e], acc[e][n][1]);
+            }
+        }
       }
     }
 
     // ---- end of pass: blend, store, clear
-    const bool pass_done = (c + 1 == n_chunks) || (p.chunks[chunk_first + c + 1].pass != cur_pass);
+    const bool pass_done = (c + 1 == n_chunks) || (ctab[c + 1].pass != cur_pass);
     if (pass_done) {
       const int o0 = (cur_pass * BPP + warp) * NB;
       int64_t in_off[4], out_off[4];
@@ -360,7 +380,8 @@ __global__ void espb_history_kernel(const float *__restrict__ in, int64_t in_ss,
 // launchers
 // ---------------------------------------------------------------------------------
 size_t resample_smem_bytes(int bpp) {
-  return (size_t) STAGES * (CJ * bpp * kGRowFloats + CJ * XROW) * sizeof(float) + STAGES * sizeof(uint64_t);
+  return (size_t) STAGES * (CJ * bpp * kGRowFloats + CJ * XROW) * sizeof(float) + STAGES * sizeof(uint64_t) +
+         MAXC * sizeof(ChunkEntry) + (size_t) MAXP * bpp * sizeof(int2);
 }
 
 size_t g_chunk_floats(int bpp) { return (size_t) CJ * bpp * kGRowFloats; }

@@ -167,3 +167,26 @@ def test_biquad_design_matches_golden(golden):
     for k, b in enumerate(meta["biquad"]):
         c = espb.biquad_lowpass(b["f"]) if b["kind"] == "lp" else espb.biquad_highpass(b["f"])
         assert bits_equal(c, arrays[f"biquad_{k}_c"])
+
+
+def test_cpp_shim_compiles_and_links(tmp_path):
+    """include/esp_audio_b200.hpp (the reference's names over the C ABI) and the plain-C header build."""
+    import shutil
+    import subprocess
+    if not shutil.which("g++"):
+        pytest.skip("no g++")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = tmp_path / "shim.cpp"
+    src.write_text('#include "esp_audio_b200.hpp"\n'
+                   "namespace b = esp_audio_libs_b200;\n"
+                   "int main() { b::resampler::Resampler r(4, 1024, 4096); (void) r;\n"
+                   "  b::art_resampler::BiquadCoefficients c; b::art_resampler::biquad_lowpass(&c, 0.2274);\n"
+                   "  return (espb_abi_version() == ESPB_ABI_VERSION && c.a0 > 0.25f && c.a0 < 0.26f) ? 0 : 1; }\n")
+    exe = tmp_path / "shim"
+    libdir = os.path.dirname(espb.library_path())
+    subprocess.run(["g++", "-std=c++11", "-I", os.path.join(root, "include"), str(src), "-o", str(exe), "-L", libdir,
+                    "-lesp_audio_b200", f"-Wl,-rpath,{libdir}"], check=True)
+    assert subprocess.run([str(exe)]).returncode == 0
+    csrc = tmp_path / "hdr.c"
+    csrc.write_text('#include "esp_audio_b200.h"\nint main(void) { return 0; }\n')
+    subprocess.run(["gcc", "-std=c99", "-fsyntax-only", "-I", os.path.join(root, "include"), str(csrc)], check=True)
