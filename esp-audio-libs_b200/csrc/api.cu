@@ -261,12 +261,22 @@ struct HostPipe {
   }
 };
 
-int pick_slab_streams(int num_streams) {
+// Streams per slab of the host pipeline: about 8 slabs, each starting on a 128-series group boundary.
+int pick_slab_streams(int num_streams, int channels) {
   long forced = env_long("ESPB_HOST_SLABS", 0);
   long slabs = forced > 0 ? forced : 8;
   if (slabs > num_streams)
     slabs = num_streams;
-  return (int) ((num_streams + slabs - 1) / slabs);
+  long per = (num_streams + slabs - 1) / slabs;
+  int a = kSeriesPerRow, b = channels;
+  while (b) {
+    int t = a % b;
+    a = b;
+    b = t;
+  }
+  const long unit = kSeriesPerRow / a;  // smallest stream count whose series fill whole groups
+  per = (per + unit - 1) / unit * unit;
+  return (int) per;
 }
 
 }  // namespace
@@ -282,8 +292,15 @@ struct EspbResampleBatch {
   int mode = ESPB_MODE_FAST;
   int bpp = 8;  // output blocks (warps) per pass
   std::vector<float> bank_host;
-  DevBuf bank, hist[2];
-  int hist_cur = 0;
+  DevBuf bank;
+  // time-major input staging xt[group][row][128]: rows [0, taps) = frames carried over from the
+  // previous call, rows [taps, taps + n_in) = this call's input, then zero padding.  Two buffers
+  // alternate; the carry of the next call is rows [carry_row, carry_row + taps) of xt[xt_cur].
+  DevBuf xt[2];
+  int xt_cur = 0;
+  int64_t xt_rows = 0;  // rows per group in both buffers
+  int carry_row = 0;
+  int n_groups() const { return (n_series() + kSeriesPerRow - 1) / kSeriesPerRow; }
   // per-call plan, cached by (state, n_in, n_out, ratio)
   Schedule sched;
   PassPlan plan;
@@ -308,11 +325,18 @@ struct EspbResampleBatch {
 
 namespace {
 
+int ensure_xt(EspbResampleBatch *c, int64_t rows);
+
 // Build (or reuse) the schedule + pass plan for this call and upload the tables.
 int prepare_call(EspbResampleBatch *c, int n_in, int n_out, float ratio, cudaStream_t stream) {
   if (c->state_event_pending) {  // order this call after an asynchronous reset issued on another stream
     CU_TRY(cudaStreamWaitEvent(stream, c->state_event, 0), "cudaStreamWaitEvent");
     c->state_event_pending = false;
+  }
+  {
+    int rc = ensure_xt(c, (int64_t) c->geo.taps + n_in + kChunkRows);
+    if (rc != ESPB_OK)
+      return rc;
   }
   ScheduleKey k;
   k.offset_bits = f2u(c->state.offset);
@@ -404,29 +428,66 @@ int pick_passes_per_cta(const EspbResampleBatch *c, int n_series, int pass_first
   return (int) ppc;
 }
 
-// Resample + history update for series [series_first, series_first + n_series) of the batch.
+// Make both staging buffers hold at least `rows` rows per group, keeping the carried frames.
+int ensure_xt(EspbResampleBatch *c, int64_t rows) {
+  if (rows <= c->xt_rows)
+    return ESPB_OK;
+  const int taps = c->geo.taps;
+  const size_t row_bytes = kSeriesPerRow * sizeof(float);
+  const size_t bytes = (size_t) c->n_groups() * rows * row_bytes;
+  DevBuf nb[2];
+  cudaError_t e = nb[0].reserve(bytes);
+  if (e == cudaSuccess)
+    e = nb[1].reserve(bytes);
+  if (e == cudaSuccess && c->xt_rows > 0)  // carry rows -> rows [0, taps) of the new current buffer
+    e = cudaMemcpy2D(nb[0].p, rows * row_bytes, c->xt[c->xt_cur].as<float>() + (size_t) c->carry_row * kSeriesPerRow,
+                     c->xt_rows * row_bytes, taps * row_bytes, c->n_groups(), cudaMemcpyDeviceToDevice);
+  else if (e == cudaSuccess)
+    e = cudaMemset2D(nb[0].p, rows * row_bytes, 0, taps * row_bytes, c->n_groups());
+  if (e != cudaSuccess) {
+    nb[0].release();
+    nb[1].release();
+    return cuda_fail(e, "staging buffers");
+  }
+  c->xt[0].release();  // cudaFree waits for work that may still read the old buffers
+  c->xt[1].release();
+  c->xt[0] = nb[0];
+  c->xt[1] = nb[1];
+  c->xt_cur = 0;
+  c->carry_row = 0;
+  c->xt_rows = rows;
+  return ESPB_OK;
+}
+
+// Stage + resample series [series_first, series_first + n_series) of the batch (series_first is a
+// multiple of 128).  The carried frames and the new input go to the spare staging buffer.
 int run_series_range(EspbResampleBatch *c, int series_first, int n_series, const float *in, const EspbLayout &il,
                      float *out, const EspbLayout &ol, int n_in, cudaStream_t stream, bool g_preexpanded) {
   const int taps = c->geo.taps;
-  const float *hist_old = c->hist[c->hist_cur].as<float>() + (size_t) series_first * taps;
-  float *hist_new = c->hist[1 - c->hist_cur].as<float>() + (size_t) series_first * taps;
+  const int g0 = series_first / kSeriesPerRow, ng = (n_series + kSeriesPerRow - 1) / kSeriesPerRow;
+  const int64_t rows = c->xt_rows;
+  const size_t row_bytes = kSeriesPerRow * sizeof(float);
+  const float *x_old = c->xt[c->xt_cur].as<float>() + (size_t) g0 * rows * kSeriesPerRow;
+  float *x_new = c->xt[1 - c->xt_cur].as<float>() + (size_t) g0 * rows * kSeriesPerRow;
+  CU_TRY(cudaMemcpy2DAsync(x_new, rows * row_bytes, x_old + (size_t) c->carry_row * kSeriesPerRow, rows * row_bytes,
+                           taps * row_bytes, ng, cudaMemcpyDeviceToDevice, stream),
+         "carry copy");
+  CU_TRY(launch_transpose(in, il.stream_stride, il.channel_stride, il.frame_stride, c->channels, n_series, n_in,
+                          x_new, rows, taps, kChunkRows, stream),
+         "transpose kernel");
   if (c->sched.generated > 0) {
     ResampleParams p{};
-    p.in = in;
-    p.in_ss = il.stream_stride;
-    p.in_cs = il.channel_stride;
-    p.in_fs = il.frame_stride;
+    p.xt = x_new;
+    p.xt_rows = rows;
     p.out = out;
     p.out_ss = ol.stream_stride;
     p.out_cs = ol.channel_stride;
     p.out_fs = ol.frame_stride;
-    p.hist = hist_old;
     p.chunks = c->d_chunks.as<ChunkEntry>();
     p.pass_chunk_begin = c->d_pcb.as<int32_t>();
     p.outs = c->d_outs.as<OutEntry>();
     p.n_series = n_series;
     p.channels = c->channels;
-    p.n_in = n_in;
     p.n_out = (int) c->sched.generated;
     p.taps = taps;
     const int n_passes = c->plan.n_passes();
@@ -460,16 +521,13 @@ int run_series_range(EspbResampleBatch *c, int series_first, int n_series, const
         CU_TRY(cudaEventRecord(ev_after, stream), "cudaEventRecord");
     }
   }
-  if (c->sched.used > 0)
-    CU_TRY(launch_history(in, il.stream_stride, il.channel_stride, il.frame_stride, hist_old, hist_new, n_series,
-                          c->channels, taps, (int) c->sched.used, stream),
-           "history kernel");
   return ESPB_OK;
 }
 
 void finish_call(EspbResampleBatch *c) {
-  if (c->sched.used > 0)
-    c->hist_cur = 1 - c->hist_cur;
+  // the frames [used - taps, used) of this call are the next call's carry: rows [used, used + taps)
+  c->xt_cur = 1 - c->xt_cur;
+  c->carry_row = (int) c->sched.used;
   c->state = c->sched.end;
 }
 
@@ -504,20 +562,15 @@ EspbResampleBatch *espb_resampleInit(int num_streams, int numChannels, int numTa
     c->g_budget_bytes = (size_t) gb << 20;
   build_filter_bank(c->geo, lowpassRatio, c->bank_host);
   const size_t bank_bytes = c->bank_host.size() * sizeof(float);
-  const size_t hist_bytes = (size_t) c->n_series() * numTaps * sizeof(float);
   cudaError_t e = c->bank.reserve(bank_bytes);
   if (e == cudaSuccess)
-    e = c->hist[0].reserve(hist_bytes);
-  if (e == cudaSuccess)
-    e = c->hist[1].reserve(hist_bytes);
-  if (e == cudaSuccess)
     e = cudaMemcpy(c->bank.p, c->bank_host.data(), bank_bytes, cudaMemcpyHostToDevice);
-  if (e == cudaSuccess)
-    e = cudaMemset(c->hist[0].p, 0, hist_bytes);
-  if (e == cudaSuccess)
-    e = cudaMemset(c->hist[1].p, 0, hist_bytes);
   if (e != cudaSuccess) {
     cuda_fail(e, "resampleInit: device allocation");
+    espb_resampleFree(c);
+    return nullptr;
+  }
+  if (ensure_xt(c, (int64_t) numTaps + kChunkRows) != ESPB_OK) {  // silent history (art_resampler.cpp:125-133)
     espb_resampleFree(c);
     return nullptr;
   }
@@ -528,8 +581,8 @@ void espb_resampleFree(EspbResampleBatch *c) {
   if (!c)
     return;
   c->bank.release();
-  c->hist[0].release();
-  c->hist[1].release();
+  c->xt[0].release();
+  c->xt[1].release();
   c->d_outs.release();
   c->d_chunks.release();
   c->d_pcb.release();
@@ -547,8 +600,9 @@ void espb_resampleFree(EspbResampleBatch *c) {
 int espb_resampleReset(EspbResampleBatch *c, void *stream) {
   if (!c)
     return fail(ESPB_ERR_ARG, "resampleReset: NULL context");
-  CU_TRY(cudaMemsetAsync(c->hist[c->hist_cur].p, 0, (size_t) c->n_series() * c->geo.taps * sizeof(float),
-                         as_stream(stream)),
+  const size_t row_bytes = kSeriesPerRow * sizeof(float);
+  CU_TRY(cudaMemset2DAsync(c->xt[c->xt_cur].as<float>() + (size_t) c->carry_row * kSeriesPerRow,
+                           c->xt_rows * row_bytes, 0, c->geo.taps * row_bytes, c->n_groups(), as_stream(stream)),
          "resampleReset");
   if (!c->state_event)
     CU_TRY(cudaEventCreateWithFlags(&c->state_event, cudaEventDisableTiming), "cudaEventCreate");
@@ -717,7 +771,7 @@ EspbResampleResult espb_resampleProcessInterleavedHost(EspbResampleBatch *c, con
       return res;
   }
   cudaEventRecord(hs->pipe.ready, s0);
-  const int per = pick_slab_streams(c->num_streams);
+  const int per = pick_slab_streams(c->num_streams, c->channels);
   EspbLayout il = {(int64_t) in_row, 1, ch}, ol = {(int64_t) out_cap_row, 1, ch};
   int slab = 0;
   for (int st0 = 0; st0 < c->num_streams; st0 += per, ++slab) {
@@ -1287,7 +1341,7 @@ EspbResamplerResults espb_resampler_resample_host(EspbResampler *r, const uint8_
       return none;
   }
   cudaEventRecord(r->pipe.ready, s0);
-  const int per = pick_slab_streams(r->num_streams);
+  const int per = pick_slab_streams(r->num_streams, r->cfg.channels);
   int slab = 0;
   for (int st0 = 0; st0 < r->num_streams; st0 += per, ++slab) {
     const int ns = st0 + per <= r->num_streams ? per : r->num_streams - st0;

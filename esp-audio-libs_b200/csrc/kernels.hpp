@@ -11,16 +11,15 @@ namespace espb {
 void count_launch();  // bumps the process-wide kernel-launch counter (api.cu)
 
 struct ResampleParams {
-  const float *in;
-  int64_t in_ss, in_cs, in_fs;  // stream / channel / frame strides, floats
+  const float *xt;  // time-major input staging of the first group of this launch: [group][xt_rows][128]
+  int64_t xt_rows;  // rows per group (row r = input frame r - taps)
   float *out;
-  int64_t out_ss, out_cs, out_fs;
-  const float *hist;  // [n_series][taps] frames consumed before this call
-  const float *G;     // expanded coefficients, chunk-major, starting at chunk g_chunk_base
+  int64_t out_ss, out_cs, out_fs;  // stream / channel / frame strides of the caller's output, floats
+  const float *G;                  // expanded coefficients, chunk-major, starting at chunk g_chunk_base
   const ChunkEntry *chunks;
   const int32_t *pass_chunk_begin;
   const OutEntry *outs;
-  int n_series, channels, n_in, n_out, taps;
+  int n_series, channels, n_out, taps;
   int pass_first, pass_end, passes_per_cta, g_chunk_base;
 };
 
@@ -29,8 +28,9 @@ size_t g_chunk_floats(int bpp);
 cudaError_t launch_expand(const float *bank, const OutEntry *outs, const ChunkEntry *chunks, float *G,
                           int chunk_first, int n_chunks, int n_out, int taps, int bpp, cudaStream_t stream);
 cudaError_t launch_resample(const ResampleParams &p, int bpp, bool exact, cudaStream_t stream);
-cudaError_t launch_history(const float *in, int64_t in_ss, int64_t in_cs, int64_t in_fs, const float *hist_old,
-                           float *hist_new, int n_series, int channels, int taps, int used, cudaStream_t stream);
+cudaError_t launch_transpose(const float *in, int64_t in_ss, int64_t in_cs, int64_t in_fs, int channels, int n_series,
+                             int n_in, float *xt, int64_t rows_cap, int row_first, int pad_rows,
+                             cudaStream_t stream);
 
 // quantization_utils
 cudaError_t launch_q2f(const uint8_t *in, int64_t in_row_bytes, float *out, int64_t out_row_floats, int rows,

@@ -7,22 +7,29 @@
 // mode, FMUL+FADD in exact mode) — splitting a sum across lanes or accumulators moves the
 // result by up to 1.8e-6 against the reference and is not allowed.
 //
-// Mapping.  The schedule (ws_n, phase_n, w_n) is the same for every stream, so the two
-// coefficient columns of every output are expanded ONCE per call into a dense,
-// pre-skewed matrix G (espb_expand_kernel):
-//     G[chunk][row j][block-in-pass b][n in block][f]  =  H[phase_n + f][j - ws_n]  (0 outside the window)
-// and the resampler becomes, per input row j, a rank-1 update
-//     acc[series e][n][f] += G[j][n][f] * x[j][series e]
-// of a 4-series x 8-output x 2-filter register tile (64 independent accumulators per
-// thread): x is a per-lane 128-bit shared-memory load (4 series), G sixteen warp-uniform
-// values (four broadcast 128-bit loads) -> 64 FFMA per 5 LDS, 8 shared-memory
-// wavefronts per 64 FFMA, every accumulator visiting its taps in order j = ws_n .. ws_n+T-1.
+// Data layout in HBM (ours, built per call):
+//   xt[group g][row r][128 series]   time-major input staging: row r holds input frame
+//        j = r - numTaps of the 128 series (stream x channel) of group g; rows [0, numTaps)
+//        are the frames carried over from the previous call (the reference keeps them at
+//        the front of its ring, art_resampler.cpp:216-222), rows past the input are zero.
+//        Written by espb_transpose_kernel from the caller's stream-major buffers.
+//   G[chunk][row][block-in-pass b][n in block][f]  =  H[phase_n + f][j - ws_n]  (0 outside the
+//        window): the two coefficient columns of every output, pre-skewed to input rows.
+//        The schedule (ws_n, phase_n, w_n) is identical for all streams, so G is expanded
+//        once per call (espb_expand_kernel) and shared by every CTA.
+// With these, one chunk (32 input rows) of either operand is ONE contiguous 16 KB block.
 //
-// A CTA owns 128 series and `BPP` consecutive output blocks (one per warp) — a "pass".
-// It sweeps the union of their windows in chunks of 32 input rows through a 3-stage
-// shared-memory ring: the G chunk arrives by one bulk-TMA copy (cp.async.bulk + mbarrier
-// complete_tx), the x chunk is transposed from the stream-major HBM layout into
-// [row][series] by 4-byte cp.async.  Warps whose window does not reach a chunk skip it.
+// Kernel.  A CTA owns one group (128 series) and sweeps "passes" of BPP consecutive output
+// blocks (8 outputs each, one block per consumer warp) over the union of their windows in
+// chunks of 32 rows.  Warp BPP is the producer: one elected lane streams the chunks through
+// a 3-stage shared-memory ring with two TMA bulk copies per chunk (cp.async.bulk ->
+// mbarrier complete_tx; SASS UBLKCP), throttled by per-stage "empty" mbarriers.  The BPP
+// consumer warps wait on the "full" mbarrier, and per input row do the rank-1 update
+//     acc[series e][n][f] += G[row][n][f] * x[row][series e]
+// of a 4-series x 8-output x 2-filter register tile: x is one per-lane 128-bit LDS, G four
+// warp-uniform 128-bit LDS (broadcast) -> 64 FFMA per 5 LDS, 8 shared-memory wavefronts
+// per 64 FFMA, every accumulator visiting its taps in order.  No block-wide barrier in the
+// main loop; warps whose window does not reach a chunk (or a group of 8 rows) skip it.
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -36,23 +43,11 @@ namespace {
 constexpr int NB = kOutputsPerBlock;  // 8
 constexpr int CJ = kChunkRows;        // 32
 constexpr int SGN = kSeriesPerRow;    // 128
-constexpr int XROW = SGN + 4;         // padded row: conflict-free transposing stores and 128-bit loads
 constexpr int STAGES = 3;
-constexpr int MAXC = kMaxChunksPerCta;   // chunk entries cached in shared memory per CTA
-constexpr int MAXP = kMaxPassesPerCta;   // passes per CTA
+constexpr int MAXC = kMaxChunksPerCta;  // chunk entries cached in shared memory per CTA
+constexpr int MAXP = kMaxPassesPerCta;  // passes per CTA
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t) __cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void cp_async_f32(float *dst_smem, const float *src, bool valid) {
-  const uint32_t d = smem_u32(dst_smem);
-  const int sz = valid ? 4 : 0;  // src-size 0 => zero fill
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;\n" ::"r"(d), "l"(src), "r"(sz) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() {
-  asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
-}
 
 __device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count) : "memory");
@@ -60,6 +55,9 @@ __device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes)
                : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
   const uint32_t a = smem_u32(bar);
@@ -130,26 +128,124 @@ __global__ void __launch_bounds__(256) espb_expand_kernel(const float *__restric
 }
 
 // ---------------------------------------------------------------------------------
+// Transposing stage: caller layout (stream-major, any strides) -> xt[group][row][128].
+// A CTA moves a 128-series x R-row tile through shared memory so that both the HBM reads
+// (along time within a stream) and the HBM writes (along series) are coalesced.  Frames
+// [j_begin, n_in) go to rows row_first + j; `pad_rows` rows after the input are zeroed
+// (chunks may read up to 31 rows past the last window).
+// ---------------------------------------------------------------------------------
+constexpr int TR_ROWS = 32;   // generic kernel
+constexpr int TF_ROWS = 64;   // fast kernel
+constexpr int TF_THREADS = 256;
+
+// Fast path: interleaved input (channel stride 1, frame stride CH) with CH in {1,2,4,8}, or planar
+// input (frame stride 1; CH = 1 and one "stream" per series), 16-byte aligned rows, full tiles only.
+// 128-bit loads along time, index arithmetic by shifts only.
+template <int CH, bool PLANAR>
+__global__ void __launch_bounds__(TF_THREADS)
+    espb_transpose_fast_kernel(const float *__restrict__ in, int64_t in_ss, int64_t in_cs, int channels,
+                               int n_series, float *__restrict__ xt, int64_t rows_cap, int row_first) {
+  __shared__ float tile[TF_ROWS][SGN + 1];
+  const int g = blockIdx.x;
+  const int j0 = blockIdx.y * TF_ROWS;
+  const int tid = threadIdx.x;
+  constexpr int UNITS = SGN / CH;         // contiguous runs per group (streams, or series when planar)
+  constexpr int V_PER_UNIT = TF_ROWS * CH / 4;  // float4 per run
+#pragma unroll 4
+  for (int v = tid; v < UNITS * V_PER_UNIT; v += TF_THREADS) {
+    const int unit = v / V_PER_UNIT, off4 = v % V_PER_UNIT;  // powers of two: shifts
+    const int q0 = g * SGN + unit * CH;                       // first series of the run
+    float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (q0 < n_series) {
+      const float *src;
+      if (PLANAR) {
+        const int st = q0 / channels, ch = q0 - st * channels;
+        src = in + (int64_t) st * in_ss + (int64_t) ch * in_cs + j0;
+      } else {
+        src = in + (int64_t) (q0 / CH) * in_ss + (int64_t) j0 * CH;
+      }
+      x = __ldg(reinterpret_cast<const float4 *>(src) + off4);
+    }
+    const int e0 = off4 * 4;
+    const float xv[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int e = e0 + k;
+      tile[e / CH][unit * CH + (e % CH)] = xv[k];
+    }
+  }
+  __syncthreads();
+  float4 *dst = reinterpret_cast<float4 *>(xt + ((int64_t) g * rows_cap + row_first + j0) * SGN);
+#pragma unroll 4
+  for (int i = tid; i < TF_ROWS * (SGN / 4); i += TF_THREADS) {
+    const int t = i / (SGN / 4), c4 = i % (SGN / 4);
+    dst[i] = make_float4(tile[t][c4 * 4], tile[t][c4 * 4 + 1], tile[t][c4 * 4 + 2], tile[t][c4 * 4 + 3]);
+  }
+}
+
+// Generic path: any strides / channel count / alignment, partial tiles and the zero padding.
+__global__ void __launch_bounds__(256)
+    espb_transpose_kernel(const float *__restrict__ in, int64_t in_ss, int64_t in_cs, int64_t in_fs, int channels,
+                          int n_series, int n_in, float *__restrict__ xt, int64_t rows_cap, int row_first,
+                          int j_begin, int pad_rows) {
+  __shared__ float tile[TR_ROWS][SGN + 1];
+  const int g = blockIdx.x;
+  const int j0 = j_begin + blockIdx.y * TR_ROWS;  // first input frame of this tile
+  const int tid = threadIdx.x;
+  const int total_rows = n_in + pad_rows;
+  // 0: frames contiguous (planar)  1: interleaved and the group covers whole streams  2: generic
+  const int mapping = (in_fs == 1) ? 0 : ((in_cs == 1 && in_fs == channels && SGN % channels == 0) ? 1 : 2);
+  for (int i = tid; i < SGN * TR_ROWS; i += 256) {
+    int sl, t;
+    if (mapping == 0) {
+      sl = i / TR_ROWS;
+      t = i - sl * TR_ROWS;
+    } else if (mapping == 1) {
+      const int per = TR_ROWS * channels;
+      const int stl = i / per, r = i - stl * per;
+      t = r / channels;
+      sl = stl * channels + (r - t * channels);
+    } else {
+      t = i / SGN;
+      sl = i - t * SGN;
+    }
+    const int q = g * SGN + sl, j = j0 + t;
+    float v = 0.0f;
+    if (q < n_series && j < n_in) {
+      const int st = q / channels, ch = q - st * channels;
+      v = __ldg(in + (int64_t) st * in_ss + (int64_t) ch * in_cs + (int64_t) j * in_fs);
+    }
+    tile[t][sl] = v;
+  }
+  __syncthreads();
+  float4 *dst = reinterpret_cast<float4 *>(xt + ((int64_t) g * rows_cap + row_first + j0) * SGN);
+  for (int i = tid; i < TR_ROWS * (SGN / 4); i += 256) {
+    const int t = i / (SGN / 4), c4 = i - t * (SGN / 4);
+    if (j0 + t < total_rows)
+      dst[i] = make_float4(tile[t][c4 * 4], tile[t][c4 * 4 + 1], tile[t][c4 * 4 + 2], tile[t][c4 * 4 + 3]);
+  }
+}
+
+// ---------------------------------------------------------------------------------
 // Resampler
 // ---------------------------------------------------------------------------------
 template <int BPP, bool EXACT>
-__global__ void __launch_bounds__(BPP * 32, (BPP <= 8 ? 2 : 1))
-    espb_resample_kernel(const ResampleParams p) {
-  constexpr int QPW = 32 / BPP;  // series quads staged per warp (x4 row groups each)
-  static_assert(32 % BPP == 0, "BPP must divide 32");
-  constexpr int XS_STAGE = CJ * XROW;             // floats
+__global__ void __maxnreg__(112) espb_resample_kernel(const ResampleParams p) {
+  constexpr int NTHREADS = (BPP + 1) * 32;
+  constexpr int XS_STAGE = CJ * SGN;                // floats
   constexpr int GS_STAGE = CJ * BPP * kGRowFloats;  // floats
-  constexpr uint32_t G_BYTES = GS_STAGE * sizeof(float);
+  constexpr uint32_t X_BYTES = XS_STAGE * sizeof(float), G_BYTES = GS_STAGE * sizeof(float);
 
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  float *gs = reinterpret_cast<float *>(smem_raw);               // [STAGES][CJ][BPP][16]
-  float *xs = gs + STAGES * GS_STAGE;                            // [STAGES][CJ][XROW]
-  uint64_t *gbar = reinterpret_cast<uint64_t *>(xs + STAGES * XS_STAGE);
-  ChunkEntry *ctab = reinterpret_cast<ChunkEntry *>(gbar + STAGES);  // [MAXC] this CTA's chunks
-  int2 *wtab = reinterpret_cast<int2 *>(ctab + MAXC);                // [MAXP][BPP] window [lo, hi) per (pass, warp)
+  float *gs = reinterpret_cast<float *>(smem_raw);                        // [STAGES][CJ][BPP][16]
+  float *xs = gs + STAGES * GS_STAGE;                                     // [STAGES][CJ][128]
+  uint64_t *full = reinterpret_cast<uint64_t *>(xs + STAGES * XS_STAGE);  // [STAGES] TMA landed
+  uint64_t *empty = full + STAGES;                                        // [STAGES] all consumers done
+  ChunkEntry *ctab = reinterpret_cast<ChunkEntry *>(empty + STAGES);      // [MAXC] this CTA's chunks
+  int2 *wtab = reinterpret_cast<int2 *>(ctab + MAXC);  // [MAXP][BPP] window [lo, hi) per (pass, warp)
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int series0 = blockIdx.x * SGN;
+  const int group = blockIdx.x;
   const int T = p.taps;
 
   // ---- which passes / chunks this CTA sweeps
@@ -160,10 +256,10 @@ __global__ void __launch_bounds__(BPP * 32, (BPP <= 8 ? 2 : 1))
   const int chunk_first = p.pass_chunk_begin[pass_first], chunk_last = p.pass_chunk_begin[pass_last];
   const int n_chunks = chunk_last - chunk_first;
 
-  // ---- cache the signal-independent tables this CTA needs (no dependent global loads in the main loop)
-  for (int i = tid; i < n_chunks; i += BPP * 32)
+  // ---- cache the signal-independent tables this CTA needs (no global loads in the main loop)
+  for (int i = tid; i < n_chunks; i += NTHREADS)
     ctab[i] = p.chunks[chunk_first + i];
-  for (int i = tid; i < (pass_last - pass_first) * BPP; i += BPP * 32) {
+  for (int i = tid; i < (pass_last - pass_first) * BPP; i += NTHREADS) {
     const int o0 = ((pass_first + i / BPP) * BPP + (i % BPP)) * NB;
     int2 w = make_int2(0, 0);
     if (o0 < p.n_out) {
@@ -173,99 +269,45 @@ __global__ void __launch_bounds__(BPP * 32, (BPP <= 8 ? 2 : 1))
     }
     wtab[i] = w;
   }
-
   if (tid == 0) {
 #pragma unroll
-    for (int s = 0; s < STAGES; ++s)
-      mbar_init(&gbar[s], 1);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], BPP);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
+  __syncthreads();
 
-  // ---- staging role: this thread copies, for QPW series quads, element `se` of the quad
-  //      at rows jl, jl+8, jl+16, jl+24 of every chunk
-  const int jl = lane >> 2, se = lane & 3;
-  const float *src_in[QPW];
-  bool series_ok[QPW];
-#pragma unroll
-  for (int q = 0; q < QPW; ++q) {
-    const int series = series0 + (warp * QPW + q) * 4 + se;
-    series_ok[q] = series < p.n_series;
-    const int sidx = series_ok[q] ? series : 0;
-    const int st = sidx / p.channels, ch = sidx - st * p.channels;
-    src_in[q] = p.in + (int64_t) st * p.in_ss + (int64_t) ch * p.in_cs;
+  const float *xt_group = p.xt + (int64_t) group * p.xt_rows * SGN;
+
+  if (warp == BPP) {
+    // ===================== producer: one lane streams the chunks with TMA =====================
+    if (lane == 0) {
+      for (int c = 0; c < n_chunks; ++c) {
+        const int st = c % STAGES, use = c / STAGES;
+        if (use > 0)
+          mbar_wait(&empty[st], (uint32_t) ((use - 1) & 1));  // all consumers released the previous use
+        mbar_expect_tx(&full[st], X_BYTES + G_BYTES);
+        tma_bulk_g2s(gs + st * GS_STAGE, p.G + (size_t) (chunk_first + c - p.g_chunk_base) * GS_STAGE, G_BYTES,
+                     &full[st]);
+        tma_bulk_g2s(xs + st * XS_STAGE, xt_group + (int64_t) (ctab[c].j_start + T) * SGN, X_BYTES, &full[st]);
+      }
+    }
+    return;
   }
-  __syncthreads();  // barrier init visible
 
-  auto stage_chunk = [&](int c) {  // c relative to chunk_first
-    const int st = c % STAGES;
-    const int gc = chunk_first + c;
-    const int j0 = ctab[c].j_start;
-    if (tid == 0) {
-      mbar_expect_tx(&gbar[st], G_BYTES);
-      tma_bulk_g2s(gs + st * GS_STAGE, p.G + (size_t) (gc - p.g_chunk_base) * GS_STAGE, G_BYTES, &gbar[st]);
-    }
-    // this thread's destination: row jl (+8 per step), column of series quad (warp*QPW + q), element se
-    float *xdst = xs + st * XS_STAGE + jl * XROW + warp * QPW * 4 + se;
-    if ((j0 >= 0) && (j0 + CJ <= p.n_in)) {  // chunk entirely inside this call's input: no per-row tests
-      const int64_t joff = (int64_t) (j0 + jl) * p.in_fs;
-      const int64_t step = (int64_t) 8 * p.in_fs;
-#pragma unroll
-      for (int q = 0; q < QPW; ++q) {
-        const float *src = src_in[q] + joff;
-#pragma unroll
-        for (int jb = 0; jb < CJ / 8; ++jb)
-          cp_async_f32(xdst + q * 4 + jb * 8 * XROW, src + jb * step, series_ok[q]);
-      }
-    } else {  // edges: rows before the call come from the carried history, rows past the input are zero
-#pragma unroll 1
-      for (int q = 0; q < QPW; ++q) {
-        const int series = series0 + (warp * QPW + q) * 4 + se;
-#pragma unroll 1
-        for (int jb = 0; jb < CJ / 8; ++jb) {
-          const int j = j0 + jb * 8 + jl;
-          const float *src = p.in;
-          bool ok = series_ok[q];
-          if (j >= 0) {
-            ok = ok && (j < p.n_in);
-            if (ok)
-              src = src_in[q] + (int64_t) j * p.in_fs;
-          } else {
-            ok = ok && (j >= -T);
-            if (ok)
-              src = p.hist + (int64_t) series * T + T + j;
-          }
-          cp_async_f32(xdst + q * 4 + jb * 8 * XROW, src, ok);
-        }
-      }
-    }
-  };
-
-  // ---- accumulators: [series e][output n][filter f]
-  float acc[4][NB][2];
+  // ===================== consumers =====================
+  float acc[4][NB][2];  // [series e][output n][filter f]
 #pragma unroll
   for (int e = 0; e < 4; ++e)
 #pragma unroll
     for (int n = 0; n < NB; ++n)
       acc[e][n][0] = acc[e][n][1] = 0.0f;
 
-  // prologue
-#pragma unroll
-  for (int s = 0; s < STAGES - 1; ++s) {
-    if (s < n_chunks)
-      stage_chunk(s);
-    cp_async_commit();
-  }
-
-  int cur_pass = -1, win_lo = 0, win_hi = 0;  // this warp's window [win_lo, win_hi) in input rows
+  int cur_pass = -1, win_lo = 0, win_hi = 0;  // this warp's window [win_lo, win_hi) in input frames
   for (int c = 0; c < n_chunks; ++c) {
     const int st = c % STAGES;
-    cp_async_wait<STAGES - 2>();
-    mbar_wait(&gbar[st], (uint32_t) ((c / STAGES) & 1));
-    __syncthreads();  // every thread's x copies of chunk c have landed; stage (c-1)%STAGES is free
-    if (c + STAGES - 1 < n_chunks)
-      stage_chunk(c + STAGES - 1);
-    cp_async_commit();
-
     const ChunkEntry ce = ctab[c];
     if (ce.pass != cur_pass) {
       cur_pass = ce.pass;
@@ -273,20 +315,21 @@ __global__ void __launch_bounds__(BPP * 32, (BPP <= 8 ? 2 : 1))
       win_lo = w.x;
       win_hi = w.y;
     }
-
     // rows of this chunk inside the warp's window, in groups of 8 (rows outside it only multiply zeros)
     int r0 = win_lo - ce.j_start, r1 = win_hi - ce.j_start;
     r0 = r0 < 0 ? 0 : (r0 >> 3);
     r1 = r1 > CJ ? CJ / 8 : ((r1 + 7) >> 3);
+
+    mbar_wait(&full[st], (uint32_t) ((c / STAGES) & 1));
     {
       const float *xrow = xs + st * XS_STAGE + lane * 4;
       const float *grow = gs + st * GS_STAGE + warp * kGRowFloats;
       for (int jb = r0; jb < r1; ++jb) {
-        const float *xb = xrow + jb * 8 * XROW;
+        const float *xb = xrow + jb * 8 * SGN;
         const float *gb = grow + jb * 8 * BPP * kGRowFloats;
 #pragma unroll
         for (int jj = 0; jj < 8; ++jj) {
-          const float4 xv = *reinterpret_cast<const float4 *>(xb + jj * XROW);
+          const float4 xv = *reinterpret_cast<const float4 *>(xb + jj * SGN);
           const float4 *gp = reinterpret_cast<const float4 *>(gb + jj * BPP * kGRowFloats);
           const float4 g0 = gp[0], g1 = gp[1], g2 = gp[2], g3 = gp[3];
           const float x4[4] = {xv.x, xv.y, xv.z, xv.w};
@@ -302,19 +345,21 @@ __global__ void __launch_bounds__(BPP * 32, (BPP <= 8 ? 2 : 1))
         }
       }
     }
+    __syncwarp();
+    if (lane == 0)
+      mbar_arrive(&empty[st]);  // this warp is done reading the stage
 
     // ---- end of pass: blend, store, clear
     const bool pass_done = (c + 1 == n_chunks) || (ctab[c + 1].pass != cur_pass);
     if (pass_done) {
       const int o0 = (cur_pass * BPP + warp) * NB;
-      int64_t in_off[4], out_off[4];
+      int64_t out_off[4];
       bool live[4];
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        const int series = series0 + lane * 4 + e;
+        const int series = group * SGN + lane * 4 + e;
         live[e] = series < p.n_series;
         const int sidx = series / p.channels, ch = series - sidx * p.channels;
-        in_off[e] = (int64_t) sidx * p.in_ss + (int64_t) ch * p.in_cs;
         out_off[e] = (int64_t) sidx * p.out_ss + (int64_t) ch * p.out_cs;
       }
 #pragma unroll
@@ -330,14 +375,7 @@ __global__ void __launch_bounds__(BPP * 32, (BPP <= 8 ? 2 : 1))
             } else if (en.kind == kKindSingle) {
               v = acc[e][n][0];
             } else {  // pass-through: *source (art_resampler.cpp:426,440) = tap numTaps/2-1 of the window
-              const int j = en.ws + T / 2 - 1;
-              v = 0.0f;
-              if (live[e]) {
-                if (j >= 0)
-                  v = (j < p.n_in) ? p.in[in_off[e] + (int64_t) j * p.in_fs] : 0.0f;
-                else if (j >= -T)
-                  v = p.hist[(int64_t) (series0 + lane * 4 + e) * T + T + j];
-              }
+              v = xt_group[(int64_t) (en.ws + T / 2 - 1 + T) * SGN + lane * 4 + e];
             }
             if (live[e])
               p.out[out_off[e] + (int64_t) o * p.out_fs] = v;
@@ -351,36 +389,13 @@ __global__ void __launch_bounds__(BPP * 32, (BPP <= 8 ? 2 : 1))
           acc[e][n][0] = acc[e][n][1] = 0.0f;
     }
   }
-  cp_async_wait<0>();
-}
-
-// ---------------------------------------------------------------------------------
-// History carry: the last `taps` consumed frames of every series (reference keeps them
-// at the front of the ring, art_resampler.cpp:216-222).  hist layout: [series][taps].
-// ---------------------------------------------------------------------------------
-__global__ void espb_history_kernel(const float *__restrict__ in, int64_t in_ss, int64_t in_cs, int64_t in_fs,
-                                    const float *__restrict__ hist_old, float *__restrict__ hist_new, int n_series,
-                                    int channels, int taps, int used) {
-  const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (int64_t) n_series * taps)
-    return;
-  const int series = (int) (i / taps), t = (int) (i - (int64_t) series * taps);
-  const int u = used - taps + t;  // frame index relative to this call's input
-  float v;
-  if (u >= 0) {
-    const int st = series / channels, ch = series - st * channels;
-    v = in[(int64_t) st * in_ss + (int64_t) ch * in_cs + (int64_t) u * in_fs];
-  } else {
-    v = (taps + u >= 0) ? hist_old[(int64_t) series * taps + taps + u] : 0.0f;
-  }
-  hist_new[i] = v;
 }
 
 // ---------------------------------------------------------------------------------
 // launchers
 // ---------------------------------------------------------------------------------
 size_t resample_smem_bytes(int bpp) {
-  return (size_t) STAGES * (CJ * bpp * kGRowFloats + CJ * XROW) * sizeof(float) + STAGES * sizeof(uint64_t) +
+  return (size_t) STAGES * (CJ * bpp * kGRowFloats + CJ * SGN) * sizeof(float) + 2 * STAGES * sizeof(uint64_t) +
          MAXC * sizeof(ChunkEntry) + (size_t) MAXP * bpp * sizeof(int2);
 }
 
@@ -392,6 +407,55 @@ cudaError_t launch_expand(const float *bank, const OutEntry *outs, const ChunkEn
     return cudaSuccess;
   espb_expand_kernel<<<n_chunks, 256, 0, stream>>>(bank, outs, chunks, G, chunk_first, n_out, taps, bpp);
   count_launch();
+  return cudaGetLastError();
+}
+
+cudaError_t launch_transpose(const float *in, int64_t in_ss, int64_t in_cs, int64_t in_fs, int channels, int n_series,
+                             int n_in, float *xt, int64_t rows_cap, int row_first, int pad_rows,
+                             cudaStream_t stream) {
+  const int n_groups = (n_series + SGN - 1) / SGN;
+  if (n_groups <= 0 || n_in + pad_rows <= 0)
+    return cudaSuccess;
+  // full 64-row tiles through the fast kernel when the layout allows it
+  int fast_rows = 0;
+  const bool aligned = ((uintptr_t) in % 16 == 0) && (in_ss % 4 == 0);
+  const bool interleaved = (in_cs == 1 && in_fs == channels);
+  const bool planar = (in_fs == 1) && (in_cs % 4 == 0);
+  if (aligned && n_in >= TF_ROWS) {
+    dim3 grid(n_groups, n_in / TF_ROWS);
+    bool done = true;
+    if (interleaved && channels == 1)
+      espb_transpose_fast_kernel<1, false><<<grid, TF_THREADS, 0, stream>>>(in, in_ss, in_cs, channels, n_series, xt,
+                                                                            rows_cap, row_first);
+    else if (interleaved && channels == 2)
+      espb_transpose_fast_kernel<2, false><<<grid, TF_THREADS, 0, stream>>>(in, in_ss, in_cs, channels, n_series, xt,
+                                                                            rows_cap, row_first);
+    else if (interleaved && channels == 4)
+      espb_transpose_fast_kernel<4, false><<<grid, TF_THREADS, 0, stream>>>(in, in_ss, in_cs, channels, n_series, xt,
+                                                                            rows_cap, row_first);
+    else if (interleaved && channels == 8)
+      espb_transpose_fast_kernel<8, false><<<grid, TF_THREADS, 0, stream>>>(in, in_ss, in_cs, channels, n_series, xt,
+                                                                            rows_cap, row_first);
+    else if (planar)
+      espb_transpose_fast_kernel<1, true><<<grid, TF_THREADS, 0, stream>>>(in, in_ss, in_cs, channels, n_series, xt,
+                                                                           rows_cap, row_first);
+    else
+      done = false;
+    if (done) {
+      count_launch();
+      fast_rows = (n_in / TF_ROWS) * TF_ROWS;
+      cudaError_t e = cudaGetLastError();
+      if (e != cudaSuccess)
+        return e;
+    }
+  }
+  const int rest = n_in + pad_rows - fast_rows;
+  if (rest > 0) {
+    dim3 grid(n_groups, (rest + TR_ROWS - 1) / TR_ROWS);
+    espb_transpose_kernel<<<grid, 256, 0, stream>>>(in, in_ss, in_cs, in_fs, channels, n_series, n_in, xt, rows_cap,
+                                                    row_first, fast_rows, pad_rows);
+    count_launch();
+  }
   return cudaGetLastError();
 }
 
@@ -407,7 +471,7 @@ static cudaError_t launch_resample_t(const ResampleParams &p, int n_groups, int 
     configured = true;
   }
   dim3 grid(n_groups, n_ctas_y);
-  espb_resample_kernel<BPP, EXACT><<<grid, BPP * 32, smem, stream>>>(p);
+  espb_resample_kernel<BPP, EXACT><<<grid, (BPP + 1) * 32, smem, stream>>>(p);
   count_launch();
   return cudaGetLastError();
 }
@@ -425,18 +489,6 @@ cudaError_t launch_resample(const ResampleParams &p, int bpp, bool exact, cudaSt
     return exact ? launch_resample_t<4, true>(p, n_groups, n_ctas_y, stream)
                  : launch_resample_t<4, false>(p, n_groups, n_ctas_y, stream);
   return cudaErrorInvalidValue;
-}
-
-cudaError_t launch_history(const float *in, int64_t in_ss, int64_t in_cs, int64_t in_fs, const float *hist_old,
-                           float *hist_new, int n_series, int channels, int taps, int used, cudaStream_t stream) {
-  const int64_t total = (int64_t) n_series * taps;
-  if (total <= 0)
-    return cudaSuccess;
-  const int threads = 256;
-  espb_history_kernel<<<(unsigned) ((total + threads - 1) / threads), threads, 0, stream>>>(
-      in, in_ss, in_cs, in_fs, hist_old, hist_new, n_series, channels, taps, used);
-  count_launch();
-  return cudaGetLastError();
 }
 
 }  // namespace espb
