@@ -21,10 +21,11 @@
 //
 // Kernel.  A CTA owns one group (128 series) and sweeps "passes" of BPP consecutive output
 // blocks (8 outputs each, one block per consumer warp) over the union of their windows in
-// chunks of 32 rows.  Warp BPP is the producer: one elected lane streams the chunks through
-// a 3-stage shared-memory ring with two TMA bulk copies per chunk (cp.async.bulk ->
-// mbarrier complete_tx; SASS UBLKCP), throttled by per-stage "empty" mbarriers.  The BPP
-// consumer warps wait on the "full" mbarrier, and per input row do the rank-1 update
+// chunks of 32 rows, streamed through a 3-stage shared-memory ring with two TMA bulk copies
+// per chunk (cp.async.bulk -> mbarrier complete_tx; SASS UBLKCP).  There is no producer
+// warp (a ninth warp would not fit twice per SM next to 128-register consumers): the last
+// warp to finish reading a stage re-arms its mbarrier and issues the refill.  The BPP
+// warps wait on the stage's "full" mbarrier, and per input row do the rank-1 update
 //     acc[series e][n][f] += G[row][n][f] * x[row][series e]
 // of a 4-series x 8-output x 2-filter register tile: x is one per-lane 128-bit LDS, G four
 // warp-uniform 128-bit LDS (broadcast) -> 64 FFMA per 5 LDS, 8 shared-memory wavefronts
@@ -32,6 +33,8 @@
 // main loop; warps whose window does not reach a chunk (or a group of 8 rows) skip it.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
 
 #include "common.hpp"
 #include "kernels.hpp"
@@ -55,9 +58,6 @@ __device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes)
                : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
   const uint32_t a = smem_u32(bar);
@@ -230,8 +230,8 @@ __global__ void __launch_bounds__(256)
 // Resampler
 // ---------------------------------------------------------------------------------
 template <int BPP, bool EXACT>
-__global__ void __maxnreg__(112) espb_resample_kernel(const ResampleParams p) {
-  constexpr int NTHREADS = (BPP + 1) * 32;
+__global__ void __launch_bounds__(BPP * 32, 2) espb_resample_kernel(const ResampleParams p) {
+  constexpr int NTHREADS = BPP * 32;
   constexpr int XS_STAGE = CJ * SGN;                // floats
   constexpr int GS_STAGE = CJ * BPP * kGRowFloats;  // floats
   constexpr uint32_t X_BYTES = XS_STAGE * sizeof(float), G_BYTES = GS_STAGE * sizeof(float);
@@ -240,8 +240,8 @@ __global__ void __maxnreg__(112) espb_resample_kernel(const ResampleParams p) {
   float *gs = reinterpret_cast<float *>(smem_raw);                        // [STAGES][CJ][BPP][16]
   float *xs = gs + STAGES * GS_STAGE;                                     // [STAGES][CJ][128]
   uint64_t *full = reinterpret_cast<uint64_t *>(xs + STAGES * XS_STAGE);  // [STAGES] TMA landed
-  uint64_t *empty = full + STAGES;                                        // [STAGES] all consumers done
-  ChunkEntry *ctab = reinterpret_cast<ChunkEntry *>(empty + STAGES);      // [MAXC] this CTA's chunks
+  int *done = reinterpret_cast<int *>(full + STAGES);                     // [2*STAGES] warps done with a stage
+  ChunkEntry *ctab = reinterpret_cast<ChunkEntry *>(done + 2 * STAGES);   // [MAXC] this CTA's chunks
   int2 *wtab = reinterpret_cast<int2 *>(ctab + MAXC);  // [MAXP][BPP] window [lo, hi) per (pass, warp)
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -273,31 +273,26 @@ __global__ void __maxnreg__(112) espb_resample_kernel(const ResampleParams p) {
 #pragma unroll
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full[s], 1);
-      mbar_init(&empty[s], BPP);
+      done[s] = 0;
     }
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   __syncthreads();
 
   const float *xt_group = p.xt + (int64_t) group * p.xt_rows * SGN;
+  const float *g_base = p.G + (size_t) (chunk_first - p.g_chunk_base) * GS_STAGE;
 
-  if (warp == BPP) {
-    // ===================== producer: one lane streams the chunks with TMA =====================
-    if (lane == 0) {
-      for (int c = 0; c < n_chunks; ++c) {
-        const int st = c % STAGES, use = c / STAGES;
-        if (use > 0)
-          mbar_wait(&empty[st], (uint32_t) ((use - 1) & 1));  // all consumers released the previous use
-        mbar_expect_tx(&full[st], X_BYTES + G_BYTES);
-        tma_bulk_g2s(gs + st * GS_STAGE, p.G + (size_t) (chunk_first + c - p.g_chunk_base) * GS_STAGE, G_BYTES,
-                     &full[st]);
-        tma_bulk_g2s(xs + st * XS_STAGE, xt_group + (int64_t) (ctab[c].j_start + T) * SGN, X_BYTES, &full[st]);
-      }
-    }
-    return;
-  }
+  // Fill stage c % STAGES with chunk c: two TMA bulk copies (16 KB of G, 16 KB of x) on one mbarrier.
+  auto issue_chunk = [&](int c) {
+    const int st = c % STAGES;
+    mbar_expect_tx(&full[st], X_BYTES + G_BYTES);
+    tma_bulk_g2s(gs + st * GS_STAGE, g_base + (size_t) c * GS_STAGE, G_BYTES, &full[st]);
+    tma_bulk_g2s(xs + st * XS_STAGE, xt_group + (int64_t) (ctab[c].j_start + T) * SGN, X_BYTES, &full[st]);
+  };
+  if (tid == 0)
+    for (int c = 0; c < STAGES && c < n_chunks; ++c)
+      issue_chunk(c);
 
-  // ===================== consumers =====================
   float acc[4][NB][2];  // [series e][output n][filter f]
 #pragma unroll
   for (int e = 0; e < 4; ++e)
@@ -345,9 +340,18 @@ __global__ void __maxnreg__(112) espb_resample_kernel(const ResampleParams p) {
         }
       }
     }
+    // Release the stage.  The last of the BPP warps to get here re-arms it and issues the refill
+    // (chunk c + STAGES); nobody waits for anybody.
     __syncwarp();
-    if (lane == 0)
-      mbar_arrive(&empty[st]);  // this warp is done reading the stage
+    if (lane == 0) {
+      __threadfence_block();  // this warp's reads of the stage are performed before the count moves
+      if (atomicAdd(&done[st], 1) == BPP - 1) {
+        done[st] = 0;
+        __threadfence_block();
+        if (c + STAGES < n_chunks)
+          issue_chunk(c + STAGES);
+      }
+    }
 
     // ---- end of pass: blend, store, clear
     const bool pass_done = (c + 1 == n_chunks) || (ctab[c + 1].pass != cur_pass);
@@ -395,8 +399,8 @@ __global__ void __maxnreg__(112) espb_resample_kernel(const ResampleParams p) {
 // launchers
 // ---------------------------------------------------------------------------------
 size_t resample_smem_bytes(int bpp) {
-  return (size_t) STAGES * (CJ * bpp * kGRowFloats + CJ * SGN) * sizeof(float) + 2 * STAGES * sizeof(uint64_t) +
-         MAXC * sizeof(ChunkEntry) + (size_t) MAXP * bpp * sizeof(int2);
+  return (size_t) STAGES * (CJ * bpp * kGRowFloats + CJ * SGN) * sizeof(float) + STAGES * sizeof(uint64_t) +
+         2 * STAGES * sizeof(int) + MAXC * sizeof(ChunkEntry) + (size_t) MAXP * bpp * sizeof(int2);
 }
 
 size_t g_chunk_floats(int bpp) { return (size_t) CJ * bpp * kGRowFloats; }
@@ -468,10 +472,23 @@ static cudaError_t launch_resample_t(const ResampleParams &p, int n_groups, int 
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
     if (e != cudaSuccess)
       return e;
+    // two CTAs per SM need the full 228 KB carve-out (the default heuristic sizes it for one)
+    e = cudaFuncSetAttribute(espb_resample_kernel<BPP, EXACT>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                             (int) cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess)
+      return e;
     configured = true;
+    if (getenv("ESPB_DEBUG")) {
+      int nb = 0;
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, espb_resample_kernel<BPP, EXACT>, BPP * 32, smem);
+      cudaFuncAttributes fa;
+      cudaFuncGetAttributes(&fa, espb_resample_kernel<BPP, EXACT>);
+      fprintf(stderr, "[espb] resample<%d,%d>: smem %zu B dyn + %zu static, %d regs, max threads %d, occupancy %d CTA/SM\n",
+              BPP, (int) EXACT, smem, fa.sharedSizeBytes, fa.numRegs, fa.maxThreadsPerBlock, nb);
+    }
   }
   dim3 grid(n_groups, n_ctas_y);
-  espb_resample_kernel<BPP, EXACT><<<grid, (BPP + 1) * 32, smem, stream>>>(p);
+  espb_resample_kernel<BPP, EXACT><<<grid, BPP * 32, smem, stream>>>(p);
   count_launch();
   return cudaGetLastError();
 }
