@@ -230,7 +230,7 @@ def main():
     in_row, out_row = N_IN * CHANNELS, cap * CHANNELS
 
     # ---- synthetic input in pinned host memory, then resident in HBM
-    x = synth_streams(ns, N_IN, rank)
+    x = synth_streams(ns, N_IN, rank)  # rank r owns global streams [r*ns, (r+1)*ns)
     h_in = espb.PinnedBuffer(ns * in_row, f32)
     h_in.array[:] = x.reshape(-1)
     del x
@@ -296,15 +296,12 @@ def main():
     value = samples_per_step / (ms_per_step * 1e-3) / 1e6
 
     # ---- correctness guard inside the bench: a sampled stream against the oracle, checksum for the gather
-    checksum = espb.checksum_u32(d_out.ptr, ns * out_row, stream)
-    if dist:
-        import torch
-        mine = torch.tensor([checksum & 0x7FFFFFFFFFFFFFFF, gen], dtype=torch.int64, device="cuda")
-        gathered = [torch.zeros_like(mine) for _ in range(world)]
-        dist.all_gather(gathered, mine)  # NCCL: the only collective, after the timed region
-        checksums = [int(g[0].item()) for g in gathered]
-    else:
-        checksums = [checksum & 0x7FFFFFFFFFFFFFFF]
+    checksum = espb.checksum_u32(d_out.ptr, ns * out_row, stream) & 0x7FFFFFFFFFFFFFFF
+    first_stream, _ = espb.shard_range(ns * world, rank, world)
+    # NCCL: the only collective, after the timed region — per-rank checksum, frames, first stream index
+    gathered = espb.gather_words([checksum, gen, first_stream], dist, device="cuda" if dist else None)
+    checksums = [g[0] for g in gathered]
+    assert [g[2] for g in gathered] == [espb.shard_range(ns * world, r, world)[0] for r in range(world)]
 
     # ---- roofline of the dominant kernel (espb_resample_kernel), from its own CUDA events
     k_ms = kernel_ms / max(kernel_launches, 1)
@@ -393,7 +390,7 @@ def main():
                        "timed_region": "per step: reset, host schedule, table upload, coefficient expansion, "
                                        "resampler kernel, history carry (plan cache off)"},
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches),
-            "clocks": clocks, "checksums": checksums, "device": info["name"], "sm_count": info["sm_count"],
+            "clocks": clocks, "checksums": checksums, "checksum_of_checksums": espb.combine_checksums(checksums), "device": info["name"], "sm_count": info["sm_count"],
         }
         print(json.dumps(line), flush=True)
     if dist:

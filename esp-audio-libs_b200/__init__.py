@@ -11,3 +11,4 @@ from .capi import (BLACKMAN_HARRIS, INCLUDE_LOWPASS, MODE_EXACT, MODE_FAST, OPT_
                    biquad_lowpass, checksum_u32, declared_symbols, device_count, device_info, float_to_quantized,
                    launch_count, lib, library_path, measure_fp32_fma_peak, plan_filter_bank, plan_policy,
                    plan_schedule, quantized_to_float, set_device)
+from .sharding import combine_checksums, gather_words, shard_range  # noqa: F401,E402

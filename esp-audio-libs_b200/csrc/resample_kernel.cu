@@ -81,6 +81,15 @@ __device__ __forceinline__ void tma_bulk_g2s(void *dst_smem, const void *src, ui
                : "memory");
 }
 
+// Counting arrival on a shared-memory word with acquire-release semantics at CTA scope: the
+// caller's earlier shared-memory reads are ordered before it, and whoever sees the last count
+// sees them done — no separate (sequentially consistent) fence needed.
+__device__ __forceinline__ int smem_arrive_acq_rel(int *counter) {
+  int old;
+  asm volatile("atom.acq_rel.cta.shared::cta.add.s32 %0, [%1], 1;\n" : "=r"(old) : "r"(smem_u32(counter)) : "memory");
+  return old;
+}
+
 template <bool EXACT>
 __device__ __forceinline__ float mac(float g, float x, float acc) {
   if (EXACT)
@@ -344,10 +353,8 @@ __global__ void __launch_bounds__(BPP * 32, 2) espb_resample_kernel(const Resamp
     // (chunk c + STAGES); nobody waits for anybody.
     __syncwarp();
     if (lane == 0) {
-      __threadfence_block();  // this warp's reads of the stage are performed before the count moves
-      if (atomicAdd(&done[st], 1) == BPP - 1) {
-        done[st] = 0;
-        __threadfence_block();
+      if (smem_arrive_acq_rel(&done[st]) == BPP - 1) {
+        done[st] = 0;  // published to the other warps by the release of the mbarrier arrive below
         if (c + STAGES < n_chunks)
           issue_chunk(c + STAGES);
       }
