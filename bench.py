@@ -162,7 +162,7 @@ def cpu_reference_arm(n_streams, n_in, threads, reps=1):
                       f"{threads} host threads, processing time only"}
 
 
-def run_reference(args):
+def run_reference(args, out):
     """--impl reference: the reference's CPU path on the host cores, same config/metric."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -188,8 +188,17 @@ def run_reference(args):
         "e2e": {"value": msps, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0, "wall_s": wall,
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=out, flush=True)
     return 0
+
+
+def protect_stdout():
+    """The contract is ONE JSON line on stdout.  Native libraries (NCCL prints its version there) write
+    to fd 1 directly, so fd 1 is pointed at stderr and the JSON line goes to a private copy of stdout."""
+    sys.stdout.flush()
+    real = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    return real
 
 
 def main():
@@ -202,8 +211,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
+    out = protect_stdout()
     if args.impl == "reference":
-        return run_reference(args)
+        return run_reference(args, out)
     if args.warmup < 3:
         args.warmup = 3  # timing rule: at least 3 warm-up steps
 
@@ -392,7 +402,7 @@ def main():
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches),
             "clocks": clocks, "checksums": checksums, "checksum_of_checksums": espb.combine_checksums(checksums), "device": info["name"], "sm_count": info["sm_count"],
         }
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=out, flush=True)
     if dist:
         dist.destroy_process_group()
     return 0
