@@ -310,6 +310,8 @@ struct EspbResampleBatch {
   int xt_cur = 0;
   int64_t xt_rows = 0;  // rows per group in both buffers
   int carry_row = 0;
+  DevBuf yt;  // time-major output scratch [group][yt_rows][128] when a library stage follows the resampler
+  int64_t yt_rows = 0;
   int n_groups() const { return (n_series() + kSeriesPerRow - 1) / kSeriesPerRow; }
   // per-call plan, cached by (state, n_in, n_out, ratio)
   Schedule sched;
@@ -469,10 +471,20 @@ int ensure_xt(EspbResampleBatch *c, int64_t rows) {
   return ESPB_OK;
 }
 
+// Optional in-library neighbours of the resampler (Resampler::resample's pre / post low-pass).
+struct StageFilter {
+  const BiquadParams *params = nullptr;  // NULL: no filter
+  float *state = nullptr;                // [series][sections][4] of the first series of the range
+  int sections = 0;
+};
+
 // Stage + resample series [series_first, series_first + n_series) of the batch (series_first is a
-// multiple of 128).  The carried frames and the new input go to the spare staging buffer.
+// multiple of 128).  The carried frames and the new input go to the spare staging buffer.  `pre`
+// filters the staged input in place (time-major); with `post` the resampler writes time-major
+// scratch, which is filtered and then laid out as the caller wants.
 int run_series_range(EspbResampleBatch *c, int series_first, int n_series, const float *in, const EspbLayout &il,
-                     float *out, const EspbLayout &ol, int n_in, cudaStream_t stream, bool g_preexpanded) {
+                     float *out, const EspbLayout &ol, int n_in, cudaStream_t stream, bool g_preexpanded,
+                     const StageFilter *pre = nullptr, const StageFilter *post = nullptr) {
   const int taps = c->geo.taps;
   const int g0 = series_first / kSeriesPerRow, ng = (n_series + kSeriesPerRow - 1) / kSeriesPerRow;
   const int64_t rows = c->xt_rows;
@@ -485,8 +497,17 @@ int run_series_range(EspbResampleBatch *c, int series_first, int n_series, const
   CU_TRY(launch_transpose(in, il.stream_stride, il.channel_stride, il.frame_stride, c->channels, n_series, n_in,
                           x_new, rows, taps, kChunkRows, stream),
          "transpose kernel");
+  if (pre && pre->params && n_in > 0)  // resampler.cpp:126-133, on the staged rows [taps, taps + n_in)
+    CU_TRY(launch_biquad_tm(x_new, rows, taps, n_in, n_series, pre->sections, *pre->params, pre->state, stream),
+           "biquad kernel");
+  const bool post_on = post && post->params && c->sched.generated > 0;
+  float *y_tm = nullptr;
+  if (post_on)
+    y_tm = c->yt.as<float>() + (size_t) g0 * c->yt_rows * kSeriesPerRow;
   if (c->sched.generated > 0) {
     ResampleParams p{};
+    p.out_tm = y_tm;
+    p.out_tm_rows = c->yt_rows;
     p.xt = x_new;
     p.xt_rows = rows;
     p.out = out;
@@ -531,6 +552,23 @@ int run_series_range(EspbResampleBatch *c, int series_first, int n_series, const
         CU_TRY(cudaEventRecord(ev_after, stream), "cudaEventRecord");
     }
   }
+  if (post_on) {  // resampler.cpp:142-149, then back to the caller's layout
+    const int gen = (int) c->sched.generated;
+    CU_TRY(launch_biquad_tm(y_tm, c->yt_rows, 0, gen, n_series, post->sections, *post->params, post->state, stream),
+           "biquad kernel");
+    CU_TRY(launch_untranspose(y_tm, c->yt_rows, 0, gen, out, ol.stream_stride, ol.channel_stride, ol.frame_stride,
+                              c->channels, n_series, stream),
+           "untranspose kernel");
+  }
+  return ESPB_OK;
+}
+
+// Scratch for time-major resampler output (post-filter path): at least `rows` rows per group.
+int ensure_yt(EspbResampleBatch *c, int64_t rows) {
+  if (rows <= c->yt_rows)
+    return ESPB_OK;
+  CU_TRY(c->yt.reserve((size_t) c->n_groups() * rows * kSeriesPerRow * sizeof(float)), "output scratch");
+  c->yt_rows = rows;
   return ESPB_OK;
 }
 
@@ -593,6 +631,7 @@ void espb_resampleFree(EspbResampleBatch *c) {
   c->bank.release();
   c->xt[0].release();
   c->xt[1].release();
+  c->yt.release();
   c->d_outs.release();
   c->d_chunks.release();
   c->d_pcb.release();
@@ -840,6 +879,8 @@ struct EspbBiquadBatch {
   int num_series = 0, num_sections = 0;
   BiquadParams params{};
   DevBuf state;
+  DevBuf tm;  // time-major scratch [group][tm_rows][128] for the stand-alone apply_buffer entry point
+  int64_t tm_rows = 0;
 };
 
 extern "C" {
@@ -880,6 +921,7 @@ EspbBiquadBatch *espb_biquad_init(int num_series, int num_sections, const EspbBi
 void espb_biquad_free(EspbBiquadBatch *f) {
   if (!f)
     return;
+  f->tm.release();
   f->state.release();
   delete f;
 }
@@ -897,10 +939,24 @@ int espb_biquad_apply_buffer(EspbBiquadBatch *f, float *buf, const EspbLayout *l
                              void *stream) {
   if (!f || !layout || channels <= 0)
     return fail(ESPB_ERR_ARG, "biquad_apply_buffer: bad arguments");
-  CU_TRY(launch_biquad(buf, layout->stream_stride, layout->channel_stride, layout->frame_stride, channels,
-                       f->num_series, f->num_sections, num_samples, f->params, f->state.as<float>(),
-                       as_stream(stream)),
+  if (num_samples <= 0)
+    return ESPB_OK;
+  // caller layout -> time-major scratch -> filter in place -> back; all three are full-bandwidth passes
+  const int n_groups = (f->num_series + kSeriesPerRow - 1) / kSeriesPerRow;
+  if (num_samples > f->tm_rows) {
+    CU_TRY(f->tm.reserve((size_t) n_groups * num_samples * kSeriesPerRow * sizeof(float)), "biquad scratch");
+    f->tm_rows = num_samples;
+  }
+  cudaStream_t s = as_stream(stream);
+  CU_TRY(launch_transpose(buf, layout->stream_stride, layout->channel_stride, layout->frame_stride, channels,
+                          f->num_series, num_samples, f->tm.as<float>(), f->tm_rows, 0, 0, s),
+         "transpose kernel");
+  CU_TRY(launch_biquad_tm(f->tm.as<float>(), f->tm_rows, 0, num_samples, f->num_series, f->num_sections, f->params,
+                          f->state.as<float>(), s),
          "biquad kernel");
+  CU_TRY(launch_untranspose(f->tm.as<float>(), f->tm_rows, 0, num_samples, buf, layout->stream_stride,
+                            layout->channel_stride, layout->frame_stride, channels, f->num_series, s),
+         "untranspose kernel");
   return ESPB_OK;
 }
 
@@ -1134,17 +1190,17 @@ int wrapper_run_range(EspbResampler *r, int s0, int ns, const uint8_t *d_in, int
   if (rs) {
     EspbLayout il = {(int64_t) r->in_samples, 1, ch}, ol = {(int64_t) r->out_samples, 1, ch};
     EspbBiquadBatch *lp = r->lowpass;
-    if (r->policy.pre && wc.todo)  // :126-133
-      CU_TRY(launch_biquad(fin, il.stream_stride, 1, ch, ch, ns * ch, lp->num_sections, (int) wc.todo, lp->params,
-                           lp->state.as<float>() + (size_t) s0 * ch * lp->num_sections * 4, stream),
-             "biquad kernel");
-    int rc = run_series_range(r->art, s0 * ch, ns * ch, fin, il, fout, ol, (int) wc.todo, stream, g_preexpanded);
+    StageFilter flt;
+    if (lp) {
+      flt.params = &lp->params;
+      flt.state = lp->state.as<float>() + (size_t) s0 * ch * lp->num_sections * 4;
+      flt.sections = lp->num_sections;
+    }
+    // :126-149 — pre-filter, resampleProcessInterleaved, post-filter
+    int rc = run_series_range(r->art, s0 * ch, ns * ch, fin, il, fout, ol, (int) wc.todo, stream, g_preexpanded,
+                              r->policy.pre ? &flt : nullptr, r->policy.post ? &flt : nullptr);
     if (rc != ESPB_OK)
       return rc;
-    if (r->policy.post && wc.generated)  // :142-149
-      CU_TRY(launch_biquad(fout, ol.stream_stride, 1, ch, ch, ns * ch, lp->num_sections, (int) wc.generated,
-                           lp->params, lp->state.as<float>() + (size_t) s0 * ch * lp->num_sections * 4, stream),
-             "biquad kernel");
   }
   (void) out_free;
   // :152-153 float_to_quantized + clip count
@@ -1176,6 +1232,11 @@ int wrapper_plan(EspbResampler *r, size_t avail, size_t out_free, cudaStream_t s
       return rc;
     wc->used = r->art->sched.used;
     wc->generated = r->art->sched.generated;
+    if (r->policy.post) {
+      rc = ensure_yt(r->art, (int64_t) wc->generated);
+      if (rc != ESPB_OK)
+        return rc;
+    }
     if (wc->generated * ch > r->out_samples)
       return fail(ESPB_ERR_ARG, "resample: output exceeds the float buffer size given at construction");
   }

@@ -1,40 +1,78 @@
-// art_biquad on the device: Direct-Form-I sections, sequential in time, one thread per
-// series (stream x channel), thousands of series in flight.
+// art_biquad on the device: Direct-Form-I sections, sequential in time, one thread per series
+// (stream x channel), thousands of series in flight.
 //
 // Reference: src/resample/art_biquad.cpp:73-93 (biquad_apply_buffer) — the sum
 //   x*a0 + in_d1*a1 + in_d2*a2 - b1*out_d1 - b2*out_d2
-// is evaluated left to right with every product and sum rounded (no FMA): contraction
-// moves the result by up to 1.8e-6, so only __fmul_rn/__fadd_rn/
-// __fsub_rn are used.  Cascaded sections are applied per sample instead of as separate
-// buffer passes; the arithmetic per section is unchanged, so the result is bit-identical.
+// is evaluated left to right with every product and sum rounded (no FMA): contraction moves the
+// result by up to 1.8e-6, so only __fmul_rn/__fadd_rn/__fsub_rn are used.
+// Cascaded sections are applied per sample instead of as separate buffer passes; the arithmetic
+// per section is unchanged, so the result is bit-identical.
 //
-// Data movement: a CTA owns 32 consecutive series and walks time in tiles of 32 frames
-// staged through shared memory, so that HBM sees the reference layout (stream-major,
-// channels interleaved) as coalesced row segments while each thread reads its own series.
+// Data movement.  The recurrence is latency-bound (~12 cycles per section per sample) and cannot
+// be parallelised in time without changing the arithmetic, so everything else must stay off its
+// critical path.  The kernel works on the time-major layout  buf[group][row][128 series]  (the
+// resampler's own staging layout): a CTA of 128 threads owns a group, 32-row chunks (16 KB,
+// contiguous) are streamed through a 4-stage shared-memory ring by TMA bulk loads, filtered in
+// place by the thread that owns the column, and written back by TMA bulk stores — HBM sees only
+// full 16 KB transfers, the threads only conflict-free LDS/STS.
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "common.hpp"
 #include "kernels.hpp"
 
 namespace espb {
 
 namespace {
 
-constexpr int kMaxSections = 4;
-constexpr int BQ_SERIES = 32;  // series per CTA (one warp does the recurrences)
-constexpr int BQ_TILE = 64;    // frames per tile
-constexpr int BQ_THREADS = 128;
+constexpr int SGN = kSeriesPerRow;  // 128
+constexpr int RB = 32;              // rows per chunk
+constexpr int BSTAGES = 4;
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t) __cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load(void *dst_smem, const void *src, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
+                   smem_u32(dst_smem)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tma_store(void *dst, const void *src_smem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n" ::"l"(dst), "r"(smem_u32(src_smem)),
+               "r"(bytes)
+               : "memory");
+}
 
 struct Section {
   float in_d1, in_d2, out_d1, out_d2;
 };
 
+template <bool FIRST_ORDER>
 __device__ __forceinline__ float section_step(Section &s, float x, const BiquadParams &c) {
   float sum = __fadd_rn(__fmul_rn(x, c.a0), __fmul_rn(s.in_d1, c.a1));
-  if (!c.first_order)
+  if (!FIRST_ORDER)
     sum = __fadd_rn(sum, __fmul_rn(s.in_d2, c.a2));
   sum = __fsub_rn(sum, __fmul_rn(c.b1, s.out_d1));
-  if (!c.first_order)
+  if (!FIRST_ORDER)
     sum = __fsub_rn(sum, __fmul_rn(c.b2, s.out_d2));
   s.out_d2 = s.out_d1;
   s.out_d1 = sum;
@@ -43,36 +81,21 @@ __device__ __forceinline__ float section_step(Section &s, float x, const BiquadP
   return sum;
 }
 
-template <int NSEC>
-__global__ void __launch_bounds__(BQ_THREADS)
-    espb_biquad_kernel(float *__restrict__ buf, int64_t ss, int64_t cs, int64_t fs, int channels, int n_series,
-                       int n_samples, BiquadParams c, float *__restrict__ state) {
-  __shared__ float tile[BQ_TILE][BQ_SERIES + 1];
-  const int q0 = blockIdx.x * BQ_SERIES;
+// buf: first group of the launch; rows [row_first, row_first + n_rows) of every group are filtered in place.
+template <int NSEC, bool FIRST_ORDER>
+__global__ void __launch_bounds__(SGN)
+    espb_biquad_tm_kernel(float *__restrict__ buf, int64_t rows_cap, int row_first, int n_rows, BiquadParams c,
+                          float *__restrict__ state, int n_series) {
+  extern __shared__ __align__(128) unsigned char bq_smem[];
+  float (*ring)[RB][SGN] = reinterpret_cast<float (*)[RB][SGN]>(bq_smem);  // [BSTAGES][RB][SGN]
+  uint64_t *full = reinterpret_cast<uint64_t *>(bq_smem + sizeof(float) * BSTAGES * RB * SGN);
   const int tid = threadIdx.x;
-
-  // loader mapping: element i of a tile -> (series, frame), chosen so that consecutive
-  // threads touch consecutive addresses in the common layouts.
-  // 0: frames contiguous (planar)  1: interleaved, CTA covers whole streams  2: generic
-  const int mapping = (fs == 1) ? 0 : ((cs == 1 && fs == channels && BQ_SERIES % channels == 0) ? 1 : 2);
-  auto locate = [&](int i, int &sl, int &t) {
-    if (mapping == 0) {
-      sl = i / BQ_TILE;
-      t = i - sl * BQ_TILE;
-    } else if (mapping == 1) {
-      const int per = BQ_TILE * channels;
-      const int stl = i / per, r = i - stl * per;
-      t = r / channels;
-      sl = stl * channels + (r - t * channels);
-    } else {
-      t = i / BQ_SERIES;
-      sl = i - t * BQ_SERIES;
-    }
-  };
+  const int q = blockIdx.x * SGN + tid;
+  float *gbase = buf + ((int64_t) blockIdx.x * rows_cap + row_first) * SGN;
+  const int n_chunks = (n_rows + RB - 1) / RB;
 
   Section sec[NSEC];
-  const int q = q0 + tid;  // recurrence owner (threads 0..31)
-  if (tid < BQ_SERIES && q < n_series) {
+  if (q < n_series) {
 #pragma unroll
     for (int k = 0; k < NSEC; ++k) {
       const float4 v = *reinterpret_cast<const float4 *>(state + ((int64_t) q * NSEC + k) * 4);
@@ -81,46 +104,70 @@ __global__ void __launch_bounds__(BQ_THREADS)
       sec[k].out_d1 = v.z;
       sec[k].out_d2 = v.w;
     }
-  }
-
-  for (int t0 = 0; t0 < n_samples; t0 += BQ_TILE) {
-    const int nt = (n_samples - t0 < BQ_TILE) ? n_samples - t0 : BQ_TILE;
-    // ---- load tile
-    for (int i = tid; i < BQ_SERIES * BQ_TILE; i += BQ_THREADS) {
-      int sl, t;
-      locate(i, sl, t);
-      const int qq = q0 + sl;
-      if (qq < n_series && t < nt) {
-        const int st = qq / channels, ch = qq - st * channels;
-        tile[t][sl] = buf[(int64_t) st * ss + (int64_t) ch * cs + (int64_t) (t0 + t) * fs];
-      }
-    }
-    __syncthreads();
-    // ---- recurrences
-    if (tid < BQ_SERIES && q < n_series) {
-      for (int t = 0; t < nt; ++t) {
-        float v = tile[t][tid];
+  } else {
 #pragma unroll
-        for (int k = 0; k < NSEC; ++k)
-          v = section_step(sec[k], v, c);
-        tile[t][tid] = v;
-      }
-    }
-    __syncthreads();
-    // ---- store tile
-    for (int i = tid; i < BQ_SERIES * BQ_TILE; i += BQ_THREADS) {
-      int sl, t;
-      locate(i, sl, t);
-      const int qq = q0 + sl;
-      if (qq < n_series && t < nt) {
-        const int st = qq / channels, ch = qq - st * channels;
-        buf[(int64_t) st * ss + (int64_t) ch * cs + (int64_t) (t0 + t) * fs] = tile[t][sl];
-      }
-    }
-    __syncthreads();
+    for (int k = 0; k < NSEC; ++k)
+      sec[k].in_d1 = sec[k].in_d2 = sec[k].out_d1 = sec[k].out_d2 = 0.0f;
   }
 
-  if (tid < BQ_SERIES && q < n_series) {
+  auto chunk_rows = [&](int k) { return (k + 1) * RB <= n_rows ? RB : n_rows - k * RB; };
+  auto load_chunk = [&](int k) {
+    const int st = k % BSTAGES;
+    const uint32_t bytes = (uint32_t) chunk_rows(k) * SGN * sizeof(float);
+    mbar_expect_tx(&full[st], bytes);
+    tma_load(&ring[st][0][0], gbase + (int64_t) k * RB * SGN, bytes, &full[st]);
+  };
+
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < BSTAGES; ++s)
+      mbar_init(&full[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    for (int k = 0; k < BSTAGES - 1 && k < n_chunks; ++k)
+      load_chunk(k);
+  }
+  __syncthreads();
+
+  for (int k = 0; k < n_chunks; ++k) {
+    const int st = k % BSTAGES;
+    const int rows = chunk_rows(k);
+    mbar_wait(&full[st], (uint32_t) ((k / BSTAGES) & 1));
+    float *col = &ring[st][0][tid];
+    if (rows == RB) {
+#pragma unroll 8
+      for (int r = 0; r < RB; ++r) {
+        float v = col[r * SGN];
+#pragma unroll
+        for (int s = 0; s < NSEC; ++s)
+          v = section_step<FIRST_ORDER>(sec[s], v, c);
+        col[r * SGN] = v;
+      }
+    } else {
+      for (int r = 0; r < rows; ++r) {
+        float v = col[r * SGN];
+#pragma unroll
+        for (int s = 0; s < NSEC; ++s)
+          v = section_step<FIRST_ORDER>(sec[s], v, c);
+        col[r * SGN] = v;
+      }
+    }
+    // generic-proxy writes -> visible to the async proxy, then one thread stores the chunk and refills
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+    __syncthreads();
+    if (tid == 0) {
+      tma_store(gbase + (int64_t) k * RB * SGN, &ring[st][0][0], (uint32_t) rows * SGN * sizeof(float));
+      asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
+      if (k + BSTAGES - 1 < n_chunks) {
+        // stage (k-1) % BSTAGES is reused: its store (issued last iteration) must have read shared memory
+        asm volatile("cp.async.bulk.wait_group.read 1;\n" ::: "memory");
+        load_chunk(k + BSTAGES - 1);
+      }
+    }
+  }
+  if (tid == 0)
+    asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory");
+
+  if (q < n_series) {
 #pragma unroll
     for (int k = 0; k < NSEC; ++k)
       *reinterpret_cast<float4 *>(state + ((int64_t) q * NSEC + k) * 4) =
@@ -128,31 +175,50 @@ __global__ void __launch_bounds__(BQ_THREADS)
   }
 }
 
-}  // namespace
-
-cudaError_t launch_biquad(float *buf, int64_t ss, int64_t cs, int64_t fs, int channels, int n_series, int n_sections,
-                          int n_samples, BiquadParams c, float *state, cudaStream_t stream) {
-  if (n_series <= 0 || n_samples <= 0)
-    return cudaSuccess;
-  if (n_sections < 1 || n_sections > kMaxSections)
-    return cudaErrorInvalidValue;
-  const unsigned grid = (n_series + BQ_SERIES - 1) / BQ_SERIES;
-  switch (n_sections) {
-    case 1:
-      espb_biquad_kernel<1><<<grid, BQ_THREADS, 0, stream>>>(buf, ss, cs, fs, channels, n_series, n_samples, c, state);
-      break;
-    case 2:
-      espb_biquad_kernel<2><<<grid, BQ_THREADS, 0, stream>>>(buf, ss, cs, fs, channels, n_series, n_samples, c, state);
-      break;
-    case 3:
-      espb_biquad_kernel<3><<<grid, BQ_THREADS, 0, stream>>>(buf, ss, cs, fs, channels, n_series, n_samples, c, state);
-      break;
-    default:
-      espb_biquad_kernel<4><<<grid, BQ_THREADS, 0, stream>>>(buf, ss, cs, fs, channels, n_series, n_samples, c, state);
-      break;
+template <int NSEC>
+cudaError_t launch_tm(float *buf, int64_t rows_cap, int row_first, int n_rows, int n_series, const BiquadParams &c,
+                      float *state, cudaStream_t stream) {
+  const unsigned grid = (n_series + SGN - 1) / SGN;
+  const size_t smem = sizeof(float) * BSTAGES * RB * SGN + BSTAGES * sizeof(uint64_t);
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(espb_biquad_tm_kernel<NSEC, true>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(espb_biquad_tm_kernel<NSEC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int) smem);
+    if (e != cudaSuccess)
+      return e;
+    configured = true;
   }
+  if (c.first_order)
+    espb_biquad_tm_kernel<NSEC, true><<<grid, SGN, smem, stream>>>(buf, rows_cap, row_first, n_rows, c, state,
+                                                                   n_series);
+  else
+    espb_biquad_tm_kernel<NSEC, false><<<grid, SGN, smem, stream>>>(buf, rows_cap, row_first, n_rows, c, state,
+                                                                    n_series);
   count_launch();
   return cudaGetLastError();
+}
+
+}  // namespace
+
+cudaError_t launch_biquad_tm(float *buf, int64_t rows_cap, int row_first, int n_rows, int n_series, int n_sections,
+                             BiquadParams c, float *state, cudaStream_t stream) {
+  if (n_series <= 0 || n_rows <= 0)
+    return cudaSuccess;
+  switch (n_sections) {
+    case 1:
+      return launch_tm<1>(buf, rows_cap, row_first, n_rows, n_series, c, state, stream);
+    case 2:
+      return launch_tm<2>(buf, rows_cap, row_first, n_rows, n_series, c, state, stream);
+    case 3:
+      return launch_tm<3>(buf, rows_cap, row_first, n_rows, n_series, c, state, stream);
+    case 4:
+      return launch_tm<4>(buf, rows_cap, row_first, n_rows, n_series, c, state, stream);
+    default:
+      return cudaErrorInvalidValue;
+  }
 }
 
 }  // namespace espb

@@ -15,6 +15,8 @@ struct ResampleParams {
   int64_t xt_rows;  // rows per group (row r = input frame r - taps)
   float *out;
   int64_t out_ss, out_cs, out_fs;  // stream / channel / frame strides of the caller's output, floats
+  float *out_tm;                   // if not NULL: write time-major yt[group][out_tm_rows][128] instead of `out`
+  int64_t out_tm_rows;
   const float *G;                  // expanded coefficients, chunk-major, starting at chunk g_chunk_base
   const ChunkEntry *chunks;
   const int32_t *pass_chunk_begin;
@@ -43,9 +45,13 @@ struct BiquadParams {
   float a0, a1, a2, b1, b2;
   int first_order;
 };
-cudaError_t launch_biquad(float *buf, int64_t ss, int64_t cs, int64_t fs, int channels, int n_series, int n_sections,
-                          int n_samples, BiquadParams c, float *state /* [series][section][4] */,
-                          cudaStream_t stream);
+// time-major in-place filter: rows [row_first, row_first + n_rows) of buf[group][rows_cap][128]
+cudaError_t launch_biquad_tm(float *buf, int64_t rows_cap, int row_first, int n_rows, int n_series, int n_sections,
+                             BiquadParams c, float *state /* [series][section][4] */, cudaStream_t stream);
+// time-major -> caller layout (inverse of launch_transpose): rows [row_first, row_first + n_rows)
+cudaError_t launch_untranspose(const float *tm, int64_t rows_cap, int row_first, int n_rows, float *out,
+                               int64_t out_ss, int64_t out_cs, int64_t out_fs, int channels, int n_series,
+                               cudaStream_t stream);
 
 // utilities
 cudaError_t launch_checksum(const uint32_t *words, uint64_t n, unsigned long long *sum_dev, cudaStream_t stream);

@@ -236,6 +236,92 @@ __global__ void __launch_bounds__(256)
 }
 
 // ---------------------------------------------------------------------------------
+// Inverse stage: time-major tm[group][row][128] -> caller layout.  Same tiling as the transposing
+// stage: 128-bit loads along series, 128-bit stores along time.
+// ---------------------------------------------------------------------------------
+template <int CH, bool PLANAR>
+__global__ void __launch_bounds__(TF_THREADS)
+    espb_untranspose_fast_kernel(const float *__restrict__ tm, int64_t rows_cap, int row_first, float *__restrict__ out,
+                                 int64_t out_ss, int64_t out_cs, int channels, int n_series) {
+  __shared__ float tile[TF_ROWS][SGN + 1];
+  const int g = blockIdx.x;
+  const int j0 = blockIdx.y * TF_ROWS;
+  const int tid = threadIdx.x;
+  const float4 *src = reinterpret_cast<const float4 *>(tm + ((int64_t) g * rows_cap + row_first + j0) * SGN);
+#pragma unroll 4
+  for (int i = tid; i < TF_ROWS * (SGN / 4); i += TF_THREADS) {
+    const int t = i / (SGN / 4), c4 = i % (SGN / 4);
+    const float4 v = __ldg(src + i);
+    tile[t][c4 * 4] = v.x;
+    tile[t][c4 * 4 + 1] = v.y;
+    tile[t][c4 * 4 + 2] = v.z;
+    tile[t][c4 * 4 + 3] = v.w;
+  }
+  __syncthreads();
+  constexpr int UNITS = SGN / CH;
+  constexpr int V_PER_UNIT = TF_ROWS * CH / 4;
+#pragma unroll 4
+  for (int v = tid; v < UNITS * V_PER_UNIT; v += TF_THREADS) {
+    const int unit = v / V_PER_UNIT, off4 = v % V_PER_UNIT;
+    const int q0 = g * SGN + unit * CH;
+    if (q0 >= n_series)
+      continue;
+    float *dst;
+    if (PLANAR) {
+      const int st = q0 / channels, ch = q0 - st * channels;
+      dst = out + (int64_t) st * out_ss + (int64_t) ch * out_cs + j0;
+    } else {
+      dst = out + (int64_t) (q0 / CH) * out_ss + (int64_t) j0 * CH;
+    }
+    const int e0 = off4 * 4;
+    float x[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int e = e0 + k;
+      x[k] = tile[e / CH][unit * CH + (e % CH)];
+    }
+    reinterpret_cast<float4 *>(dst)[off4] = make_float4(x[0], x[1], x[2], x[3]);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+    espb_untranspose_kernel(const float *__restrict__ tm, int64_t rows_cap, int row_first, int j_begin, int n_rows,
+                            float *__restrict__ out, int64_t out_ss, int64_t out_cs, int64_t out_fs, int channels,
+                            int n_series) {
+  __shared__ float tile[TR_ROWS][SGN + 1];
+  const int g = blockIdx.x;
+  const int j0 = j_begin + blockIdx.y * TR_ROWS;
+  const int tid = threadIdx.x;
+  const float *src = tm + ((int64_t) g * rows_cap + row_first + j0) * SGN;
+  for (int i = tid; i < TR_ROWS * SGN; i += 256) {
+    const int t = i / SGN, sl = i - t * SGN;
+    tile[t][sl] = (j0 + t < n_rows) ? __ldg(src + i) : 0.0f;
+  }
+  __syncthreads();
+  const int mapping = (out_fs == 1) ? 0 : ((out_cs == 1 && out_fs == channels && SGN % channels == 0) ? 1 : 2);
+  for (int i = tid; i < SGN * TR_ROWS; i += 256) {
+    int sl, t;
+    if (mapping == 0) {
+      sl = i / TR_ROWS;
+      t = i - sl * TR_ROWS;
+    } else if (mapping == 1) {
+      const int per = TR_ROWS * channels;
+      const int stl = i / per, r = i - stl * per;
+      t = r / channels;
+      sl = stl * channels + (r - t * channels);
+    } else {
+      t = i / SGN;
+      sl = i - t * SGN;
+    }
+    const int q = g * SGN + sl, j = j0 + t;
+    if (q < n_series && j < n_rows) {
+      const int st = q / channels, ch = q - st * channels;
+      out[(int64_t) st * out_ss + (int64_t) ch * out_cs + (int64_t) j * out_fs] = tile[t][sl];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------
 // Resampler
 // ---------------------------------------------------------------------------------
 template <int BPP, bool EXACT>
@@ -378,18 +464,25 @@ __global__ void __launch_bounds__(BPP * 32, 2) espb_resample_kernel(const Resamp
         const int o = o0 + n;
         if (o < p.n_out) {
           const OutEntry en = p.outs[o];
+          float v[4];
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            float v;
             if (en.kind == kKindBlend) {  // art_resampler.cpp:450, un-fused
-              v = __fadd_rn(__fmul_rn(acc[e][n][1], en.w), __fmul_rn(acc[e][n][0], __fsub_rn(1.0f, en.w)));
+              v[e] = __fadd_rn(__fmul_rn(acc[e][n][1], en.w), __fmul_rn(acc[e][n][0], __fsub_rn(1.0f, en.w)));
             } else if (en.kind == kKindSingle) {
-              v = acc[e][n][0];
+              v[e] = acc[e][n][0];
             } else {  // pass-through: *source (art_resampler.cpp:426,440) = tap numTaps/2-1 of the window
-              v = xt_group[(int64_t) (en.ws + T / 2 - 1 + T) * SGN + lane * 4 + e];
+              v[e] = xt_group[(int64_t) (en.ws + T / 2 - 1 + T) * SGN + lane * 4 + e];
             }
-            if (live[e])
-              p.out[out_off[e] + (int64_t) o * p.out_fs] = v;
+          }
+          if (p.out_tm) {  // time-major scratch for a following in-library stage: one 16-byte store per lane
+            *reinterpret_cast<float4 *>(p.out_tm + ((int64_t) group * p.out_tm_rows + o) * SGN + lane * 4) =
+                make_float4(v[0], v[1], v[2], v[3]);
+          } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              if (live[e])
+                p.out[out_off[e] + (int64_t) o * p.out_fs] = v[e];
           }
         }
       }
@@ -465,6 +558,54 @@ cudaError_t launch_transpose(const float *in, int64_t in_ss, int64_t in_cs, int6
     dim3 grid(n_groups, (rest + TR_ROWS - 1) / TR_ROWS);
     espb_transpose_kernel<<<grid, 256, 0, stream>>>(in, in_ss, in_cs, in_fs, channels, n_series, n_in, xt, rows_cap,
                                                     row_first, fast_rows, pad_rows);
+    count_launch();
+  }
+  return cudaGetLastError();
+}
+
+cudaError_t launch_untranspose(const float *tm, int64_t rows_cap, int row_first, int n_rows, float *out,
+                               int64_t out_ss, int64_t out_cs, int64_t out_fs, int channels, int n_series,
+                               cudaStream_t stream) {
+  const int n_groups = (n_series + SGN - 1) / SGN;
+  if (n_groups <= 0 || n_rows <= 0)
+    return cudaSuccess;
+  int fast_rows = 0;
+  const bool aligned = ((uintptr_t) out % 16 == 0) && (out_ss % 4 == 0);
+  const bool interleaved = (out_cs == 1 && out_fs == channels);
+  const bool planar = (out_fs == 1) && (out_cs % 4 == 0);
+  if (aligned && n_rows >= TF_ROWS) {
+    dim3 grid(n_groups, n_rows / TF_ROWS);
+    bool done = true;
+    if (interleaved && channels == 1)
+      espb_untranspose_fast_kernel<1, false><<<grid, TF_THREADS, 0, stream>>>(tm, rows_cap, row_first, out, out_ss,
+                                                                              out_cs, channels, n_series);
+    else if (interleaved && channels == 2)
+      espb_untranspose_fast_kernel<2, false><<<grid, TF_THREADS, 0, stream>>>(tm, rows_cap, row_first, out, out_ss,
+                                                                              out_cs, channels, n_series);
+    else if (interleaved && channels == 4)
+      espb_untranspose_fast_kernel<4, false><<<grid, TF_THREADS, 0, stream>>>(tm, rows_cap, row_first, out, out_ss,
+                                                                              out_cs, channels, n_series);
+    else if (interleaved && channels == 8)
+      espb_untranspose_fast_kernel<8, false><<<grid, TF_THREADS, 0, stream>>>(tm, rows_cap, row_first, out, out_ss,
+                                                                              out_cs, channels, n_series);
+    else if (planar)
+      espb_untranspose_fast_kernel<1, true><<<grid, TF_THREADS, 0, stream>>>(tm, rows_cap, row_first, out, out_ss,
+                                                                             out_cs, channels, n_series);
+    else
+      done = false;
+    if (done) {
+      count_launch();
+      fast_rows = (n_rows / TF_ROWS) * TF_ROWS;
+      cudaError_t e = cudaGetLastError();
+      if (e != cudaSuccess)
+        return e;
+    }
+  }
+  const int rest = n_rows - fast_rows;
+  if (rest > 0) {
+    dim3 grid(n_groups, (rest + TR_ROWS - 1) / TR_ROWS);
+    espb_untranspose_kernel<<<grid, 256, 0, stream>>>(tm, rows_cap, row_first, fast_rows, n_rows, out, out_ss, out_cs,
+                                                      out_fs, channels, n_series);
     count_launch();
   }
   return cudaGetLastError();
