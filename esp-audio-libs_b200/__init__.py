@@ -5,7 +5,7 @@ include/esp_audio_b200.h); this package is only the thin Python host binding the
 tests and bench.py use.  There is no CPU compute path: importing works anywhere (the
 `-m "not gpu"` tests check the exported symbols), computing needs a B200.
 """
-from .capi import (BLACKMAN_HARRIS, INCLUDE_LOWPASS, MODE_EXACT, MODE_FAST, OPT_BLOCKS_PER_PASS,  # noqa: F401
+from .capi import (BLACKMAN_HARRIS, INCLUDE_LOWPASS, MODE_EXACT, MODE_FAST,  # noqa: F401
                    OPT_KERNEL_TIMING, OPT_PLAN_CACHE, SUBSAMPLE_INTERPOLATE,
                    BiquadBatch, DeviceBuffer, EspbError, PinnedBuffer, ResampleBatch, Resampler, biquad_highpass,
                    biquad_lowpass, checksum_u32, declared_symbols, device_count, device_info, float_to_quantized,

@@ -12,7 +12,7 @@ _HEADER = os.path.join(_ROOT, "include", "esp_audio_b200.h")
 
 SUBSAMPLE_INTERPOLATE, BLACKMAN_HARRIS, INCLUDE_LOWPASS = 0x1, 0x2, 0x4
 MODE_FAST, MODE_EXACT = 0, 1
-OPT_PLAN_CACHE, OPT_KERNEL_TIMING, OPT_BLOCKS_PER_PASS = 1, 2, 3
+OPT_PLAN_CACHE, OPT_KERNEL_TIMING = 1, 2
 
 
 class EspbError(RuntimeError):

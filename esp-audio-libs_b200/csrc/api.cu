@@ -603,8 +603,7 @@ EspbResampleBatch *espb_resampleInit(int num_streams, int numChannels, int numTa
   c->geo = ArtGeometry{numTaps, numFilters, flags};
   c->lowpass = lowpassRatio;
   c->state = initial_state(numTaps);
-  long bpp = env_long("ESPB_BPP", 8);
-  c->bpp = (bpp == 4) ? 4 : 8;
+  c->bpp = 8;
   long gb = env_long("ESPB_G_MBYTES", 0);
   if (gb > 0)
     c->g_budget_bytes = (size_t) gb << 20;
@@ -695,12 +694,6 @@ int espb_resampleSetOption(EspbResampleBatch *c, int option, int value) {
     case ESPB_OPT_KERNEL_TIMING:
       c->kernel_timing = value != 0;
       c->ev_used = 0;
-      return ESPB_OK;
-    case ESPB_OPT_BLOCKS_PER_PASS:
-      if (value != 4 && value != 8)
-        return fail(ESPB_ERR_ARG, "resampleSetOption: blocks per pass must be 4 or 8");
-      c->bpp = value;
-      c->plan_on_device = false;
       return ESPB_OK;
     default:
       return fail(ESPB_ERR_ARG, "resampleSetOption: unknown option");

@@ -324,7 +324,8 @@ __global__ void __launch_bounds__(256)
 // ---------------------------------------------------------------------------------
 // Resampler
 // ---------------------------------------------------------------------------------
-template <int BPP, bool EXACT>
+// TM: write the output time-major (scratch for a following library stage) instead of the caller's layout.
+template <int BPP, bool EXACT, bool TM>
 __global__ void __launch_bounds__(BPP * 32, 2) espb_resample_kernel(const ResampleParams p) {
   constexpr int NTHREADS = BPP * 32;
   constexpr int XS_STAGE = CJ * SGN;                // floats
@@ -464,26 +465,25 @@ __global__ void __launch_bounds__(BPP * 32, 2) espb_resample_kernel(const Resamp
         const int o = o0 + n;
         if (o < p.n_out) {
           const OutEntry en = p.outs[o];
-          float v[4];
+          float vt[4];
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
+            float v;
             if (en.kind == kKindBlend) {  // art_resampler.cpp:450, un-fused
-              v[e] = __fadd_rn(__fmul_rn(acc[e][n][1], en.w), __fmul_rn(acc[e][n][0], __fsub_rn(1.0f, en.w)));
+              v = __fadd_rn(__fmul_rn(acc[e][n][1], en.w), __fmul_rn(acc[e][n][0], __fsub_rn(1.0f, en.w)));
             } else if (en.kind == kKindSingle) {
-              v[e] = acc[e][n][0];
+              v = acc[e][n][0];
             } else {  // pass-through: *source (art_resampler.cpp:426,440) = tap numTaps/2-1 of the window
-              v[e] = xt_group[(int64_t) (en.ws + T / 2 - 1 + T) * SGN + lane * 4 + e];
+              v = xt_group[(int64_t) (en.ws + T / 2 - 1 + T) * SGN + lane * 4 + e];
             }
+            if constexpr (TM)
+              vt[e] = v;
+            else if (live[e])
+              p.out[out_off[e] + (int64_t) o * p.out_fs] = v;
           }
-          if (p.out_tm) {  // time-major scratch for a following in-library stage: one 16-byte store per lane
+          if constexpr (TM)  // time-major scratch for a following in-library stage: one 16-byte store per lane
             *reinterpret_cast<float4 *>(p.out_tm + ((int64_t) group * p.out_tm_rows + o) * SGN + lane * 4) =
-                make_float4(v[0], v[1], v[2], v[3]);
-          } else {
-#pragma unroll
-            for (int e = 0; e < 4; ++e)
-              if (live[e])
-                p.out[out_off[e] + (int64_t) o * p.out_fs] = v[e];
-          }
+                make_float4(vt[0], vt[1], vt[2], vt[3]);
         }
       }
 #pragma unroll
@@ -611,32 +611,32 @@ cudaError_t launch_untranspose(const float *tm, int64_t rows_cap, int row_first,
   return cudaGetLastError();
 }
 
-template <int BPP, bool EXACT>
+template <int BPP, bool EXACT, bool TM>
 static cudaError_t launch_resample_t(const ResampleParams &p, int n_groups, int n_ctas_y, cudaStream_t stream) {
   const size_t smem = resample_smem_bytes(BPP);
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(espb_resample_kernel<BPP, EXACT>,
+    cudaError_t e = cudaFuncSetAttribute(espb_resample_kernel<BPP, EXACT, TM>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
     if (e != cudaSuccess)
       return e;
     // two CTAs per SM need the full 228 KB carve-out (the default heuristic sizes it for one)
-    e = cudaFuncSetAttribute(espb_resample_kernel<BPP, EXACT>, cudaFuncAttributePreferredSharedMemoryCarveout,
+    e = cudaFuncSetAttribute(espb_resample_kernel<BPP, EXACT, TM>, cudaFuncAttributePreferredSharedMemoryCarveout,
                              (int) cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess)
       return e;
     configured = true;
     if (getenv("ESPB_DEBUG")) {
       int nb = 0;
-      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, espb_resample_kernel<BPP, EXACT>, BPP * 32, smem);
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, espb_resample_kernel<BPP, EXACT, TM>, BPP * 32, smem);
       cudaFuncAttributes fa;
-      cudaFuncGetAttributes(&fa, espb_resample_kernel<BPP, EXACT>);
-      fprintf(stderr, "[espb] resample<%d,%d>: smem %zu B dyn + %zu static, %d regs, max threads %d, occupancy %d CTA/SM\n",
-              BPP, (int) EXACT, smem, fa.sharedSizeBytes, fa.numRegs, fa.maxThreadsPerBlock, nb);
+      cudaFuncGetAttributes(&fa, espb_resample_kernel<BPP, EXACT, TM>);
+      fprintf(stderr, "[espb] resample<%d,%d,%d>: smem %zu B, %d regs, occupancy %d CTA/SM\n", BPP, (int) EXACT,
+              (int) TM, smem, fa.numRegs, nb);
     }
   }
   dim3 grid(n_groups, n_ctas_y);
-  espb_resample_kernel<BPP, EXACT><<<grid, BPP * 32, smem, stream>>>(p);
+  espb_resample_kernel<BPP, EXACT, TM><<<grid, BPP * 32, smem, stream>>>(p);
   count_launch();
   return cudaGetLastError();
 }
@@ -647,13 +647,14 @@ cudaError_t launch_resample(const ResampleParams &p, int bpp, bool exact, cudaSt
   if (n_groups <= 0 || n_passes <= 0)
     return cudaSuccess;
   const int n_ctas_y = (n_passes + p.passes_per_cta - 1) / p.passes_per_cta;
-  if (bpp == 8)
-    return exact ? launch_resample_t<8, true>(p, n_groups, n_ctas_y, stream)
-                 : launch_resample_t<8, false>(p, n_groups, n_ctas_y, stream);
-  if (bpp == 4)
-    return exact ? launch_resample_t<4, true>(p, n_groups, n_ctas_y, stream)
-                 : launch_resample_t<4, false>(p, n_groups, n_ctas_y, stream);
-  return cudaErrorInvalidValue;
+  const bool tm = p.out_tm != nullptr;
+  if (bpp != 8)
+    return cudaErrorInvalidValue;
+  if (exact)
+    return tm ? launch_resample_t<8, true, true>(p, n_groups, n_ctas_y, stream)
+              : launch_resample_t<8, true, false>(p, n_groups, n_ctas_y, stream);
+  return tm ? launch_resample_t<8, false, true>(p, n_groups, n_ctas_y, stream)
+            : launch_resample_t<8, false, false>(p, n_groups, n_ctas_y, stream);
 }
 
 }  // namespace espb

@@ -101,10 +101,9 @@ unsigned int espb_resampleGetExpectedOutput(EspbResampleBatch *cxt, int numInput
 int espb_resampleSetMode(EspbResampleBatch *cxt, int mode);            /* ESPB_MODE_FAST (default) / _EXACT */
 /* options: plan cache (default on: a call that repeats the previous call's state, frame counts
  * and ratio reuses its schedule and expanded coefficients), per-launch CUDA-event timing of the
- * resampler kernel (read with espb_resampleGetKernelTime), output blocks per pass (4 or 8) */
+ * resampler kernel (read with espb_resampleGetKernelTime) */
 #define ESPB_OPT_PLAN_CACHE 1
 #define ESPB_OPT_KERNEL_TIMING 2
-#define ESPB_OPT_BLOCKS_PER_PASS 3
 int espb_resampleSetOption(EspbResampleBatch *cxt, int option, int value);
 /* sum of the resampler-kernel durations recorded since the last query, and their count */
 int espb_resampleGetKernelTime(EspbResampleBatch *cxt, float *total_ms, int *launches);
