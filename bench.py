@@ -253,7 +253,8 @@ def main():
     espb.capi._check(L.espb_stream_sync(stream), "sync")
 
     # ---- FP32 FMA peak of this device, measured now (roofline denominator)
-    fma_tflops, fma_clock = espb.measure_fp32_fma_peak()
+    fma_tflops, fma_clock = espb.measure_fp32_fma_peak()  # best of the scalar FFMA and packed FFMA2 probes
+    fma_scalar, fma_packed = espb.measure_fp32_fma_peak2()
 
     ctx = espb.ResampleBatch(ns, CHANNELS, TAPS, FILTERS, 1.0, FLAGS, mode=espb.MODE_FAST)
     ctx.set_option(espb.OPT_PLAN_CACHE, 0)  # every step re-plans: schedule, upload and expansion are timed
@@ -326,10 +327,11 @@ def main():
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     roofline = {
-        "kernel": "espb_resample_kernel<8,false>", "bound": "fp32_fma", "achieved": achieved_tf,
+        "kernel": "espb_resample_kernel<8,false,false>", "bound": "fp32_fma", "achieved": achieved_tf,
         "peak": fma_tflops, "unit": "TFLOP/s", "frac": achieved_tf / fma_tflops if fma_tflops else None,
-        "peak_source": "FFMA-only probe (espb_measure_fp32_fma_peak) on this GPU in this run; nominal 148 SM x 128 "
-                       "lanes x 2 x 1.965 GHz = 74.4",
+        "peak_source": "FMA-only probes (espb_measure_fp32_fma_peak: best of scalar FFMA and packed FFMA2) on this "
+                       "GPU in this run; nominal 148 SM x 128 lanes x 2 x 1.965 GHz = 74.4",
+        "peak_probe_ffma_tflops": fma_scalar, "peak_probe_ffma2_tflops": fma_packed,
         "peak_implied_sm_mhz": fma_clock, "traffic": None,
         "flop_per_sample": FLOP_PER_SAMPLE, "kernel_ms": k_ms, "kernel_share_of_step": kernel_ms / total_ms,
         "hbm": {"achieved_gbs": bytes_per_launch / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0, "peak_gbs": hbm_peak,
@@ -393,7 +395,7 @@ def main():
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "streams_per_gpu": ns, "channels": CHANNELS, "taps": TAPS,
                        "filters": FILTERS, "ratio": float(RATIO), "frames_in": N_IN, "frames_out": gen,
-                       "mode": "fast (tap-order FFMA chain, <=1e-6 of the reference)",
+                       "mode": "fast (tap-order FMA chain per accumulator, packed FFMA2; <=1e-6 of the reference)",
                        "signals": f"{DISTINCT} distinct streams (multitone + uniform noise, A=0.5) tiled",
                        "parallelism": f"streams sharded by index over {world} GPU(s), no data-path collective",
                        "l2": "inputs+outputs 3.0 GB per step >> 126 MB L2 (no flush needed)",

@@ -9,6 +9,6 @@ from .capi import (BLACKMAN_HARRIS, INCLUDE_LOWPASS, MODE_EXACT, MODE_FAST,  # n
                    OPT_KERNEL_TIMING, OPT_PLAN_CACHE, SUBSAMPLE_INTERPOLATE,
                    BiquadBatch, DeviceBuffer, EspbError, PinnedBuffer, ResampleBatch, Resampler, biquad_highpass,
                    biquad_lowpass, checksum_u32, declared_symbols, device_count, device_info, float_to_quantized,
-                   launch_count, lib, library_path, measure_fp32_fma_peak, plan_filter_bank, plan_policy,
+                   launch_count, lib, library_path, measure_fp32_fma_peak, measure_fp32_fma_peak2, plan_filter_bank, plan_policy,
                    plan_schedule, quantized_to_float, set_device)
 from .sharding import combine_checksums, gather_words, shard_range  # noqa: F401,E402

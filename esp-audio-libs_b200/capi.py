@@ -132,6 +132,7 @@ def lib():
         "espb_plan_policy": (i, [C.POINTER(_Config), C.POINTER(_Coeffs), C.POINTER(f), C.POINTER(f), C.POINTER(i)]),
         "espb_checksum_u32": (i, [vp, u64, vp, vp]),
         "espb_measure_fp32_fma_peak": (i, [C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+        "espb_measure_fp32_fma_peak2": (i, [C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -204,6 +205,12 @@ def plan_policy(src_rate, dst_rate, src_bits, dst_bits, channels, use_filter, in
     return dict(filter={0: "none", 1: "pre", 2: "post"}[kind],
                 coeffs=np.array([c.a0, c.a1, c.a2, c.b1, c.b2], np.float32), sample_ratio=np.float32(ratio.value),
                 art_lowpass=np.float32(lp.value), art_flags=int(flags.value))
+
+
+def measure_fp32_fma_peak2():
+    a, b = C.c_double(0), C.c_double(0)
+    _check(lib().espb_measure_fp32_fma_peak2(C.byref(a), C.byref(b)), "measure_fp32_fma_peak2")
+    return a.value, b.value
 
 
 class DeviceBuffer:

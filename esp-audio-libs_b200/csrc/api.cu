@@ -1136,7 +1136,13 @@ int espb_checksum_u32(const void *buf, uint64_t num_words, uint64_t *sum_dev, vo
 int espb_measure_fp32_fma_peak(double *tflops, double *sm_clock_mhz_estimate) {
   if (!tflops)
     return fail(ESPB_ERR_ARG, "measure_fp32_fma_peak: NULL");
-  CU_TRY(run_fma_probe(tflops, sm_clock_mhz_estimate), "fma probe");
+  CU_TRY(run_fma_probe(tflops, sm_clock_mhz_estimate, nullptr, nullptr), "fma probe");
+  return ESPB_OK;
+}
+
+int espb_measure_fp32_fma_peak2(double *tflops_scalar_ffma, double *tflops_packed_ffma2) {
+  double top = 0.0;
+  CU_TRY(run_fma_probe(&top, nullptr, tflops_scalar_ffma, tflops_packed_ffma2), "fma probe");
   return ESPB_OK;
 }
 

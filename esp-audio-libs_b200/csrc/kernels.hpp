@@ -55,6 +55,6 @@ cudaError_t launch_untranspose(const float *tm, int64_t rows_cap, int row_first,
 
 // utilities
 cudaError_t launch_checksum(const uint32_t *words, uint64_t n, unsigned long long *sum_dev, cudaStream_t stream);
-cudaError_t run_fma_probe(double *tflops, double *clock_mhz);
+cudaError_t run_fma_probe(double *tflops, double *clock_mhz, double *tflops_scalar, double *tflops_packed);
 
 }  // namespace espb

@@ -90,6 +90,15 @@ __device__ __forceinline__ int smem_arrive_acq_rel(int *counter) {
   return old;
 }
 
+// Packed FP32 pairs (Blackwell FFMA2): two independent IEEE FMAs per lane per instruction — the same
+// results as two scalar FFMAs, half the issue slots.  A pair is (filter 0, filter 1) of one output, whose
+// coefficients are adjacent in G.
+// Fast mode only: ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 (unlike the scalar forms, whose
+// explicit .rn is honoured), so exact mode keeps scalar FMUL + FADD.
+__device__ __forceinline__ float2 fma2(float2 g, float x, float2 acc) {
+  return __ffma2_rn(g, make_float2(x, x), acc);  // SASS: FFMA2 acc, g.F32x2, x.F32 (scalar broadcast), acc
+}
+
 template <bool EXACT>
 __device__ __forceinline__ float mac(float g, float x, float acc) {
   if (EXACT)
@@ -389,12 +398,25 @@ __global__ void __launch_bounds__(BPP * 32, 2) espb_resample_kernel(const Resamp
     for (int c = 0; c < STAGES && c < n_chunks; ++c)
       issue_chunk(c);
 
-  float acc[4][NB][2];  // [series e][output n][filter f]
+  // accumulators [series e][output n] x (filter 0, filter 1): packed pairs in fast mode, scalars in exact mode
+  float2 acc2[EXACT ? 1 : 4][EXACT ? 1 : NB];
+  float acc1[EXACT ? 4 : 1][EXACT ? NB : 1][2];
+  auto clear_acc = [&]() {
+    if constexpr (EXACT) {
 #pragma unroll
-  for (int e = 0; e < 4; ++e)
+      for (int e = 0; e < 4; ++e)
 #pragma unroll
-    for (int n = 0; n < NB; ++n)
-      acc[e][n][0] = acc[e][n][1] = 0.0f;
+        for (int n = 0; n < NB; ++n)
+          acc1[e][n][0] = acc1[e][n][1] = 0.0f;
+    } else {
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+#pragma unroll
+        for (int n = 0; n < NB; ++n)
+          acc2[e][n] = make_float2(0.0f, 0.0f);
+    }
+  };
+  clear_acc();
 
   int cur_pass = -1, win_lo = 0, win_hi = 0;  // this warp's window [win_lo, win_hi) in input frames
   for (int c = 0; c < n_chunks; ++c) {
@@ -421,21 +443,36 @@ __global__ void __launch_bounds__(BPP * 32, 2) espb_resample_kernel(const Resamp
 #pragma unroll
         for (int jj = 0; jj < 8; ++jj) {
           const float4 xv = *reinterpret_cast<const float4 *>(xb + jj * SGN);
-          const float4 *gp = reinterpret_cast<const float4 *>(gb + jj * BPP * kGRowFloats);
-          const float4 g0 = gp[0], g1 = gp[1], g2 = gp[2], g3 = gp[3];
-          const float x4[4] = {xv.x, xv.y, xv.z, xv.w};
-          const float g16[16] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w,
-                                 g2.x, g2.y, g2.z, g2.w, g3.x, g3.y, g3.z, g3.w};
+          if constexpr (EXACT) {
+            const float4 *gp = reinterpret_cast<const float4 *>(gb + jj * BPP * kGRowFloats);
+            const float4 g0 = gp[0], g1 = gp[1], g2 = gp[2], g3 = gp[3];
+            const float x4[4] = {xv.x, xv.y, xv.z, xv.w};
+            const float g16[16] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w,
+                                   g2.x, g2.y, g2.z, g2.w, g3.x, g3.y, g3.z, g3.w};
 #pragma unroll
-          for (int n = 0; n < NB; ++n)
+            for (int n = 0; n < NB; ++n)
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              acc[e][n][0] = mac<EXACT>(g16[2 * n], x4[e], acc[e][n][0]);
-              acc[e][n][1] = mac<EXACT>(g16[2 * n + 1], x4[e], acc[e][n][1]);
-            }
+              for (int e = 0; e < 4; ++e) {
+                acc1[e][n][0] = mac<true>(g16[2 * n], x4[e], acc1[e][n][0]);
+                acc1[e][n][1] = mac<true>(g16[2 * n + 1], x4[e], acc1[e][n][1]);
+              }
+          } else {
+            const float4 *gp = reinterpret_cast<const float4 *>(gb + jj * BPP * kGRowFloats);
+            const float4 g0 = gp[0], g1 = gp[1], g2 = gp[2], g3 = gp[3];
+            const float x4[4] = {xv.x, xv.y, xv.z, xv.w};
+            const float2 gg[NB] = {make_float2(g0.x, g0.y), make_float2(g0.z, g0.w), make_float2(g1.x, g1.y),
+                                   make_float2(g1.z, g1.w), make_float2(g2.x, g2.y), make_float2(g2.z, g2.w),
+                                   make_float2(g3.x, g3.y), make_float2(g3.z, g3.w)};  // (filter 0, filter 1) pairs
+#pragma unroll
+            for (int n = 0; n < NB; ++n)
+#pragma unroll
+              for (int e = 0; e < 4; ++e)
+                acc2[e][n] = fma2(gg[n], x4[e], acc2[e][n]);
+          }
         }
       }
     }
+
     // Release the stage.  The last of the BPP warps to get here re-arms it and issues the refill
     // (chunk c + STAGES); nobody waits for anybody.
     __syncwarp();
@@ -468,11 +505,18 @@ __global__ void __launch_bounds__(BPP * 32, 2) espb_resample_kernel(const Resamp
           float vt[4];
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            float v;
+            float v, sum1, sum2;
+            if constexpr (EXACT) {
+              sum1 = acc1[e][n][0];
+              sum2 = acc1[e][n][1];
+            } else {
+              sum1 = acc2[e][n].x;
+              sum2 = acc2[e][n].y;
+            }
             if (en.kind == kKindBlend) {  // art_resampler.cpp:450, un-fused
-              v = __fadd_rn(__fmul_rn(acc[e][n][1], en.w), __fmul_rn(acc[e][n][0], __fsub_rn(1.0f, en.w)));
+              v = __fadd_rn(__fmul_rn(sum2, en.w), __fmul_rn(sum1, __fsub_rn(1.0f, en.w)));
             } else if (en.kind == kKindSingle) {
-              v = acc[e][n][0];
+              v = sum1;
             } else {  // pass-through: *source (art_resampler.cpp:426,440) = tap numTaps/2-1 of the window
               v = xt_group[(int64_t) (en.ws + T / 2 - 1 + T) * SGN + lane * 4 + e];
             }
@@ -486,11 +530,7 @@ __global__ void __launch_bounds__(BPP * 32, 2) espb_resample_kernel(const Resamp
                 make_float4(vt[0], vt[1], vt[2], vt[3]);
         }
       }
-#pragma unroll
-      for (int e = 0; e < 4; ++e)
-#pragma unroll
-        for (int n = 0; n < NB; ++n)
-          acc[e][n][0] = acc[e][n][1] = 0.0f;
+      clear_acc();
     }
   }
 }

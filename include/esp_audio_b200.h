@@ -250,6 +250,9 @@ int espb_plan_policy(const EspbResamplerConfiguration *config, EspbBiquadCoeffic
 int espb_checksum_u32(const void *buf, uint64_t num_words, uint64_t *sum_dev, void *stream);
 /* FFMA-only probe: achieved FP32 TFLOP/s of this device right now (roofline denominator). */
 int espb_measure_fp32_fma_peak(double *tflops, double *sm_clock_mhz_estimate);
+/* the two probes separately: scalar FFMA and packed FFMA2 (fma.rn.f32x2); espb_measure_fp32_fma_peak returns the
+ * larger */
+int espb_measure_fp32_fma_peak2(double *tflops_scalar_ffma, double *tflops_packed_ffma2);
 
 #ifdef __cplusplus
 }
