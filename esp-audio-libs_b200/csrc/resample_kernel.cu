@@ -49,6 +49,8 @@ constexpr int SGN = kSeriesPerRow;    // 128
 constexpr int STAGES = 3;
 constexpr int MAXC = kMaxChunksPerCta;  // chunk entries cached in shared memory per CTA
 constexpr int MAXP = kMaxPassesPerCta;  // passes per CTA
+constexpr int kLastChunkOfPass = 1 << 30;
+constexpr int RG = 4;  // rows per skip group / inner unroll
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t) __cvta_generic_to_shared(p); }
 
@@ -81,12 +83,12 @@ __device__ __forceinline__ void tma_bulk_g2s(void *dst_smem, const void *src, ui
                : "memory");
 }
 
-// Counting arrival on a shared-memory word with acquire-release semantics at CTA scope: the
-// caller's earlier shared-memory reads are ordered before it, and whoever sees the last count
-// sees them done — no separate (sequentially consistent) fence needed.
-__device__ __forceinline__ int smem_arrive_acq_rel(int *counter) {
+// Counting arrival on a shared-memory word.  Relaxed is enough: every shared-memory load of the stage
+// has already returned its value (the FMAs consumed them) when the warp gets here, so nothing of this
+// warp can still observe the refill; the refill itself is published by the mbarrier arrive (release).
+__device__ __forceinline__ int smem_arrive(int *counter) {
   int old;
-  asm volatile("atom.acq_rel.cta.shared::cta.add.s32 %0, [%1], 1;\n" : "=r"(old) : "r"(smem_u32(counter)) : "memory");
+  asm volatile("atom.relaxed.cta.shared::cta.add.s32 %0, [%1], 1;\n" : "=r"(old) : "r"(smem_u32(counter)) : "memory");
   return old;
 }
 
@@ -359,11 +361,15 @@ __global__ void __launch_bounds__(BPP * 32, 2) espb_resample_kernel(const Resamp
   if (pass_last > p.pass_end)
     pass_last = p.pass_end;
   const int chunk_first = p.pass_chunk_begin[pass_first], chunk_last = p.pass_chunk_begin[pass_last];
-  const int n_chunks = chunk_last - chunk_first;
+  const int n_chunks = __shfl_sync(0xffffffffu, chunk_last - chunk_first, 0);  // warp-uniform by construction
 
   // ---- cache the signal-independent tables this CTA needs (no global loads in the main loop)
-  for (int i = tid; i < n_chunks; i += NTHREADS)
-    ctab[i] = p.chunks[chunk_first + i];
+  for (int i = tid; i < n_chunks; i += NTHREADS) {  // .pass gets bit 30 set on the last chunk of its pass
+    ChunkEntry ce = p.chunks[chunk_first + i];
+    if (i + 1 == n_chunks || p.chunks[chunk_first + i + 1].pass != ce.pass)
+      ce.pass |= kLastChunkOfPass;
+    ctab[i] = ce;
+  }
   for (int i = tid; i < (pass_last - pass_first) * BPP; i += NTHREADS) {
     const int o0 = ((pass_first + i / BPP) * BPP + (i % BPP)) * NB;
     int2 w = make_int2(0, 0);
@@ -421,27 +427,29 @@ __global__ void __launch_bounds__(BPP * 32, 2) espb_resample_kernel(const Resamp
   int cur_pass = -1, win_lo = 0, win_hi = 0;  // this warp's window [win_lo, win_hi) in input frames
   for (int c = 0; c < n_chunks; ++c) {
     const int st = c % STAGES;
-    const ChunkEntry ce = ctab[c];
+    ChunkEntry ce = ctab[c];
+    const bool pass_done = (ce.pass & kLastChunkOfPass) != 0;
+    ce.pass &= ~kLastChunkOfPass;
     if (ce.pass != cur_pass) {
       cur_pass = ce.pass;
       const int2 w = wtab[(cur_pass - pass_first) * BPP + warp];
       win_lo = w.x;
       win_hi = w.y;
     }
-    // rows of this chunk inside the warp's window, in groups of 8 (rows outside it only multiply zeros)
+    // rows of this chunk inside the warp's window, in groups of RG (rows outside it only multiply zeros)
     int r0 = win_lo - ce.j_start, r1 = win_hi - ce.j_start;
-    r0 = r0 < 0 ? 0 : (r0 >> 3);
-    r1 = r1 > CJ ? CJ / 8 : ((r1 + 7) >> 3);
+    r0 = r0 < 0 ? 0 : (r0 / RG);
+    r1 = r1 > CJ ? CJ / RG : ((r1 + RG - 1) / RG);
 
     mbar_wait(&full[st], (uint32_t) ((c / STAGES) & 1));
     {
       const float *xrow = xs + st * XS_STAGE + lane * 4;
       const float *grow = gs + st * GS_STAGE + warp * kGRowFloats;
       for (int jb = r0; jb < r1; ++jb) {
-        const float *xb = xrow + jb * 8 * SGN;
-        const float *gb = grow + jb * 8 * BPP * kGRowFloats;
+        const float *xb = xrow + jb * RG * SGN;
+        const float *gb = grow + jb * RG * BPP * kGRowFloats;
 #pragma unroll
-        for (int jj = 0; jj < 8; ++jj) {
+        for (int jj = 0; jj < RG; ++jj) {
           const float4 xv = *reinterpret_cast<const float4 *>(xb + jj * SGN);
           if constexpr (EXACT) {
             const float4 *gp = reinterpret_cast<const float4 *>(gb + jj * BPP * kGRowFloats);
@@ -477,7 +485,7 @@ __global__ void __launch_bounds__(BPP * 32, 2) espb_resample_kernel(const Resamp
     // (chunk c + STAGES); nobody waits for anybody.
     __syncwarp();
     if (lane == 0) {
-      if (smem_arrive_acq_rel(&done[st]) == BPP - 1) {
+      if (smem_arrive(&done[st]) == BPP - 1) {
         done[st] = 0;  // published to the other warps by the release of the mbarrier arrive below
         if (c + STAGES < n_chunks)
           issue_chunk(c + STAGES);
@@ -485,7 +493,6 @@ __global__ void __launch_bounds__(BPP * 32, 2) espb_resample_kernel(const Resamp
     }
 
     // ---- end of pass: blend, store, clear
-    const bool pass_done = (c + 1 == n_chunks) || (ctab[c + 1].pass != cur_pass);
     if (pass_done) {
       const int o0 = (cur_pass * BPP + warp) * NB;
       int64_t out_off[4];
