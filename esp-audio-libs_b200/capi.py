@@ -114,6 +114,8 @@ def lib():
         "espb_biquad_free": (None, [vp]),
         "espb_biquad_reset": (i, [vp, vp]),
         "espb_biquad_apply_buffer": (i, [vp, vp, C.POINTER(_Layout), i, i, vp]),
+        "espb_biquad_set_time_blocks": (i, [vp, i, i]),
+        "espb_resampler_set_biquad_time_blocks": (i, [vp, i, i]),
         "espb_biquad_get_state": (i, [vp, vp]),
         "espb_quantized_to_float": (i, [vp, vp, u64, C.c_uint8, f, vp]),
         "espb_float_to_quantized": (i, [vp, vp, u64, C.c_uint8, vp, vp]),
@@ -429,6 +431,9 @@ class BiquadBatch:
     def reset(self, stream=None):
         _check(lib().espb_biquad_reset(self.h, stream), "biquad_reset")
 
+    def set_time_blocks(self, block_rows, warmup_rows):
+        _check(lib().espb_biquad_set_time_blocks(self.h, block_rows, warmup_rows), "biquad_set_time_blocks")
+
     def apply_dev(self, d_buf, layout, channels, n_samples, stream=None):
         lay = _Layout(*layout)
         _check(lib().espb_biquad_apply_buffer(self.h, d_buf, C.byref(lay), channels, n_samples, stream),
@@ -510,6 +515,10 @@ class Resampler:
             self.free()
         except Exception:
             pass
+
+    def set_biquad_time_blocks(self, block_rows, warmup_rows):
+        _check(lib().espb_resampler_set_biquad_time_blocks(self.h, block_rows, warmup_rows),
+               "resampler_set_biquad_time_blocks")
 
     def policy(self):
         c, ratio, lp, flags = _Coeffs(), C.c_float(0), C.c_float(0), C.c_int(0)

@@ -310,8 +310,8 @@ struct EspbResampleBatch {
   int xt_cur = 0;
   int64_t xt_rows = 0;  // rows per group in both buffers
   int carry_row = 0;
-  DevBuf yt;  // time-major output scratch [group][yt_rows][128] when a library stage follows the resampler
-  int64_t yt_rows = 0;
+  DevBuf yt, yt2;  // time-major output scratch [group][yt_rows][128] when a library stage follows the resampler
+  int64_t yt_rows = 0, yt2_rows = 0;
   int n_groups() const { return (n_series() + kSeriesPerRow - 1) / kSeriesPerRow; }
   // per-call plan, cached by (state, n_in, n_out, ratio)
   Schedule sched;
@@ -476,6 +476,7 @@ struct StageFilter {
   const BiquadParams *params = nullptr;  // NULL: no filter
   float *state = nullptr;                // [series][sections][4] of the first series of the range
   int sections = 0;
+  int block_rows = 0, warm_rows = 0;     // time-block mode of the biquad kernel (0 = sequential)
 };
 
 // Stage + resample series [series_first, series_first + n_series) of the batch (series_first is a
@@ -494,12 +495,30 @@ int run_series_range(EspbResampleBatch *c, int series_first, int n_series, const
   CU_TRY(cudaMemcpy2DAsync(x_new, rows * row_bytes, x_old + (size_t) c->carry_row * kSeriesPerRow, rows * row_bytes,
                            taps * row_bytes, ng, cudaMemcpyDeviceToDevice, stream),
          "carry copy");
-  CU_TRY(launch_transpose(in, il.stream_stride, il.channel_stride, il.frame_stride, c->channels, n_series, n_in,
-                          x_new, rows, taps, kChunkRows, stream),
-         "transpose kernel");
-  if (pre && pre->params && n_in > 0)  // resampler.cpp:126-133, on the staged rows [taps, taps + n_in)
-    CU_TRY(launch_biquad_tm(x_new, rows, taps, n_in, n_series, pre->sections, *pre->params, pre->state, stream),
+  const bool pre_on = pre && pre->params && n_in > 0;
+  const bool pre_blocks = pre_on && pre->block_rows > 0 && n_in > pre->block_rows;
+  if (pre_blocks) {
+    // time-block pre-filter is out of place: the raw frames go to the other staging buffer (its carry rows
+    // were copied above, the rest is free), the filter writes the rows the resampler reads
+    float *x_raw = c->xt[c->xt_cur].as<float>() + (size_t) g0 * rows * kSeriesPerRow;
+    CU_TRY(launch_transpose(in, il.stream_stride, il.channel_stride, il.frame_stride, c->channels, n_series, n_in,
+                            x_raw, rows, taps, 0, stream),
+           "transpose kernel");
+    CU_TRY(cudaMemset2DAsync(x_new + (size_t) (taps + n_in) * kSeriesPerRow, rows * row_bytes, 0,
+                             kChunkRows * row_bytes, ng, stream),
+           "pad rows");
+    CU_TRY(launch_biquad_tm(x_raw, x_new, rows, taps, n_in, n_series, pre->sections, *pre->params, pre->state,
+                            pre->block_rows, pre->warm_rows, stream),
            "biquad kernel");
+  } else {
+    CU_TRY(launch_transpose(in, il.stream_stride, il.channel_stride, il.frame_stride, c->channels, n_series, n_in,
+                            x_new, rows, taps, kChunkRows, stream),
+           "transpose kernel");
+    if (pre_on)  // resampler.cpp:126-133, on the staged rows [taps, taps + n_in)
+      CU_TRY(launch_biquad_tm(x_new, x_new, rows, taps, n_in, n_series, pre->sections, *pre->params, pre->state, 0,
+                              0, stream),
+             "biquad kernel");
+  }
   const bool post_on = post && post->params && c->sched.generated > 0;
   float *y_tm = nullptr;
   if (post_on)
@@ -554,9 +573,16 @@ int run_series_range(EspbResampleBatch *c, int series_first, int n_series, const
   }
   if (post_on) {  // resampler.cpp:142-149, then back to the caller's layout
     const int gen = (int) c->sched.generated;
-    CU_TRY(launch_biquad_tm(y_tm, c->yt_rows, 0, gen, n_series, post->sections, *post->params, post->state, stream),
+    float *y_f = y_tm;
+    int blocks = 0;
+    if (post->block_rows > 0 && gen > post->block_rows && c->yt2_rows >= c->yt_rows) {
+      y_f = c->yt2.as<float>() + (size_t) g0 * c->yt_rows * kSeriesPerRow;
+      blocks = post->block_rows;
+    }
+    CU_TRY(launch_biquad_tm(y_tm, y_f, c->yt_rows, 0, gen, n_series, post->sections, *post->params, post->state,
+                            blocks, post->warm_rows, stream),
            "biquad kernel");
-    CU_TRY(launch_untranspose(y_tm, c->yt_rows, 0, gen, out, ol.stream_stride, ol.channel_stride, ol.frame_stride,
+    CU_TRY(launch_untranspose(y_f, c->yt_rows, 0, gen, out, ol.stream_stride, ol.channel_stride, ol.frame_stride,
                               c->channels, n_series, stream),
            "untranspose kernel");
   }
@@ -564,11 +590,16 @@ int run_series_range(EspbResampleBatch *c, int series_first, int n_series, const
 }
 
 // Scratch for time-major resampler output (post-filter path): at least `rows` rows per group.
-int ensure_yt(EspbResampleBatch *c, int64_t rows) {
-  if (rows <= c->yt_rows)
-    return ESPB_OK;
-  CU_TRY(c->yt.reserve((size_t) c->n_groups() * rows * kSeriesPerRow * sizeof(float)), "output scratch");
-  c->yt_rows = rows;
+int ensure_yt(EspbResampleBatch *c, int64_t rows, bool second) {
+  if (rows > c->yt_rows) {
+    CU_TRY(c->yt.reserve((size_t) c->n_groups() * rows * kSeriesPerRow * sizeof(float)), "output scratch");
+    c->yt_rows = rows;
+    c->yt2_rows = 0;
+  }
+  if (second && c->yt2_rows < c->yt_rows) {
+    CU_TRY(c->yt2.reserve((size_t) c->n_groups() * c->yt_rows * kSeriesPerRow * sizeof(float)), "output scratch");
+    c->yt2_rows = c->yt_rows;
+  }
   return ESPB_OK;
 }
 
@@ -631,6 +662,7 @@ void espb_resampleFree(EspbResampleBatch *c) {
   c->xt[0].release();
   c->xt[1].release();
   c->yt.release();
+  c->yt2.release();
   c->d_outs.release();
   c->d_chunks.release();
   c->d_pcb.release();
@@ -872,8 +904,9 @@ struct EspbBiquadBatch {
   int num_series = 0, num_sections = 0;
   BiquadParams params{};
   DevBuf state;
-  DevBuf tm;  // time-major scratch [group][tm_rows][128] for the stand-alone apply_buffer entry point
-  int64_t tm_rows = 0;
+  DevBuf tm, tm2;  // time-major scratch [group][tm_rows][128] (tm2: output side of the time-block mode)
+  int64_t tm_rows = 0, tm2_rows = 0;
+  int block_rows = 0, warm_rows = 0;  // 0: one sequential run per series (exact); else time blocks with warm-up
 };
 
 extern "C" {
@@ -915,6 +948,7 @@ void espb_biquad_free(EspbBiquadBatch *f) {
   if (!f)
     return;
   f->tm.release();
+  f->tm2.release();
   f->state.release();
   delete f;
 }
@@ -944,12 +978,29 @@ int espb_biquad_apply_buffer(EspbBiquadBatch *f, float *buf, const EspbLayout *l
   CU_TRY(launch_transpose(buf, layout->stream_stride, layout->channel_stride, layout->frame_stride, channels,
                           f->num_series, num_samples, f->tm.as<float>(), f->tm_rows, 0, 0, s),
          "transpose kernel");
-  CU_TRY(launch_biquad_tm(f->tm.as<float>(), f->tm_rows, 0, num_samples, f->num_series, f->num_sections, f->params,
-                          f->state.as<float>(), s),
+  float *filtered = f->tm.as<float>();
+  if (f->block_rows > 0 && num_samples > f->block_rows) {
+    if (f->tm_rows > f->tm2_rows) {
+      CU_TRY(f->tm2.reserve((size_t) n_groups * f->tm_rows * kSeriesPerRow * sizeof(float)), "biquad scratch");
+      f->tm2_rows = f->tm_rows;
+    }
+    filtered = f->tm2.as<float>();
+  }
+  CU_TRY(launch_biquad_tm(f->tm.as<float>(), filtered, f->tm_rows, 0, num_samples, f->num_series, f->num_sections,
+                          f->params, f->state.as<float>(), filtered == f->tm.as<float>() ? 0 : f->block_rows,
+                          f->warm_rows, s),
          "biquad kernel");
-  CU_TRY(launch_untranspose(f->tm.as<float>(), f->tm_rows, 0, num_samples, buf, layout->stream_stride,
+  CU_TRY(launch_untranspose(filtered, f->tm_rows, 0, num_samples, buf, layout->stream_stride,
                             layout->channel_stride, layout->frame_stride, channels, f->num_series, s),
          "untranspose kernel");
+  return ESPB_OK;
+}
+
+int espb_biquad_set_time_blocks(EspbBiquadBatch *f, int block_rows, int warmup_rows) {
+  if (!f || block_rows < 0 || warmup_rows < 0 || block_rows % 32 || warmup_rows % 32)
+    return fail(ESPB_ERR_ARG, "biquad_set_time_blocks: rows must be non-negative multiples of 32");
+  f->block_rows = block_rows;
+  f->warm_rows = warmup_rows;
   return ESPB_OK;
 }
 
@@ -1194,6 +1245,8 @@ int wrapper_run_range(EspbResampler *r, int s0, int ns, const uint8_t *d_in, int
       flt.params = &lp->params;
       flt.state = lp->state.as<float>() + (size_t) s0 * ch * lp->num_sections * 4;
       flt.sections = lp->num_sections;
+      flt.block_rows = lp->block_rows;
+      flt.warm_rows = lp->warm_rows;
     }
     // :126-149 — pre-filter, resampleProcessInterleaved, post-filter
     int rc = run_series_range(r->art, s0 * ch, ns * ch, fin, il, fout, ol, (int) wc.todo, stream, g_preexpanded,
@@ -1232,7 +1285,7 @@ int wrapper_plan(EspbResampler *r, size_t avail, size_t out_free, cudaStream_t s
     wc->used = r->art->sched.used;
     wc->generated = r->art->sched.generated;
     if (r->policy.post) {
-      rc = ensure_yt(r->art, (int64_t) wc->generated);
+      rc = ensure_yt(r->art, (int64_t) wc->generated, r->lowpass && r->lowpass->block_rows > 0);
       if (rc != ESPB_OK)
         return rc;
     }
@@ -1335,6 +1388,12 @@ int espb_resampler_set_mode(EspbResampler *r, int mode) {
   if (!r)
     return fail(ESPB_ERR_ARG, "resampler_set_mode: NULL");
   return r->art ? espb_resampleSetMode(r->art, mode) : ESPB_OK;
+}
+
+int espb_resampler_set_biquad_time_blocks(EspbResampler *r, int block_rows, int warmup_rows) {
+  if (!r)
+    return fail(ESPB_ERR_ARG, "resampler_set_biquad_time_blocks: NULL");
+  return r->lowpass ? espb_biquad_set_time_blocks(r->lowpass, block_rows, warmup_rows) : ESPB_OK;
 }
 
 int espb_resampler_policy(EspbResampler *r, EspbBiquadCoefficients *coeffs, float *sample_ratio, float *art_lowpass,

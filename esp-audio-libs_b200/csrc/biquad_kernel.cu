@@ -15,6 +15,13 @@
 // contiguous) are streamed through a 4-stage shared-memory ring by TMA bulk loads, filtered in
 // place by the thread that owns the column, and written back by TMA bulk stores — HBM sees only
 // full 16 KB transfers, the threads only conflict-free LDS/STS.
+//
+// Long single streams (few series, many rows) additionally offer time blocks (blockIdx.y): block k
+// filters rows [k*L, (k+1)*L) after re-running the recurrence over the W rows before it from a zero
+// state ("warm-up"), out of place.  Once the two trajectories (true state vs zero start) have rounded to
+// the same two consecutive outputs they stay bit-identical; measured on the CPU oracle this happens
+// within 64 rows for pole radius 0.49, 256 for 0.77, 4096 for 0.92, and never for 0.98 (SURVEY.md §5
+// lists 1.2e-7..1.8e-6 for the superposition form of the same idea).  Opt-in; the default is one block.
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -81,21 +88,33 @@ __device__ __forceinline__ float section_step(Section &s, float x, const BiquadP
   return sum;
 }
 
-// buf: first group of the launch; rows [row_first, row_first + n_rows) of every group are filtered in place.
+// src/dst: first group of the launch (may be the same buffer when there is one time block); rows
+// [row_first, row_first + n_rows) of every group are filtered.  blockIdx.y = time block of block_rows rows
+// (0 = all rows in one block) preceded by warm_rows rows of warm-up.
 template <int NSEC, bool FIRST_ORDER>
 __global__ void __launch_bounds__(SGN)
-    espb_biquad_tm_kernel(float *__restrict__ buf, int64_t rows_cap, int row_first, int n_rows, BiquadParams c,
-                          float *__restrict__ state, int n_series) {
+    espb_biquad_tm_kernel(const float *src, float *dst, int64_t rows_cap, int row_first, int n_rows, BiquadParams c,
+                          float *__restrict__ state, int n_series, int block_rows, int warm_rows) {
   extern __shared__ __align__(128) unsigned char bq_smem[];
   float (*ring)[RB][SGN] = reinterpret_cast<float (*)[RB][SGN]>(bq_smem);  // [BSTAGES][RB][SGN]
   uint64_t *full = reinterpret_cast<uint64_t *>(bq_smem + sizeof(float) * BSTAGES * RB * SGN);
   const int tid = threadIdx.x;
   const int q = blockIdx.x * SGN + tid;
-  float *gbase = buf + ((int64_t) blockIdx.x * rows_cap + row_first) * SGN;
-  const int n_chunks = (n_rows + RB - 1) / RB;
+  // this CTA's time block: rows [blk_lo, blk_hi), started warm_rows earlier (block 0 starts from the saved state)
+  const int blk = blockIdx.y;
+  const int blk_lo = block_rows > 0 ? blk * block_rows : 0;
+  const int blk_hi = (block_rows > 0 && blk_lo + block_rows < n_rows) ? blk_lo + block_rows : n_rows;
+  const int run_lo = (blk == 0 || blk_lo < warm_rows) ? 0 : blk_lo - warm_rows;
+  const bool from_saved_state = (run_lo == 0);
+  const bool last_block = (blk_hi == n_rows);
+  const float *gsrc = src + ((int64_t) blockIdx.x * rows_cap + row_first + run_lo) * SGN;
+  float *gdst = dst + ((int64_t) blockIdx.x * rows_cap + row_first + run_lo) * SGN;
+  const int run_rows = blk_hi - run_lo;
+  const int n_chunks = (run_rows + RB - 1) / RB;
+  const int first_store_chunk = (blk_lo - run_lo) / RB;  // warm-up chunks are filtered but not written
 
   Section sec[NSEC];
-  if (q < n_series) {
+  if (q < n_series && from_saved_state) {
 #pragma unroll
     for (int k = 0; k < NSEC; ++k) {
       const float4 v = *reinterpret_cast<const float4 *>(state + ((int64_t) q * NSEC + k) * 4);
@@ -110,12 +129,12 @@ __global__ void __launch_bounds__(SGN)
       sec[k].in_d1 = sec[k].in_d2 = sec[k].out_d1 = sec[k].out_d2 = 0.0f;
   }
 
-  auto chunk_rows = [&](int k) { return (k + 1) * RB <= n_rows ? RB : n_rows - k * RB; };
+  auto chunk_rows = [&](int k) { return (k + 1) * RB <= run_rows ? RB : run_rows - k * RB; };
   auto load_chunk = [&](int k) {
     const int st = k % BSTAGES;
     const uint32_t bytes = (uint32_t) chunk_rows(k) * SGN * sizeof(float);
     mbar_expect_tx(&full[st], bytes);
-    tma_load(&ring[st][0][0], gbase + (int64_t) k * RB * SGN, bytes, &full[st]);
+    tma_load(&ring[st][0][0], gsrc + (int64_t) k * RB * SGN, bytes, &full[st]);
   };
 
   if (tid == 0) {
@@ -155,8 +174,9 @@ __global__ void __launch_bounds__(SGN)
     asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
     __syncthreads();
     if (tid == 0) {
-      tma_store(gbase + (int64_t) k * RB * SGN, &ring[st][0][0], (uint32_t) rows * SGN * sizeof(float));
-      asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
+      if (k >= first_store_chunk)
+        tma_store(gdst + (int64_t) k * RB * SGN, &ring[st][0][0], (uint32_t) rows * SGN * sizeof(float));
+      asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");  // (possibly empty) group keeps the count uniform
       if (k + BSTAGES - 1 < n_chunks) {
         // stage (k-1) % BSTAGES is reused: its store (issued last iteration) must have read shared memory
         asm volatile("cp.async.bulk.wait_group.read 1;\n" ::: "memory");
@@ -167,7 +187,7 @@ __global__ void __launch_bounds__(SGN)
   if (tid == 0)
     asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory");
 
-  if (q < n_series) {
+  if (q < n_series && last_block) {
 #pragma unroll
     for (int k = 0; k < NSEC; ++k)
       *reinterpret_cast<float4 *>(state + ((int64_t) q * NSEC + k) * 4) =
@@ -176,9 +196,10 @@ __global__ void __launch_bounds__(SGN)
 }
 
 template <int NSEC>
-cudaError_t launch_tm(float *buf, int64_t rows_cap, int row_first, int n_rows, int n_series, const BiquadParams &c,
-                      float *state, cudaStream_t stream) {
-  const unsigned grid = (n_series + SGN - 1) / SGN;
+cudaError_t launch_tm(const float *src, float *dst, int64_t rows_cap, int row_first, int n_rows, int n_series,
+                      const BiquadParams &c, float *state, int block_rows, int warm_rows, cudaStream_t stream) {
+  const int n_blocks = block_rows > 0 ? (n_rows + block_rows - 1) / block_rows : 1;
+  const dim3 grid((n_series + SGN - 1) / SGN, n_blocks);
   const size_t smem = sizeof(float) * BSTAGES * RB * SGN + BSTAGES * sizeof(uint64_t);
   static bool configured = false;
   if (!configured) {
@@ -192,30 +213,35 @@ cudaError_t launch_tm(float *buf, int64_t rows_cap, int row_first, int n_rows, i
     configured = true;
   }
   if (c.first_order)
-    espb_biquad_tm_kernel<NSEC, true><<<grid, SGN, smem, stream>>>(buf, rows_cap, row_first, n_rows, c, state,
-                                                                   n_series);
+    espb_biquad_tm_kernel<NSEC, true><<<grid, SGN, smem, stream>>>(src, dst, rows_cap, row_first, n_rows, c, state,
+                                                                   n_series, block_rows, warm_rows);
   else
-    espb_biquad_tm_kernel<NSEC, false><<<grid, SGN, smem, stream>>>(buf, rows_cap, row_first, n_rows, c, state,
-                                                                    n_series);
+    espb_biquad_tm_kernel<NSEC, false><<<grid, SGN, smem, stream>>>(src, dst, rows_cap, row_first, n_rows, c, state,
+                                                                    n_series, block_rows, warm_rows);
   count_launch();
   return cudaGetLastError();
 }
 
 }  // namespace
 
-cudaError_t launch_biquad_tm(float *buf, int64_t rows_cap, int row_first, int n_rows, int n_series, int n_sections,
-                             BiquadParams c, float *state, cudaStream_t stream) {
+cudaError_t launch_biquad_tm(const float *src, float *dst, int64_t rows_cap, int row_first, int n_rows, int n_series,
+                             int n_sections, BiquadParams c, float *state, int block_rows, int warm_rows,
+                             cudaStream_t stream) {
   if (n_series <= 0 || n_rows <= 0)
     return cudaSuccess;
+  if (block_rows > 0 && (block_rows % RB || warm_rows % RB || src == dst))
+    return cudaErrorInvalidValue;  // time blocks: multiples of the 32-row chunk, and out of place
+  if (block_rows >= n_rows)
+    block_rows = 0;
   switch (n_sections) {
     case 1:
-      return launch_tm<1>(buf, rows_cap, row_first, n_rows, n_series, c, state, stream);
+      return launch_tm<1>(src, dst, rows_cap, row_first, n_rows, n_series, c, state, block_rows, warm_rows, stream);
     case 2:
-      return launch_tm<2>(buf, rows_cap, row_first, n_rows, n_series, c, state, stream);
+      return launch_tm<2>(src, dst, rows_cap, row_first, n_rows, n_series, c, state, block_rows, warm_rows, stream);
     case 3:
-      return launch_tm<3>(buf, rows_cap, row_first, n_rows, n_series, c, state, stream);
+      return launch_tm<3>(src, dst, rows_cap, row_first, n_rows, n_series, c, state, block_rows, warm_rows, stream);
     case 4:
-      return launch_tm<4>(buf, rows_cap, row_first, n_rows, n_series, c, state, stream);
+      return launch_tm<4>(src, dst, rows_cap, row_first, n_rows, n_series, c, state, block_rows, warm_rows, stream);
     default:
       return cudaErrorInvalidValue;
   }

@@ -45,9 +45,11 @@ struct BiquadParams {
   float a0, a1, a2, b1, b2;
   int first_order;
 };
-// time-major in-place filter: rows [row_first, row_first + n_rows) of buf[group][rows_cap][128]
-cudaError_t launch_biquad_tm(float *buf, int64_t rows_cap, int row_first, int n_rows, int n_series, int n_sections,
-                             BiquadParams c, float *state /* [series][section][4] */, cudaStream_t stream);
+// time-major filter of rows [row_first, row_first + n_rows) of src[group][rows_cap][128] into dst (same
+// geometry; may be src itself when block_rows == 0).  block_rows > 0: time blocks with warm_rows of warm-up.
+cudaError_t launch_biquad_tm(const float *src, float *dst, int64_t rows_cap, int row_first, int n_rows, int n_series,
+                             int n_sections, BiquadParams c, float *state /* [series][section][4] */,
+                             int block_rows, int warm_rows, cudaStream_t stream);
 // time-major -> caller layout (inverse of launch_transpose): rows [row_first, row_first + n_rows)
 cudaError_t launch_untranspose(const float *tm, int64_t rows_cap, int row_first, int n_rows, float *out,
                                int64_t out_ss, int64_t out_cs, int64_t out_fs, int channels, int n_series,

@@ -155,6 +155,13 @@ int espb_biquad_reset(EspbBiquadBatch *f, void *stream);
  * (stream q / channels, channel q % channels) of the layout. */
 int espb_biquad_apply_buffer(EspbBiquadBatch *f, float *buf, const EspbLayout *layout, int channels, int num_samples,
                              void *stream);
+/* Long single streams: filter time blocks of `block_rows` frames in parallel, each after re-running the
+ * recurrence over the `warmup_rows` frames before it from a zero state (multiples of 32; 0/0 = off, the
+ * default: one exact sequential run per series).  The two trajectories merge bit-exactly once they round to
+ * the same consecutive outputs — within 256 frames for the pole radii the Resampler policy produces
+ * (cutoff >= 0.16: radius <= 0.77), measured; not guaranteed for radii near 1 (cutoff < 0.02), where the
+ * deviation is ~1e-7..4e-6.  Use a warm-up of >= 1024 frames. */
+int espb_biquad_set_time_blocks(EspbBiquadBatch *f, int block_rows, int warmup_rows);
 int espb_biquad_get_state(EspbBiquadBatch *f, float *host_dst /* num_series*num_sections*4: in_d1,in_d2,out_d1,out_d2 */);
 
 /* ---- quantization_utils: replaces include/quantization_utils.h:15-25 ------------ */
@@ -205,6 +212,8 @@ EspbResampler *espb_resampler_create(int num_streams, size_t input_buffer_sample
                                      const EspbResamplerConfiguration *config);
 void espb_resampler_free(EspbResampler *r);
 int espb_resampler_set_mode(EspbResampler *r, int mode);
+/* time-block mode of the pre/post low-pass (see espb_biquad_set_time_blocks) */
+int espb_resampler_set_biquad_time_blocks(EspbResampler *r, int block_rows, int warmup_rows);
 /* policy introspection: 0 none / 1 pre / 2 post; coefficients; ART low-pass and flags */
 int espb_resampler_policy(EspbResampler *r, EspbBiquadCoefficients *coeffs, float *sample_ratio, float *art_lowpass,
                           int *art_flags);

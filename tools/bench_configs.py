@@ -20,18 +20,24 @@ f32 = np.float32
 L = espb.lib()
 
 
-def timed(fn, reps=5, warm=2):
+def timed(fn, reps=7, warm=3):
+    """Median per-call time from CUDA events around each call (first calls allocate scratch)."""
     for _ in range(warm):
         fn()
     L.espb_device_sync()
-    ev0, ev1 = L.espb_event_create(), L.espb_event_create()
-    L.espb_event_record(ev0, None)
+    times = []
     for _ in range(reps):
+        ev0, ev1 = L.espb_event_create(), L.espb_event_create()
+        L.espb_event_record(ev0, None)
         fn()
-    L.espb_event_record(ev1, None)
-    ms = espb.capi.C.c_float(0)
-    L.espb_event_elapsed_ms(ev0, ev1, espb.capi.C.byref(ms))
-    return ms.value / reps
+        L.espb_event_record(ev1, None)
+        ms = espb.capi.C.c_float(0)
+        L.espb_event_elapsed_ms(ev0, ev1, espb.capi.C.byref(ms))
+        times.append(ms.value)
+        L.espb_event_destroy(ev0)
+        L.espb_event_destroy(ev1)
+    times.sort()
+    return times[len(times) // 2], times
 
 
 def pcm_noise(ns, n, bits, rng):
@@ -44,10 +50,12 @@ def pcm_noise(ns, n, bits, rng):
     return np.tile(raw, (reps, 1))[:ns]
 
 
-def run_wrapper(name, ns, ch, src, dst, sb, db, taps, filters, frames, mode=espb.MODE_FAST):
+def run_wrapper(name, ns, ch, src, dst, sb, db, taps, filters, frames, mode=espb.MODE_FAST, blocks=None):
     rng = np.random.default_rng(1)
     cap = int(frames * dst / src) + 64
     r = espb.Resampler(ns, frames * ch, cap * ch, src, dst, sb, db, ch, True, True, taps, filters, mode=mode)
+    if blocks:
+        r.set_biquad_time_blocks(*blocks)
     raw = pcm_noise(ns, frames * ch, sb, rng)
     d_in = espb.DeviceBuffer.from_numpy(raw)
     ob = (db + 7) // 8
@@ -59,12 +67,13 @@ def run_wrapper(name, ns, ch, src, dst, sb, db, taps, filters, frames, mode=espb
         # steady-state streaming: state carries from call to call (no reset), as a real stream would
         res["r"] = r.resample_dev(d_in.ptr, raw.shape[1], d_out.ptr, out_row, frames, cap, 0.0)
 
-    ms = timed(step)
+    ms, all_ms = timed(step)
     gen = res["r"]["frames_generated"]
     samples = gen * ch * ns
     pol = r.policy()
     line = dict(config=name, streams=ns, channels=ch, src_rate=src, dst_rate=dst, bits=(sb, db), taps=taps,
                 filters=filters, frames_in=frames, frames_out=gen, filter=pol["filter"], ms_per_call=ms,
+                ms_all=[round(t, 2) for t in all_ms],
                 msamples_per_s=samples / ms / 1e3, flop_per_sample=4 * taps,
                 resampler_tflops_if_all_time=4 * taps * samples / ms / 1e9)
     print(json.dumps(line), flush=True)
@@ -82,6 +91,8 @@ def main():
     if "c4" in which:  # 96 kHz -> 44.1 kHz, 8 channels, 24-bit, 1024 taps, long streams (10 s per call), few streams
         run_wrapper("C4 96k->44.1k 8ch int24 T=1024, pre-biquad", max(int(32 * scale), 1), 8, 96000, 44100, 24, 24,
                     1024, 256, 960000)
+        run_wrapper("C4 same, pre-biquad in time blocks of 8192 frames (1024 warm-up)", max(int(32 * scale), 1), 8,
+                    96000, 44100, 24, 24, 1024, 256, 960000, blocks=(8192, 1024))
     if "c5" in which:  # 48 -> 44.1 kHz stereo f32-equivalent (32-bit PCM), low-pass, 8192 streams (= 65536 / 8 GPUs)
         run_wrapper("C5 shard 48k->44.1k stereo int32, pre-biquad, 8192 streams", int(8192 * scale), 2, 48000, 44100,
                     32, 32, 256, 256, 48000)
