@@ -360,7 +360,7 @@ int prepare_call(EspbResampleBatch *c, int n_in, int n_out, float ratio, cudaStr
     return ESPB_OK;
   c->plan_on_device = false;
   c->g_resident_first = c->g_resident_end = -1;
-  build_schedule(c->geo, c->state, n_in, n_out, ratio, c->sched);
+  build_schedule(c->geo, c->state, n_in, n_out, ratio, c->sched, /*finalize=*/false);  // pass 2 runs on the device
   build_pass_plan(c->sched, c->geo.taps, c->bpp, c->plan);
   c->key = k;
   if (c->sched.generated == 0) {
@@ -373,6 +373,9 @@ int prepare_call(EspbResampleBatch *c, int n_in, int n_out, float ratio, cudaStr
   CU_TRY(cudaMemcpyAsync(c->d_outs.p, c->sched.outs.data(), c->sched.outs.size() * sizeof(OutEntry),
                          cudaMemcpyHostToDevice, stream),
          "upload schedule");
+  CU_TRY(launch_finalize(c->d_outs.as<OutEntry>(), (int) c->sched.outs.size(), c->geo.filters,
+                         (c->geo.flags & kFlagLowpass) != 0, (c->geo.flags & kFlagInterpolate) != 0, stream),
+         "finalize kernel");
   CU_TRY(cudaMemcpyAsync(c->d_chunks.p, c->plan.chunks.data(), c->plan.chunks.size() * sizeof(ChunkEntry),
                          cudaMemcpyHostToDevice, stream),
          "upload chunks");
@@ -1264,33 +1267,32 @@ int wrapper_run_range(EspbResampler *r, int s0, int ns, const uint8_t *d_in, int
 
 // The host-known part of the call: frames_to_process and the schedule.
 int wrapper_plan(EspbResampler *r, size_t avail, size_t out_free, cudaStream_t stream, WrapperCall *wc) {
-  size_t todo = avail;
-  if (r->policy.resampling) {  // :104-107
-    const size_t need = espb_resampleGetRequiredSamples(r->art, (int) out_free, r->policy.sample_ratio);
-    if (need < todo)
-      todo = need;
-  } else if (out_free < todo) {
-    todo = out_free;
-  }
   const size_t ch = r->cfg.channels;
-  if (todo * ch > (r->policy.resampling ? r->in_samples : r->out_samples))
+  if (!r->policy.resampling) {  // :108-110, :116-119 — conversion only
+    const size_t todo = out_free < avail ? out_free : avail;
+    if (todo * ch > r->out_samples)
+      return fail(ESPB_ERR_ARG, "resample: frames exceed the float buffer size given at construction");
+    wc->todo = wc->used = wc->generated = todo;
+    return ESPB_OK;
+  }
+  // :104-107 caps the input at resampleGetRequiredSamples(output_frames_free).  Running the state machine
+  // once over (all available frames, output_frames_free) stops at exactly that frame — the loop ends with
+  // the last output, before it would consume another frame — so frames_to_process == frames_used and the
+  // separate dry run is not needed.
+  int rc = prepare_call(r->art, (int) avail, (int) out_free, r->policy.sample_ratio, stream);
+  if (rc != ESPB_OK)
+    return rc;
+  wc->used = r->art->sched.used;
+  wc->todo = wc->used;
+  wc->generated = r->art->sched.generated;
+  if (wc->todo * ch > r->in_samples)
     return fail(ESPB_ERR_ARG, "resample: frames exceed the float buffer size given at construction");
-  wc->todo = todo;
-  wc->used = todo;
-  wc->generated = todo;
-  if (r->policy.resampling) {
-    int rc = prepare_call(r->art, (int) todo, (int) out_free, r->policy.sample_ratio, stream);
+  if (wc->generated * ch > r->out_samples)
+    return fail(ESPB_ERR_ARG, "resample: output exceeds the float buffer size given at construction");
+  if (r->policy.post) {
+    rc = ensure_yt(r->art, (int64_t) wc->generated, r->lowpass && r->lowpass->block_rows > 0);
     if (rc != ESPB_OK)
       return rc;
-    wc->used = r->art->sched.used;
-    wc->generated = r->art->sched.generated;
-    if (r->policy.post) {
-      rc = ensure_yt(r->art, (int64_t) wc->generated, r->lowpass && r->lowpass->block_rows > 0);
-      if (rc != ESPB_OK)
-        return rc;
-    }
-    if (wc->generated * ch > r->out_samples)
-      return fail(ESPB_ERR_ARG, "resample: output exceeds the float buffer size given at construction");
   }
   return ESPB_OK;
 }

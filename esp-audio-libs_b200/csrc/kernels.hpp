@@ -27,6 +27,7 @@ struct ResampleParams {
 
 size_t resample_smem_bytes(int bpp);
 size_t g_chunk_floats(int bpp);
+cudaError_t launch_finalize(OutEntry *outs, int n, int n_filters, bool lowpass, bool interp, cudaStream_t stream);
 cudaError_t launch_expand(const float *bank, const OutEntry *outs, const ChunkEntry *chunks, float *G,
                           int chunk_first, int n_chunks, int n_out, int taps, int bpp, cudaStream_t stream);
 cudaError_t launch_resample(const ResampleParams &p, int bpp, bool exact, cudaStream_t stream);

@@ -80,8 +80,9 @@ float position_of(const ArtGeometry &g, ArtState st) { return st.offset + ((floa
 
 namespace {
 
-// The signal-independent core of the reference loop.  `emit(offset, base)` is called for
-// every output with the pre-increment offset and the accumulated ring rebase.
+// The signal-independent core of the reference loop.  `emit(offset, base)` is called for every output with
+// the pre-increment offset and the accumulated ring rebase.  (A closed-form jump over runs of "consume"
+// steps was measured slower than this loop: the steps are cheap and well predicted.)
 template <typename Emit>
 inline void run_machine(const ArtGeometry &g, ArtState &st, int n_in, int n_out, float ratio, bool stop_on_input,
                         bool stop_on_output, unsigned *used, unsigned *generated, Emit emit) {
@@ -120,37 +121,67 @@ inline void run_machine(const ArtGeometry &g, ArtState &st, int n_in, int n_out,
 
 }  // namespace
 
-void build_schedule(const ArtGeometry &g, ArtState start, int n_in, int n_out, float ratio, Schedule &s) {
+// floorf for the non-negative values of the state machine (offsets live in [0, 16*taps), phase products in
+// [0, filters]): truncation is the same value and avoids a libm call per output.
+static inline float floor_nonneg(float v) { return (float) (int) v; }
+
+void build_schedule(const ArtGeometry &g, ArtState start, int n_in, int n_out, float ratio, Schedule &s,
+                    bool finalize) {
+  // Upper bound on the outputs of this call: capacity, and what the input can feed — every output moves the
+  // offset by 1/ratio, and the offset can run at most (frames available + what is already buffered) ahead.
+  size_t cap = n_out > 0 ? (size_t) n_out : 0;
+  {
+    const double room = (double) (n_in > 0 ? n_in : 0) + (double) start.index - (double) start.offset + 2.0;
+    const double feed = room * (double) ratio + 16.0;
+    if (feed < (double) cap)
+      cap = feed > 0.0 ? (size_t) feed : 0;
+  }
   s.outs.clear();
-  if (n_out > 0)
-    s.outs.reserve((size_t) n_out < (size_t) 1 << 24 ? n_out : 1 << 24);
+  s.outs.reserve(cap + 1);
+  // Pass 1 (sequential, branchy): the state machine records, per output, the offset (in .w) and the ring
+  // rebase folded into a window-start base (in .ws).  Pass 2 (finalize_entries, independent per output; on
+  // the device in the processing path): window start, phase, weight and kind from the offset
+  // (art_resampler.cpp:421-451), written into the same 16-byte entries.
   const int half = g.taps / 2, idx0 = start.index;
-  const bool lowpass = (g.flags & kFlagLowpass) != 0, interp = (g.flags & kFlagInterpolate) != 0;
-  const float nf = (float) g.filters;
   ArtState st = start;
   run_machine(g, st, n_in, n_out, ratio, true, true, &s.used, &s.generated, [&](float off, long long base) {
-    const float fl = floorf(off);
+    OutEntry e;
+    e.ws = (int32_t) (base - half + 1 - idx0);
+    e.w = off;
+    s.outs.push_back(e);  // grows if the bound above was ever too small
+  });
+  s.end = st;
+  s.raw = !finalize;
+  if (finalize)
+    finalize_entries(g, s.outs.data(), s.outs.size());
+}
+
+void finalize_entries(const ArtGeometry &g, OutEntry *out, size_t n) {
+  const bool lowpass = (g.flags & kFlagLowpass) != 0, interp = (g.flags & kFlagInterpolate) != 0;
+  const float nf = (float) g.filters;
+  for (size_t k = 0; k < n; ++k) {
+    const float off = out[k].w;
+    const float fl = floor_nonneg(off);
     float frac = off - fl;
     OutEntry e;
-    e.ws = (int32_t) (base + (long long) (int) fl - half + 1 - idx0);
+    e.ws = out[k].ws + (int32_t) fl;
     e.phase = 0;
     e.w = 0.0f;
     if (frac == 0.0f && !lowpass) {
       e.kind = kKindPass;
     } else if (!interp) {
       e.kind = kKindSingle;
-      e.phase = (int) floorf(frac * nf + 0.5f);
+      e.phase = (int) floor_nonneg(frac * nf + 0.5f);
     } else {
       frac *= nf;
-      const int i = (int) floorf(frac);
+      const int i = (int) floor_nonneg(frac);
       frac -= (float) i;
       e.phase = i;
       e.w = frac;
       e.kind = (frac == 0.0f && !lowpass) ? kKindSingle : kKindBlend;
     }
-    s.outs.push_back(e);
-  });
-  s.end = st;
+    out[k] = e;
+  }
 }
 
 unsigned required_samples(const ArtGeometry &g, ArtState st, int n_out, float ratio) {
@@ -165,16 +196,27 @@ unsigned expected_output(const ArtGeometry &g, ArtState st, int n_in, float rati
   return gen;
 }
 
+static inline int32_t entry_ws(const Schedule &s, int k) {
+  return s.raw ? s.outs[k].ws + (int32_t) s.outs[k].w : s.outs[k].ws;  // raw: base + floor(offset)
+}
+
 void build_pass_plan(const Schedule &s, int taps, int blocks_per_pass, PassPlan &p) {
   const int opp = blocks_per_pass * kOutputsPerBlock;
   const int n = (int) s.outs.size();
   p.outputs_per_pass = opp;
   p.chunks.clear();
   p.pass_chunk_begin.clear();
+  if (n > 0) {  // windows advance monotonically: the last pass's span bounds the chunk count per pass well enough
+    const size_t n_passes = ((size_t) n + opp - 1) / opp;
+    const long long span = (long long) entry_ws(s, n - 1) - entry_ws(s, 0);
+    const size_t per_pass = (size_t) ((span / (long long) n_passes + taps) / kChunkRows + 3);
+    p.chunks.reserve(n_passes * per_pass);
+    p.pass_chunk_begin.reserve(n_passes + 1);
+  }
   p.pass_chunk_begin.push_back(0);
   for (int first = 0, pass = 0; first < n; first += opp, ++pass) {
     const int last = (first + opp < n ? first + opp : n) - 1;
-    const int j0 = s.outs[first].ws, j1 = s.outs[last].ws + taps;
+    const int j0 = entry_ws(s, first), j1 = entry_ws(s, last) + taps;
     for (int j = j0; j < j1; j += kChunkRows)
       p.chunks.push_back(ChunkEntry{j, pass});
     p.pass_chunk_begin.push_back((int32_t) p.chunks.size());

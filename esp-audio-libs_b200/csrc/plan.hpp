@@ -1,6 +1,8 @@
 // Host-side planning for the B200 ART resampler path: everything that is
 // signal-independent is computed here once per call and shared by all streams.
 #pragma once
+#include <stdlib.h>
+
 #include <vector>
 
 #include "common.hpp"
@@ -29,15 +31,48 @@ void build_filter_bank(const ArtGeometry &g, float lowpass, std::vector<float> &
 
 ArtState initial_state(int taps);  // art_resampler.cpp:135-136
 
+// Growable array of plain structs without value-initialisation (the schedule tables are written once,
+// front to back, right after sizing).
+template <typename T>
+struct PodBuffer {
+  T *ptr = nullptr;
+  size_t count = 0, cap = 0;
+  PodBuffer() = default;
+  PodBuffer(const PodBuffer &) = delete;
+  PodBuffer &operator=(const PodBuffer &) = delete;
+  ~PodBuffer() { free(ptr); }
+  void reserve(size_t n) {
+    if (n > cap) {
+      ptr = static_cast<T *>(realloc(ptr, n * sizeof(T)));
+      cap = n;
+    }
+  }
+  void clear() { count = 0; }
+  void push_back(const T &v) {
+    if (count == cap)
+      reserve(cap ? cap * 2 : 1024);
+    ptr[count++] = v;
+  }
+  T *data() { return ptr; }
+  const T *data() const { return ptr; }
+  size_t size() const { return count; }
+  T &operator[](size_t i) { return ptr[i]; }
+  const T &operator[](size_t i) const { return ptr[i]; }
+};
+
 struct Schedule {
-  std::vector<OutEntry> outs;
+  PodBuffer<OutEntry> outs;
   unsigned used = 0, generated = 0;
   ArtState end{};
+  bool raw = false;  // entries still hold (window-start base, offset): finalize_entries() not applied yet
 };
 
 // Data-free run of the resampleProcess state machine (art_resampler.cpp:172-199 /
 // :213-240) that records, per output, the window start / phase / weight / kind.
-void build_schedule(const ArtGeometry &g, ArtState start, int n_in, int n_out, float ratio, Schedule &s);
+void build_schedule(const ArtGeometry &g, ArtState start, int n_in, int n_out, float ratio, Schedule &s,
+                    bool finalize = true);
+// Second pass of the schedule (host version; espb_finalize_kernel is the device twin).
+void finalize_entries(const ArtGeometry &g, OutEntry *entries, size_t n);
 
 unsigned required_samples(const ArtGeometry &g, ArtState st, int n_out, float ratio);  // :257-279
 unsigned expected_output(const ArtGeometry &g, ArtState st, int n_in, float ratio);    // :281-306
@@ -47,8 +82,8 @@ float position_of(const ArtGeometry &g, ArtState st);                           
 // sweeps input rows [ws(first), ws(last)+taps) in chunks of kChunkRows.
 struct PassPlan {
   int outputs_per_pass = 0;
-  std::vector<ChunkEntry> chunks;
-  std::vector<int32_t> pass_chunk_begin;  // n_passes + 1 prefix
+  PodBuffer<ChunkEntry> chunks;
+  PodBuffer<int32_t> pass_chunk_begin;  // n_passes + 1 prefix
   int n_passes() const { return (int) pass_chunk_begin.size() - 1; }
 };
 void build_pass_plan(const Schedule &s, int taps, int blocks_per_pass, PassPlan &p);

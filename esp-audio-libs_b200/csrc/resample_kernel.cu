@@ -111,6 +111,39 @@ __device__ __forceinline__ float mac(float g, float x, float acc) {
 }  // namespace
 
 // ---------------------------------------------------------------------------------
+// Second pass of the schedule on the device (twin of plan.cpp:finalize_entries; the same IEEE
+// operations, so the same bits): entries arrive as (window-start base, offset) and leave as
+// (window start, phase, weight, kind) — art_resampler.cpp:421-451.
+// ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+    espb_finalize_kernel(OutEntry *__restrict__ outs, int n, float n_filters, int lowpass, int interp) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n)
+    return;
+  const float off = outs[k].w;
+  const float fl = (float) (int) off;  // offsets are non-negative: truncation == floor
+  float frac = __fsub_rn(off, fl);
+  OutEntry e;
+  e.ws = outs[k].ws + (int32_t) fl;
+  e.phase = 0;
+  e.w = 0.0f;
+  if (frac == 0.0f && !lowpass) {
+    e.kind = kKindPass;
+  } else if (!interp) {
+    e.kind = kKindSingle;
+    e.phase = (int) __fadd_rn(__fmul_rn(frac, n_filters), 0.5f);
+  } else {
+    frac = __fmul_rn(frac, n_filters);
+    const int i = (int) frac;
+    frac = __fsub_rn(frac, (float) i);
+    e.phase = i;
+    e.w = frac;
+    e.kind = (frac == 0.0f && !lowpass) ? kKindSingle : kKindBlend;
+  }
+  outs[k] = e;
+}
+
+// ---------------------------------------------------------------------------------
 // G expansion: one CTA per chunk, one float4 (two outputs x two filters) per thread-iteration.
 // ---------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) espb_expand_kernel(const float *__restrict__ bank,
@@ -551,6 +584,14 @@ size_t resample_smem_bytes(int bpp) {
 }
 
 size_t g_chunk_floats(int bpp) { return (size_t) CJ * bpp * kGRowFloats; }
+
+cudaError_t launch_finalize(OutEntry *outs, int n, int n_filters, bool lowpass, bool interp, cudaStream_t stream) {
+  if (n <= 0)
+    return cudaSuccess;
+  espb_finalize_kernel<<<(n + 255) / 256, 256, 0, stream>>>(outs, n, (float) n_filters, lowpass, interp);
+  count_launch();
+  return cudaGetLastError();
+}
 
 cudaError_t launch_expand(const float *bank, const OutEntry *outs, const ChunkEntry *chunks, float *G,
                           int chunk_first, int n_chunks, int n_out, int taps, int bpp, cudaStream_t stream) {
