@@ -326,13 +326,22 @@ def main():
     except Exception:
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    traffic = None  # dram bytes per launch of the dominant kernel, from the committed ncu capture
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as fh:
+            traffic = json.load(fh)
+    except Exception:
+        pass
     roofline = {
         "kernel": "espb_resample_kernel<8,false,false>", "bound": "fp32_fma", "achieved": achieved_tf,
         "peak": fma_tflops, "unit": "TFLOP/s", "frac": achieved_tf / fma_tflops if fma_tflops else None,
         "peak_source": "FMA-only probes (espb_measure_fp32_fma_peak: best of scalar FFMA and packed FFMA2) on this "
                        "GPU in this run; nominal 148 SM x 128 lanes x 2 x 1.965 GHz = 74.4",
         "peak_probe_ffma_tflops": fma_scalar, "peak_probe_ffma2_tflops": fma_packed,
-        "peak_implied_sm_mhz": fma_clock, "traffic": None,
+        "peak_implied_sm_mhz": fma_clock,
+        "traffic": (traffic or {}).get("dram_bytes_per_launch") if ns == STREAMS_PER_GPU else None,
+        "traffic_source": (traffic or {}).get("source"),
+        "algorithmic_bytes_per_launch": bytes_per_launch,
         "flop_per_sample": FLOP_PER_SAMPLE, "kernel_ms": k_ms, "kernel_share_of_step": kernel_ms / total_ms,
         "hbm": {"achieved_gbs": bytes_per_launch / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0, "peak_gbs": hbm_peak,
                 "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6.65 TB/s",

@@ -474,6 +474,25 @@ int ensure_xt(EspbResampleBatch *c, int64_t rows) {
   return ESPB_OK;
 }
 
+// Packed-PCM endpoints of a wrapper call (Resampler::resample converts with quantization_utils on both
+// sides): when given, the conversion is fused into the layout stages instead of running as separate passes.
+struct PcmIn {
+  const uint8_t *data = nullptr;  // row of the first stream of the range
+  int64_t row_bytes = 0;
+  int bits = 0;
+  float gain_factor = 1.0f;
+  float *scratch = nullptr;  // stream-major float rows for what the fused kernel does not cover
+  int64_t scratch_row = 0;
+};
+struct PcmOut {
+  uint8_t *data = nullptr;
+  int64_t row_bytes = 0;
+  int bits = 0;
+  uint32_t *clipped = nullptr;  // per stream
+  float *scratch = nullptr;
+  int64_t scratch_row = 0;
+};
+
 // Optional in-library neighbours of the resampler (Resampler::resample's pre / post low-pass).
 struct StageFilter {
   const BiquadParams *params = nullptr;  // NULL: no filter
@@ -488,7 +507,8 @@ struct StageFilter {
 // scratch, which is filtered and then laid out as the caller wants.
 int run_series_range(EspbResampleBatch *c, int series_first, int n_series, const float *in, const EspbLayout &il,
                      float *out, const EspbLayout &ol, int n_in, cudaStream_t stream, bool g_preexpanded,
-                     const StageFilter *pre = nullptr, const StageFilter *post = nullptr) {
+                     const StageFilter *pre = nullptr, const StageFilter *post = nullptr,
+                     const PcmIn *pcm_in = nullptr, const PcmOut *pcm_out = nullptr) {
   const int taps = c->geo.taps;
   const int g0 = series_first / kSeriesPerRow, ng = (n_series + kSeriesPerRow - 1) / kSeriesPerRow;
   const int64_t rows = c->xt_rows;
@@ -498,15 +518,45 @@ int run_series_range(EspbResampleBatch *c, int series_first, int n_series, const
   CU_TRY(cudaMemcpy2DAsync(x_new, rows * row_bytes, x_old + (size_t) c->carry_row * kSeriesPerRow, rows * row_bytes,
                            taps * row_bytes, ng, cudaMemcpyDeviceToDevice, stream),
          "carry copy");
+  // caller's frames -> rows [taps, taps + n_in) of `dst` (+ `pad` zero rows): float layouts through the
+  // transposing stage; packed PCM through the fused conversion, with the stage-by-stage path for the tail
+  auto stage_input = [&](float *dst, int pad) -> int {
+    if (pcm_in) {
+      cudaError_t e = cudaSuccess;
+      const int n_streams = n_series / c->channels;
+      const int fast = launch_pcm_to_tm(pcm_in->data, pcm_in->row_bytes, pcm_in->bits, pcm_in->gain_factor,
+                                        c->channels, n_series, n_in, dst, rows, taps, stream, &e);
+      CU_TRY(e, "pcm_to_tm kernel");
+      if (fast < n_in) {
+        const int nbytes = (pcm_in->bits + 7) / 8;
+        CU_TRY(launch_q2f(pcm_in->data + (size_t) fast * c->channels * nbytes, pcm_in->row_bytes,
+                          pcm_in->scratch + (size_t) fast * c->channels, pcm_in->scratch_row, n_streams,
+                          (uint32_t) ((n_in - fast) * c->channels), pcm_in->bits, pcm_in->gain_factor, stream),
+               "q2f kernel");
+      }
+      if (fast > 0)
+        CU_TRY(launch_transpose_from(pcm_in->scratch, pcm_in->scratch_row, 1, c->channels, c->channels, n_series,
+                                     n_in, dst, rows, taps, fast, pad, stream),
+               "transpose kernel");
+      else  // layout not covered by the fused kernel: the two separate stages
+        CU_TRY(launch_transpose(pcm_in->scratch, pcm_in->scratch_row, 1, c->channels, c->channels, n_series, n_in,
+                                dst, rows, taps, pad, stream),
+               "transpose kernel");
+      return ESPB_OK;
+    }
+    CU_TRY(launch_transpose(in, il.stream_stride, il.channel_stride, il.frame_stride, c->channels, n_series, n_in,
+                            dst, rows, taps, pad, stream),
+           "transpose kernel");
+    return ESPB_OK;
+  };
   const bool pre_on = pre && pre->params && n_in > 0;
   const bool pre_blocks = pre_on && pre->block_rows > 0 && n_in > pre->block_rows;
   if (pre_blocks) {
     // time-block pre-filter is out of place: the raw frames go to the other staging buffer (its carry rows
     // were copied above, the rest is free), the filter writes the rows the resampler reads
     float *x_raw = c->xt[c->xt_cur].as<float>() + (size_t) g0 * rows * kSeriesPerRow;
-    CU_TRY(launch_transpose(in, il.stream_stride, il.channel_stride, il.frame_stride, c->channels, n_series, n_in,
-                            x_raw, rows, taps, 0, stream),
-           "transpose kernel");
+    if (int rc = stage_input(x_raw, 0))
+      return rc;
     CU_TRY(cudaMemset2DAsync(x_new + (size_t) (taps + n_in) * kSeriesPerRow, rows * row_bytes, 0,
                              kChunkRows * row_bytes, ng, stream),
            "pad rows");
@@ -514,17 +564,17 @@ int run_series_range(EspbResampleBatch *c, int series_first, int n_series, const
                             pre->block_rows, pre->warm_rows, stream),
            "biquad kernel");
   } else {
-    CU_TRY(launch_transpose(in, il.stream_stride, il.channel_stride, il.frame_stride, c->channels, n_series, n_in,
-                            x_new, rows, taps, kChunkRows, stream),
-           "transpose kernel");
+    if (int rc = stage_input(x_new, kChunkRows))
+      return rc;
     if (pre_on)  // resampler.cpp:126-133, on the staged rows [taps, taps + n_in)
       CU_TRY(launch_biquad_tm(x_new, x_new, rows, taps, n_in, n_series, pre->sections, *pre->params, pre->state, 0,
                               0, stream),
              "biquad kernel");
   }
   const bool post_on = post && post->params && c->sched.generated > 0;
+  const bool tm_out = (post_on || pcm_out) && c->sched.generated > 0;  // a library stage follows the resampler
   float *y_tm = nullptr;
-  if (post_on)
+  if (tm_out)
     y_tm = c->yt.as<float>() + (size_t) g0 * c->yt_rows * kSeriesPerRow;
   if (c->sched.generated > 0) {
     ResampleParams p{};
@@ -574,20 +624,45 @@ int run_series_range(EspbResampleBatch *c, int series_first, int n_series, const
         CU_TRY(cudaEventRecord(ev_after, stream), "cudaEventRecord");
     }
   }
-  if (post_on) {  // resampler.cpp:142-149, then back to the caller's layout
+  if (tm_out) {
     const int gen = (int) c->sched.generated;
     float *y_f = y_tm;
-    int blocks = 0;
-    if (post->block_rows > 0 && gen > post->block_rows && c->yt2_rows >= c->yt_rows) {
-      y_f = c->yt2.as<float>() + (size_t) g0 * c->yt_rows * kSeriesPerRow;
-      blocks = post->block_rows;
+    if (post_on) {  // resampler.cpp:142-149
+      int blocks = 0;
+      if (post->block_rows > 0 && gen > post->block_rows && c->yt2_rows >= c->yt_rows) {
+        y_f = c->yt2.as<float>() + (size_t) g0 * c->yt_rows * kSeriesPerRow;
+        blocks = post->block_rows;
+      }
+      CU_TRY(launch_biquad_tm(y_tm, y_f, c->yt_rows, 0, gen, n_series, post->sections, *post->params, post->state,
+                              blocks, post->warm_rows, stream),
+             "biquad kernel");
     }
-    CU_TRY(launch_biquad_tm(y_tm, y_f, c->yt_rows, 0, gen, n_series, post->sections, *post->params, post->state,
-                            blocks, post->warm_rows, stream),
-           "biquad kernel");
-    CU_TRY(launch_untranspose(y_f, c->yt_rows, 0, gen, out, ol.stream_stride, ol.channel_stride, ol.frame_stride,
-                              c->channels, n_series, stream),
-           "untranspose kernel");
+    if (pcm_out) {  // resampler.cpp:152-153: float_to_quantized, fused with the way back to the caller's layout
+      cudaError_t e = cudaSuccess;
+      const int n_streams = n_series / c->channels;
+      const int fast = launch_tm_to_pcm(y_f, c->yt_rows, 0, gen, pcm_out->data, pcm_out->row_bytes, pcm_out->bits,
+                                        c->channels, n_series, pcm_out->clipped, stream, &e);
+      CU_TRY(e, "tm_to_pcm kernel");
+      if (fast < gen) {
+        const int nbytes = (pcm_out->bits + 7) / 8;
+        if (fast > 0)
+          CU_TRY(launch_untranspose_from(y_f, c->yt_rows, 0, fast, gen, pcm_out->scratch, pcm_out->scratch_row, 1,
+                                         c->channels, c->channels, n_series, stream),
+                 "untranspose kernel");
+        else
+          CU_TRY(launch_untranspose(y_f, c->yt_rows, 0, gen, pcm_out->scratch, pcm_out->scratch_row, 1, c->channels,
+                                    c->channels, n_series, stream),
+                 "untranspose kernel");
+        CU_TRY(launch_f2q(pcm_out->scratch + (size_t) fast * c->channels, pcm_out->scratch_row,
+                          pcm_out->data + (size_t) fast * c->channels * nbytes, pcm_out->row_bytes, n_streams,
+                          (uint32_t) ((gen - fast) * c->channels), pcm_out->bits, pcm_out->clipped, true, stream),
+               "f2q kernel");
+      }
+    } else {
+      CU_TRY(launch_untranspose(y_f, c->yt_rows, 0, gen, out, ol.stream_stride, ol.channel_stride, ol.frame_stride,
+                                c->channels, n_series, stream),
+             "untranspose kernel");
+    }
   }
   return ESPB_OK;
 }
@@ -1235,34 +1310,44 @@ int wrapper_run_range(EspbResampler *r, int s0, int ns, const uint8_t *d_in, int
   uint8_t *out = d_out + (size_t) s0 * out_stride_bytes;
   CU_TRY(cudaMemsetAsync(clip, 0, ns * sizeof(uint32_t), stream), "clip counters");
   const bool rs = r->policy.resampling;
-  // :112-119 quantized_to_float into the float input (or, without resampling, output) buffer
-  CU_TRY(launch_q2f(in, in_stride_bytes, rs ? fin : fout, (int64_t) (rs ? r->in_samples : r->out_samples), ns,
-                    (uint32_t) (wc.todo * ch), r->cfg.source_bits_per_sample,
-                    q2f_gain_factor(r->cfg.source_bits_per_sample, gain_db), stream),
-         "q2f kernel");
-  if (rs) {
-    EspbLayout il = {(int64_t) r->in_samples, 1, ch}, ol = {(int64_t) r->out_samples, 1, ch};
-    EspbBiquadBatch *lp = r->lowpass;
-    StageFilter flt;
-    if (lp) {
-      flt.params = &lp->params;
-      flt.state = lp->state.as<float>() + (size_t) s0 * ch * lp->num_sections * 4;
-      flt.sections = lp->num_sections;
-      flt.block_rows = lp->block_rows;
-      flt.warm_rows = lp->warm_rows;
-    }
-    // :126-149 — pre-filter, resampleProcessInterleaved, post-filter
-    int rc = run_series_range(r->art, s0 * ch, ns * ch, fin, il, fout, ol, (int) wc.todo, stream, g_preexpanded,
-                              r->policy.pre ? &flt : nullptr, r->policy.post ? &flt : nullptr);
-    if (rc != ESPB_OK)
-      return rc;
+  if (!rs) {  // :116-119 + :152-153 — bit-depth conversion only
+    CU_TRY(launch_q2f(in, in_stride_bytes, fout, (int64_t) r->out_samples, ns, (uint32_t) (wc.todo * ch),
+                      r->cfg.source_bits_per_sample, q2f_gain_factor(r->cfg.source_bits_per_sample, gain_db), stream),
+           "q2f kernel");
+    CU_TRY(launch_f2q(fout, (int64_t) r->out_samples, out, out_stride_bytes, ns, (uint32_t) (wc.generated * ch),
+                      r->cfg.target_bits_per_sample, clip, true, stream),
+           "f2q kernel");
+    return ESPB_OK;
+  }
+  // :112-153 — quantized_to_float, pre-filter, resampleProcessInterleaved, post-filter, float_to_quantized:
+  // the conversions ride on the layout stages of the resampler, fin/fout only hold the tails
+  EspbLayout il = {(int64_t) r->in_samples, 1, ch}, ol = {(int64_t) r->out_samples, 1, ch};
+  PcmIn pin;
+  pin.data = in;
+  pin.row_bytes = in_stride_bytes;
+  pin.bits = r->cfg.source_bits_per_sample;
+  pin.gain_factor = q2f_gain_factor(r->cfg.source_bits_per_sample, gain_db);
+  pin.scratch = fin;
+  pin.scratch_row = (int64_t) r->in_samples;
+  PcmOut pout;
+  pout.data = out;
+  pout.row_bytes = out_stride_bytes;
+  pout.bits = r->cfg.target_bits_per_sample;
+  pout.clipped = clip;
+  pout.scratch = fout;
+  pout.scratch_row = (int64_t) r->out_samples;
+  EspbBiquadBatch *lp = r->lowpass;
+  StageFilter flt;
+  if (lp) {
+    flt.params = &lp->params;
+    flt.state = lp->state.as<float>() + (size_t) s0 * ch * lp->num_sections * 4;
+    flt.sections = lp->num_sections;
+    flt.block_rows = lp->block_rows;
+    flt.warm_rows = lp->warm_rows;
   }
   (void) out_free;
-  // :152-153 float_to_quantized + clip count
-  CU_TRY(launch_f2q(fout, (int64_t) r->out_samples, out, out_stride_bytes, ns, (uint32_t) (wc.generated * ch),
-                    r->cfg.target_bits_per_sample, clip, true, stream),
-         "f2q kernel");
-  return ESPB_OK;
+  return run_series_range(r->art, s0 * ch, ns * ch, fin, il, fout, ol, (int) wc.todo, stream, g_preexpanded,
+                          r->policy.pre ? &flt : nullptr, r->policy.post ? &flt : nullptr, &pin, &pout);
 }
 
 // The host-known part of the call: frames_to_process and the schedule.
@@ -1289,11 +1374,10 @@ int wrapper_plan(EspbResampler *r, size_t avail, size_t out_free, cudaStream_t s
     return fail(ESPB_ERR_ARG, "resample: frames exceed the float buffer size given at construction");
   if (wc->generated * ch > r->out_samples)
     return fail(ESPB_ERR_ARG, "resample: output exceeds the float buffer size given at construction");
-  if (r->policy.post) {
-    rc = ensure_yt(r->art, (int64_t) wc->generated, r->lowpass && r->lowpass->block_rows > 0);
-    if (rc != ESPB_OK)
-      return rc;
-  }
+  // the resampler writes time-major scratch; the post-filter and the PCM packing read it
+  rc = ensure_yt(r->art, (int64_t) wc->generated, r->policy.post && r->lowpass && r->lowpass->block_rows > 0);
+  if (rc != ESPB_OK)
+    return rc;
   return ESPB_OK;
 }
 

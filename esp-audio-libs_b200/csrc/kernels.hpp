@@ -41,6 +41,21 @@ cudaError_t launch_q2f(const uint8_t *in, int64_t in_row_bytes, float *out, int6
 cudaError_t launch_f2q(const float *in, int64_t in_row_floats, uint8_t *out, int64_t out_row_bytes, int rows,
                        uint32_t row_samples, int bits, uint32_t *clipped, bool clipped_per_row, cudaStream_t stream);
 
+// PCM <-> time-major float, fused conversion + layout change (full 64-frame tiles, channels in {1,2,4,8},
+// 4-byte aligned PCM rows).  Return the number of frames handled (0: not applicable, use the separate stages).
+int launch_pcm_to_tm(const uint8_t *in, int64_t in_row_bytes, int bits, float gain_factor, int channels, int n_series,
+                     int n_frames, float *tm, int64_t rows_cap, int row_first, cudaStream_t stream, cudaError_t *err);
+int launch_tm_to_pcm(const float *tm, int64_t rows_cap, int row_first, int n_frames, uint8_t *out,
+                     int64_t out_row_bytes, int bits, int channels, int n_series, uint32_t *clipped_per_stream,
+                     cudaStream_t stream, cudaError_t *err);
+// the stage-by-stage twins with a starting frame (tails after the fused tiles, other layouts)
+cudaError_t launch_transpose_from(const float *in, int64_t in_ss, int64_t in_cs, int64_t in_fs, int channels,
+                                  int n_series, int n_in, float *xt, int64_t rows_cap, int row_first, int j_begin,
+                                  int pad_rows, cudaStream_t stream);
+cudaError_t launch_untranspose_from(const float *tm, int64_t rows_cap, int row_first, int j_begin, int n_rows,
+                                    float *out, int64_t out_ss, int64_t out_cs, int64_t out_fs, int channels,
+                                    int n_series, cudaStream_t stream);
+
 // art_biquad
 struct BiquadParams {
   float a0, a1, a2, b1, b2;

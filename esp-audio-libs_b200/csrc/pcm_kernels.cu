@@ -9,6 +9,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "common.hpp"
 #include "kernels.hpp"
 
 namespace espb {
@@ -175,6 +176,150 @@ __global__ void __launch_bounds__(256)
     atomicAdd(clipped_out + (clipped_per_row ? blockIdx.y : 0), clipped);
 }
 
+// ---- fused with the layout stages of the resampler ------------------------------------
+// PCM rows (stream-major, channels interleaved) <-> time-major float tm[group][row][128 series]: the
+// conversion rides on the transposing pass, so the wrapper path never materialises a stream-major float
+// copy.  Tiles of 128 series x 64 frames through shared memory; 32-bit word accesses on the PCM side
+// (4 samples = NBYTES words), 128-bit on the float side.  CH in {1,2,4,8}; full tiles only.
+constexpr int SGN = kSeriesPerRow;  // 128
+constexpr int PT_ROWS = 64;
+constexpr int PT_THREADS = 256;
+
+template <int NBYTES, int CH>
+__global__ void __launch_bounds__(PT_THREADS)
+    espb_pcm_to_tm_kernel(const uint8_t *__restrict__ in, int64_t in_row_bytes, float *__restrict__ tm,
+                          int64_t rows_cap, int row_first, int n_series, float k) {
+  __shared__ float tile[PT_ROWS][SGN + 1];
+  const int g = blockIdx.x, j0 = blockIdx.y * PT_ROWS, tid = threadIdx.x;
+  constexpr int UNITS = SGN / CH;            // streams per group
+  constexpr int GROUPS = PT_ROWS * CH / 4;   // 4-sample groups per stream per tile
+#pragma unroll 2
+  for (int v = tid; v < UNITS * GROUPS; v += PT_THREADS) {
+    const int unit = v / GROUPS, grp = v % GROUPS;
+    const int q0 = g * SGN + unit * CH;
+    int32_t s[4] = {0, 0, 0, 0};
+    if (q0 < n_series) {
+      const uint32_t *wp = reinterpret_cast<const uint32_t *>(in + (int64_t) (q0 / CH) * in_row_bytes +
+                                                              ((int64_t) j0 * CH + grp * 4) * NBYTES);
+      uint32_t w[NBYTES];
+#pragma unroll
+      for (int i = 0; i < NBYTES; ++i)
+        w[i] = __ldg(wp + i);
+      decode_words<NBYTES>(w, s);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int e = grp * 4 + i;
+      tile[e / CH][unit * CH + (e % CH)] = (q0 < n_series) ? __fmul_rn(__int2float_rn(s[i]), k) : 0.0f;
+    }
+  }
+  __syncthreads();
+  float4 *dst = reinterpret_cast<float4 *>(tm + ((int64_t) g * rows_cap + row_first + j0) * SGN);
+#pragma unroll 4
+  for (int i = tid; i < PT_ROWS * (SGN / 4); i += PT_THREADS) {
+    const int t = i / (SGN / 4), c4 = i % (SGN / 4);
+    dst[i] = make_float4(tile[t][c4 * 4], tile[t][c4 * 4 + 1], tile[t][c4 * 4 + 2], tile[t][c4 * 4 + 3]);
+  }
+}
+
+template <int NBYTES, int CH>
+__global__ void __launch_bounds__(PT_THREADS)
+    espb_tm_to_pcm_kernel(const float *__restrict__ tm, int64_t rows_cap, int row_first, uint8_t *__restrict__ out,
+                          int64_t out_row_bytes, int n_series, F2QConst c, uint32_t *__restrict__ clipped_per_stream) {
+  __shared__ float tile[PT_ROWS][SGN + 1];
+  const int g = blockIdx.x, j0 = blockIdx.y * PT_ROWS, tid = threadIdx.x;
+  const float4 *src = reinterpret_cast<const float4 *>(tm + ((int64_t) g * rows_cap + row_first + j0) * SGN);
+#pragma unroll 4
+  for (int i = tid; i < PT_ROWS * (SGN / 4); i += PT_THREADS) {
+    const int t = i / (SGN / 4), c4 = i % (SGN / 4);
+    const float4 v = __ldg(src + i);
+    tile[t][c4 * 4] = v.x;
+    tile[t][c4 * 4 + 1] = v.y;
+    tile[t][c4 * 4 + 2] = v.z;
+    tile[t][c4 * 4 + 3] = v.w;
+  }
+  __syncthreads();
+  constexpr int UNITS = SGN / CH;
+  constexpr int GROUPS = PT_ROWS * CH / 4;
+#pragma unroll 2
+  for (int v = tid; v < UNITS * GROUPS; v += PT_THREADS) {
+    const int unit = v / GROUPS, grp = v % GROUPS;
+    const int q0 = g * SGN + unit * CH;
+    if (q0 >= n_series)
+      continue;
+    const int stream = q0 / CH;
+    uint32_t clipped = 0;
+    int32_t s[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int e = grp * 4 + i;
+      s[i] = quantise_one(tile[e / CH][unit * CH + (e % CH)], c, clipped);
+    }
+    uint32_t w[NBYTES];
+    encode_words<NBYTES>(s, w);
+    uint32_t *wp = reinterpret_cast<uint32_t *>(out + (int64_t) stream * out_row_bytes +
+                                                ((int64_t) j0 * CH + grp * 4) * NBYTES);
+#pragma unroll
+    for (int i = 0; i < NBYTES; ++i)
+      wp[i] = w[i];
+    if (clipped && clipped_per_stream)
+      atomicAdd(clipped_per_stream + stream, clipped);  // clipping is rare: no reduction needed
+  }
+}
+
+template <int NBYTES>
+bool launch_pcm_to_tm_ch(int ch, dim3 grid, cudaStream_t s, const uint8_t *in, int64_t in_row_bytes, float *tm,
+                         int64_t rows_cap, int row_first, int n_series, float k) {
+  switch (ch) {
+    case 1:
+      espb_pcm_to_tm_kernel<NBYTES, 1><<<grid, PT_THREADS, 0, s>>>(in, in_row_bytes, tm, rows_cap, row_first, n_series, k);
+      return true;
+    case 2:
+      espb_pcm_to_tm_kernel<NBYTES, 2><<<grid, PT_THREADS, 0, s>>>(in, in_row_bytes, tm, rows_cap, row_first, n_series, k);
+      return true;
+    case 4:
+      espb_pcm_to_tm_kernel<NBYTES, 4><<<grid, PT_THREADS, 0, s>>>(in, in_row_bytes, tm, rows_cap, row_first, n_series, k);
+      return true;
+    case 8:
+      espb_pcm_to_tm_kernel<NBYTES, 8><<<grid, PT_THREADS, 0, s>>>(in, in_row_bytes, tm, rows_cap, row_first, n_series, k);
+      return true;
+    default:
+      return false;
+  }
+}
+
+template <int NBYTES>
+bool launch_tm_to_pcm_ch(int ch, dim3 grid, cudaStream_t s, const float *tm, int64_t rows_cap, int row_first,
+                         uint8_t *out, int64_t out_row_bytes, int n_series, const F2QConst &c, uint32_t *clipped) {
+  switch (ch) {
+    case 1:
+      espb_tm_to_pcm_kernel<NBYTES, 1><<<grid, PT_THREADS, 0, s>>>(tm, rows_cap, row_first, out, out_row_bytes, n_series, c, clipped);
+      return true;
+    case 2:
+      espb_tm_to_pcm_kernel<NBYTES, 2><<<grid, PT_THREADS, 0, s>>>(tm, rows_cap, row_first, out, out_row_bytes, n_series, c, clipped);
+      return true;
+    case 4:
+      espb_tm_to_pcm_kernel<NBYTES, 4><<<grid, PT_THREADS, 0, s>>>(tm, rows_cap, row_first, out, out_row_bytes, n_series, c, clipped);
+      return true;
+    case 8:
+      espb_tm_to_pcm_kernel<NBYTES, 8><<<grid, PT_THREADS, 0, s>>>(tm, rows_cap, row_first, out, out_row_bytes, n_series, c, clipped);
+      return true;
+    default:
+      return false;
+  }
+}
+
+F2QConst make_f2q_const(int bits) {
+  F2QConst c;
+  c.bits = bits;
+  c.scalar = (float) ((uint64_t) 1 << bits) / 2.0f;  // :52
+  c.offset = (bits <= 8) ? 128 : 0;                   // :53
+  c.hi = (int32_t) ((1u << (bits - 1)) - 1u);         // :54
+  c.lo = ~c.hi;                                       // :55
+  c.shift = (32 - bits) % 8;                          // :56
+  return c;
+}
+
 inline unsigned grid_x_for(uint32_t n, int rows) {
   // enough CTAs to cover the row once at 4 samples/thread, capped so rows*grid stays sane
   uint64_t want = ((uint64_t) n / 4 + 255) / 256;
@@ -225,13 +370,7 @@ cudaError_t launch_f2q(const float *in, int64_t in_row_floats, uint8_t *out, int
   if (rows <= 0 || row_samples == 0)
     return cudaSuccess;
   const int nbytes = (bits + 7) / 8;
-  F2QConst c;
-  c.bits = bits;
-  c.scalar = (float) ((uint64_t) 1 << bits) / 2.0f;  // :52
-  c.offset = (bits <= 8) ? 128 : 0;                   // :53
-  c.hi = (int32_t) ((1u << (bits - 1)) - 1u);         // :54
-  c.lo = ~c.hi;                                       // :55
-  c.shift = (32 - bits) % 8;                          // :56
+  const F2QConst c = make_f2q_const(bits);
   const int vec_ok = ((uintptr_t) out % 4 == 0) && (out_row_bytes % 4 == 0 || rows == 1) &&
                      ((uintptr_t) in % 16 == 0) && (in_row_floats % 4 == 0 || rows == 1);
   dim3 grid(grid_x_for(row_samples, rows), rows);
@@ -257,6 +396,71 @@ cudaError_t launch_f2q(const float *in, int64_t in_row_floats, uint8_t *out, int
   }
   count_launch();
   return cudaGetLastError();
+}
+
+// Frames [0, n_frames) (n_frames a multiple of 64) of every stream -> rows row_first.. of tm.  Returns the
+// number of frames handled: 0 when the layout does not qualify (caller falls back to q2f + transpose).
+int launch_pcm_to_tm(const uint8_t *in, int64_t in_row_bytes, int bits, float gain_factor, int channels, int n_series,
+                     int n_frames, float *tm, int64_t rows_cap, int row_first, cudaStream_t stream, cudaError_t *err) {
+  *err = cudaSuccess;
+  const int fast = (n_frames / PT_ROWS) * PT_ROWS;
+  if (fast <= 0 || ((uintptr_t) in % 4) || (in_row_bytes % 4) || n_series <= 0)
+    return 0;
+  const int nbytes = (bits + 7) / 8;
+  dim3 grid((n_series + SGN - 1) / SGN, fast / PT_ROWS);
+  bool ok = false;
+  switch (nbytes) {
+    case 1:
+      ok = launch_pcm_to_tm_ch<1>(channels, grid, stream, in, in_row_bytes, tm, rows_cap, row_first, n_series, gain_factor);
+      break;
+    case 2:
+      ok = launch_pcm_to_tm_ch<2>(channels, grid, stream, in, in_row_bytes, tm, rows_cap, row_first, n_series, gain_factor);
+      break;
+    case 3:
+      ok = launch_pcm_to_tm_ch<3>(channels, grid, stream, in, in_row_bytes, tm, rows_cap, row_first, n_series, gain_factor);
+      break;
+    case 4:
+      ok = launch_pcm_to_tm_ch<4>(channels, grid, stream, in, in_row_bytes, tm, rows_cap, row_first, n_series, gain_factor);
+      break;
+  }
+  if (!ok)
+    return 0;
+  count_launch();
+  *err = cudaGetLastError();
+  return fast;
+}
+
+// Rows [row_first, row_first + n_frames) of tm -> frames [0, n_frames) of every stream's PCM row.
+int launch_tm_to_pcm(const float *tm, int64_t rows_cap, int row_first, int n_frames, uint8_t *out,
+                     int64_t out_row_bytes, int bits, int channels, int n_series, uint32_t *clipped_per_stream,
+                     cudaStream_t stream, cudaError_t *err) {
+  *err = cudaSuccess;
+  const int fast = (n_frames / PT_ROWS) * PT_ROWS;
+  if (fast <= 0 || ((uintptr_t) out % 4) || (out_row_bytes % 4) || n_series <= 0)
+    return 0;
+  const int nbytes = (bits + 7) / 8;
+  const F2QConst c = make_f2q_const(bits);
+  dim3 grid((n_series + SGN - 1) / SGN, fast / PT_ROWS);
+  bool ok = false;
+  switch (nbytes) {
+    case 1:
+      ok = launch_tm_to_pcm_ch<1>(channels, grid, stream, tm, rows_cap, row_first, out, out_row_bytes, n_series, c, clipped_per_stream);
+      break;
+    case 2:
+      ok = launch_tm_to_pcm_ch<2>(channels, grid, stream, tm, rows_cap, row_first, out, out_row_bytes, n_series, c, clipped_per_stream);
+      break;
+    case 3:
+      ok = launch_tm_to_pcm_ch<3>(channels, grid, stream, tm, rows_cap, row_first, out, out_row_bytes, n_series, c, clipped_per_stream);
+      break;
+    case 4:
+      ok = launch_tm_to_pcm_ch<4>(channels, grid, stream, tm, rows_cap, row_first, out, out_row_bytes, n_series, c, clipped_per_stream);
+      break;
+  }
+  if (!ok)
+    return 0;
+  count_launch();
+  *err = cudaGetLastError();
+  return fast;
 }
 
 }  // namespace espb

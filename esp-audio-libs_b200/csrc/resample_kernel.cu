@@ -651,6 +651,35 @@ cudaError_t launch_transpose(const float *in, int64_t in_ss, int64_t in_cs, int6
   return cudaGetLastError();
 }
 
+// generic kernels only, starting at frame j_begin (used for the tails after the fused PCM tiles)
+cudaError_t launch_transpose_from(const float *in, int64_t in_ss, int64_t in_cs, int64_t in_fs, int channels,
+                                  int n_series, int n_in, float *xt, int64_t rows_cap, int row_first, int j_begin,
+                                  int pad_rows, cudaStream_t stream) {
+  const int n_groups = (n_series + SGN - 1) / SGN;
+  const int rest = n_in + pad_rows - j_begin;
+  if (n_groups <= 0 || rest <= 0)
+    return cudaSuccess;
+  dim3 grid(n_groups, (rest + TR_ROWS - 1) / TR_ROWS);
+  espb_transpose_kernel<<<grid, 256, 0, stream>>>(in, in_ss, in_cs, in_fs, channels, n_series, n_in, xt, rows_cap,
+                                                  row_first, j_begin, pad_rows);
+  count_launch();
+  return cudaGetLastError();
+}
+
+cudaError_t launch_untranspose_from(const float *tm, int64_t rows_cap, int row_first, int j_begin, int n_rows,
+                                    float *out, int64_t out_ss, int64_t out_cs, int64_t out_fs, int channels,
+                                    int n_series, cudaStream_t stream) {
+  const int n_groups = (n_series + SGN - 1) / SGN;
+  const int rest = n_rows - j_begin;
+  if (n_groups <= 0 || rest <= 0)
+    return cudaSuccess;
+  dim3 grid(n_groups, (rest + TR_ROWS - 1) / TR_ROWS);
+  espb_untranspose_kernel<<<grid, 256, 0, stream>>>(tm, rows_cap, row_first, j_begin, n_rows, out, out_ss, out_cs,
+                                                    out_fs, channels, n_series);
+  count_launch();
+  return cudaGetLastError();
+}
+
 cudaError_t launch_untranspose(const float *tm, int64_t rows_cap, int row_first, int n_rows, float *out,
                                int64_t out_ss, int64_t out_cs, int64_t out_fs, int channels, int n_series,
                                cudaStream_t stream) {
