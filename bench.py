@@ -333,7 +333,7 @@ def main():
     except Exception:
         pass
     roofline = {
-        "kernel": "espb_resample_kernel<8,false,false>", "bound": "fp32_fma", "achieved": achieved_tf,
+        "kernel": "espb_resample_kernel<4,2,false,false>", "bound": "fp32_fma", "achieved": achieved_tf,
         "peak": fma_tflops, "unit": "TFLOP/s", "frac": achieved_tf / fma_tflops if fma_tflops else None,
         "peak_source": "FMA-only probes (espb_measure_fp32_fma_peak: best of scalar FFMA and packed FFMA2) on this "
                        "GPU in this run; nominal 148 SM x 128 lanes x 2 x 1.965 GHz = 74.4",

@@ -9,7 +9,13 @@ constexpr int kOutputsPerBlock = 8;   // NB: outputs accumulated per thread
 constexpr int kChunkRows = 32;        // CJ: input frames staged per pipeline stage
 constexpr int kSeriesPerRow = 128;    // series (stream x channel) per warp row: 32 lanes x 4
 constexpr int kGRowFloats = 2 * kOutputsPerBlock;  // 16 coefficients per (row, output block)
-constexpr int kMaxChunksPerCta = 768;  // chunk-table entries a CTA caches in shared memory
+// chunk-table entries a CTA caches in shared memory (fewer for the 4-warp variant: four CTAs share an SM)
+#ifdef __CUDACC__
+#define ESPB_HD __host__ __device__
+#else
+#define ESPB_HD
+#endif
+ESPB_HD constexpr int max_chunks_per_cta(int bpp) { return bpp == 8 ? 768 : 320; }
 constexpr int kMaxPassesPerCta = 64;
 
 // What the reference does for one output sample (art_resampler.cpp:421-451).

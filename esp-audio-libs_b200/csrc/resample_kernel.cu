@@ -46,9 +46,6 @@ namespace {
 constexpr int NB = kOutputsPerBlock;  // 8
 constexpr int CJ = kChunkRows;        // 32
 constexpr int SGN = kSeriesPerRow;    // 128
-constexpr int STAGES = 3;
-constexpr int MAXC = kMaxChunksPerCta;  // chunk entries cached in shared memory per CTA
-constexpr int MAXP = kMaxPassesPerCta;  // passes per CTA
 constexpr int kLastChunkOfPass = 1 << 30;
 constexpr int RG = 4;  // rows per skip group / inner unroll
 
@@ -369,9 +366,13 @@ __global__ void __launch_bounds__(256)
 // Resampler
 // ---------------------------------------------------------------------------------
 // TM: write the output time-major (scratch for a following library stage) instead of the caller's layout.
-template <int BPP, bool EXACT, bool TM>
-__global__ void __launch_bounds__(BPP * 32, 2) espb_resample_kernel(const ResampleParams p) {
+// BPP: output blocks (= warps) per pass; NST: ring stages.  <8,3>: two 8-warp CTAs per SM; <4,2>: four 4-warp
+// CTAs per SM (shorter passes: less idle time at the pass edges, twice the x traffic from L2).
+template <int BPP, int NST, bool EXACT, bool TM>
+__global__ void __launch_bounds__(BPP * 32, 16 / BPP) espb_resample_kernel(const ResampleParams p) {
   constexpr int NTHREADS = BPP * 32;
+  constexpr int STAGES = NST;
+  constexpr int MAXC = max_chunks_per_cta(BPP), MAXP = kMaxPassesPerCta;
   constexpr int XS_STAGE = CJ * SGN;                // floats
   constexpr int GS_STAGE = CJ * BPP * kGRowFloats;  // floats
   constexpr uint32_t X_BYTES = XS_STAGE * sizeof(float), G_BYTES = GS_STAGE * sizeof(float);
@@ -578,9 +579,13 @@ __global__ void __launch_bounds__(BPP * 32, 2) espb_resample_kernel(const Resamp
 // ---------------------------------------------------------------------------------
 // launchers
 // ---------------------------------------------------------------------------------
+int resample_stages(int bpp) { return bpp == 8 ? 3 : 2; }
+
 size_t resample_smem_bytes(int bpp) {
-  return (size_t) STAGES * (CJ * bpp * kGRowFloats + CJ * SGN) * sizeof(float) + STAGES * sizeof(uint64_t) +
-         2 * STAGES * sizeof(int) + MAXC * sizeof(ChunkEntry) + (size_t) MAXP * bpp * sizeof(int2);
+  const int stages = resample_stages(bpp);
+  return (size_t) stages * (CJ * bpp * kGRowFloats + CJ * SGN) * sizeof(float) + stages * sizeof(uint64_t) +
+         2 * stages * sizeof(int) + max_chunks_per_cta(bpp) * sizeof(ChunkEntry) +
+         (size_t) kMaxPassesPerCta * bpp * sizeof(int2);
 }
 
 size_t g_chunk_floats(int bpp) { return (size_t) CJ * bpp * kGRowFloats; }
@@ -728,32 +733,32 @@ cudaError_t launch_untranspose(const float *tm, int64_t rows_cap, int row_first,
   return cudaGetLastError();
 }
 
-template <int BPP, bool EXACT, bool TM>
+template <int BPP, int NST, bool EXACT, bool TM>
 static cudaError_t launch_resample_t(const ResampleParams &p, int n_groups, int n_ctas_y, cudaStream_t stream) {
   const size_t smem = resample_smem_bytes(BPP);
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(espb_resample_kernel<BPP, EXACT, TM>,
+    cudaError_t e = cudaFuncSetAttribute(espb_resample_kernel<BPP, NST, EXACT, TM>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
     if (e != cudaSuccess)
       return e;
     // two CTAs per SM need the full 228 KB carve-out (the default heuristic sizes it for one)
-    e = cudaFuncSetAttribute(espb_resample_kernel<BPP, EXACT, TM>, cudaFuncAttributePreferredSharedMemoryCarveout,
+    e = cudaFuncSetAttribute(espb_resample_kernel<BPP, NST, EXACT, TM>, cudaFuncAttributePreferredSharedMemoryCarveout,
                              (int) cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess)
       return e;
     configured = true;
     if (getenv("ESPB_DEBUG")) {
       int nb = 0;
-      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, espb_resample_kernel<BPP, EXACT, TM>, BPP * 32, smem);
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, espb_resample_kernel<BPP, NST, EXACT, TM>, BPP * 32, smem);
       cudaFuncAttributes fa;
-      cudaFuncGetAttributes(&fa, espb_resample_kernel<BPP, EXACT, TM>);
-      fprintf(stderr, "[espb] resample<%d,%d,%d>: smem %zu B, %d regs, occupancy %d CTA/SM\n", BPP, (int) EXACT,
-              (int) TM, smem, fa.numRegs, nb);
+      cudaFuncGetAttributes(&fa, espb_resample_kernel<BPP, NST, EXACT, TM>);
+      fprintf(stderr, "[espb] resample<%d,%d,%d,%d>: smem %zu B, %d regs, occupancy %d CTA/SM\n", BPP, NST,
+              (int) EXACT, (int) TM, smem, fa.numRegs, nb);
     }
   }
   dim3 grid(n_groups, n_ctas_y);
-  espb_resample_kernel<BPP, EXACT, TM><<<grid, BPP * 32, smem, stream>>>(p);
+  espb_resample_kernel<BPP, NST, EXACT, TM><<<grid, BPP * 32, smem, stream>>>(p);
   count_launch();
   return cudaGetLastError();
 }
@@ -765,13 +770,17 @@ cudaError_t launch_resample(const ResampleParams &p, int bpp, bool exact, cudaSt
     return cudaSuccess;
   const int n_ctas_y = (n_passes + p.passes_per_cta - 1) / p.passes_per_cta;
   const bool tm = p.out_tm != nullptr;
-  if (bpp != 8)
-    return cudaErrorInvalidValue;
-  if (exact)
-    return tm ? launch_resample_t<8, true, true>(p, n_groups, n_ctas_y, stream)
-              : launch_resample_t<8, true, false>(p, n_groups, n_ctas_y, stream);
-  return tm ? launch_resample_t<8, false, true>(p, n_groups, n_ctas_y, stream)
-            : launch_resample_t<8, false, false>(p, n_groups, n_ctas_y, stream);
+#define ESPB_LAUNCH(BPP_, NST_)                                                                        \
+  (exact ? (tm ? launch_resample_t<BPP_, NST_, true, true>(p, n_groups, n_ctas_y, stream)              \
+               : launch_resample_t<BPP_, NST_, true, false>(p, n_groups, n_ctas_y, stream))            \
+         : (tm ? launch_resample_t<BPP_, NST_, false, true>(p, n_groups, n_ctas_y, stream)             \
+               : launch_resample_t<BPP_, NST_, false, false>(p, n_groups, n_ctas_y, stream)))
+  if (bpp == 8)
+    return ESPB_LAUNCH(8, 3);
+  if (bpp == 4)
+    return ESPB_LAUNCH(4, 2);
+#undef ESPB_LAUNCH
+  return cudaErrorInvalidValue;
 }
 
 }  // namespace espb
