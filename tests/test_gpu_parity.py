@@ -390,6 +390,53 @@ def test_wrapper_vs_oracle_fast_mode_within_one_lsb(oracle, cfg):
         r.free()
 
 
+@pytest.mark.parametrize("cfg", [
+    # src_rate, dst_rate, src_bits, dst_bits, channels, streams, frames: channel counts / frame counts that take the
+    # generic layout kernels, the < 64-frame tails and unaligned PCM rows (odd bytes per row)
+    (44100, 48000, 24, 16, 3, 45, 1001),
+    (48000, 32000, 16, 24, 6, 22, 777),
+    (22050, 44100, 8, 32, 5, 27, 63),
+    (32000, 48000, 16, 16, 2, 3, 130),
+])
+def test_wrapper_odd_shapes_vs_composed_oracle(oracle, cfg):
+    """The oracle wrapper is limited to 2 channels (include/resampler.h:64), so the reference pipeline is composed
+    from the oracle's stages with the policy the library reports."""
+    sr, dr, sb, db, ch, ns, frames = cfg
+    nb, ob = (sb + 7) // 8, (db + 7) // 8
+    rng = np.random.default_rng(frames)
+    raw = rng.integers(0, 256, size=(ns, frames * ch * nb), dtype=np.uint8)
+    cap = int(frames * dr / sr) + 40
+    r = espb.Resampler(ns, frames * ch, cap * ch, sr, dr, sb, db, ch, True, True, 64, 64, mode=espb.MODE_EXACT)
+    pol = r.policy()
+    outs = []
+    for it in range(2):  # two calls: state carries through every stage
+        out, res = r.resample(raw, frames, cap, -2.5)
+        outs.append((out, res))
+    states = {}
+    for s in range(0, ns, 4):
+        o = oracle.resampler(ch, 64, 64, float(pol["art_lowpass"]), pol["art_flags"])
+        o.advance(32.0)
+        bq = [[oracle.biquad(pol["coeffs"], 1.0) for _ in range(2)] for _ in range(ch)]
+        for it in range(2):
+            xf = oracle.quantized_to_float(raw[s], frames * ch, sb, -2.5)
+            if pol["filter"] == "pre":
+                for c in range(ch):
+                    for k in range(2):
+                        bq[c][k].apply_buffer(xf[c:], ch, n=frames)
+            yf, used, gen = o.process_interleaved(xf, cap, pol["sample_ratio"])
+            yf = np.ascontiguousarray(yf)
+            if pol["filter"] == "post":
+                for c in range(ch):
+                    for k in range(2):
+                        bq[c][k].apply_buffer(yf[c:], ch, n=gen)
+            q, clipped = oracle.float_to_quantized(yf, db)
+            out, res = outs[it]
+            assert (res["frames_used"], res["frames_generated"]) == (used, gen)
+            assert bits_equal(out[s], q), (cfg, s, it)
+            assert int(res["clipped_per_stream"][s]) == clipped
+    r.free()
+
+
 def _le_to_int(bytes_, nb):
     b = bytes_.reshape(-1, nb).astype(np.int64)
     v = np.zeros(b.shape[0], np.int64)
