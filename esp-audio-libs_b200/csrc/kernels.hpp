@@ -23,7 +23,9 @@ struct ResampleParams {
   const OutEntry *outs;
   int n_series, channels, n_out, taps;
   int pass_first, pass_end, passes_per_cta, g_chunk_base;
+  int out_vec;  // OutVec: set by launch_resample from the output layout
 };
+enum OutVec : int { kOutVecNone = 0, kOutVecPlanar = 1, kOutVecStereo = 2, kOutVecFrame4 = 3 };
 
 size_t resample_smem_bytes(int bpp);
 size_t g_chunk_floats(int bpp);

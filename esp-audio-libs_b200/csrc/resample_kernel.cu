@@ -80,6 +80,11 @@ __device__ __forceinline__ void tma_bulk_g2s(void *dst_smem, const void *src, ui
                : "memory");
 }
 
+__device__ __forceinline__ void cp_async_16(void *dst_smem, const void *src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;\n" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
+
 // Counting arrival on a shared-memory word.  Relaxed is enough: every shared-memory load of the stage
 // has already returned its value (the FMAs consumed them) when the warp gets here, so nothing of this
 // warp can still observe the refill; the refill itself is published by the mbarrier arrive (release).
@@ -384,6 +389,8 @@ __global__ void __launch_bounds__(BPP * 32, 16 / BPP) espb_resample_kernel(const
   int *done = reinterpret_cast<int *>(full + STAGES);                     // [2*STAGES] warps done with a stage
   ChunkEntry *ctab = reinterpret_cast<ChunkEntry *>(done + 2 * STAGES);   // [MAXC] this CTA's chunks
   int2 *wtab = reinterpret_cast<int2 *>(ctab + MAXC);  // [MAXP][BPP] window [lo, hi) per (pass, warp)
+  // [BPP][NB] schedule entries of the block each warp is finishing, fetched by cp.async during the pass's last chunk
+  OutEntry *etab = reinterpret_cast<OutEntry *>(wtab + MAXP * BPP);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int group = blockIdx.x;
@@ -424,12 +431,14 @@ __global__ void __launch_bounds__(BPP * 32, 16 / BPP) espb_resample_kernel(const
   }
   __syncthreads();
 
-  const float *xt_group = p.xt + (int64_t) group * p.xt_rows * SGN;
-  const float *g_base = p.G + (size_t) (chunk_first - p.g_chunk_base) * GS_STAGE;
-
   // Fill stage c % STAGES with chunk c: two TMA bulk copies (16 KB of G, 16 KB of x) on one mbarrier.
+  // (Addresses are rebuilt from the parameters here — one lane runs this once per chunk — rather than held in
+  // registers across the FMA loop.)
   auto issue_chunk = [&](int c) {
     const int st = c % STAGES;
+    const float *xt_group = p.xt + (int64_t) blockIdx.x * p.xt_rows * SGN;
+    const float *g_base =
+        p.G + (size_t) (p.pass_chunk_begin[p.pass_first + blockIdx.y * p.passes_per_cta] - p.g_chunk_base) * GS_STAGE;
     mbar_expect_tx(&full[st], X_BYTES + G_BYTES);
     tma_bulk_g2s(gs + st * GS_STAGE, g_base + (size_t) c * GS_STAGE, G_BYTES, &full[st]);
     tma_bulk_g2s(xs + st * XS_STAGE, xt_group + (int64_t) (ctab[c].j_start + T) * SGN, X_BYTES, &full[st]);
@@ -475,6 +484,11 @@ __global__ void __launch_bounds__(BPP * 32, 16 / BPP) espb_resample_kernel(const
     r0 = r0 < 0 ? 0 : (r0 / RG);
     r1 = r1 > CJ ? CJ / RG : ((r1 + RG - 1) / RG);
 
+    if (pass_done && lane < NB) {  // the epilogue's schedule entries: global -> shared, no register held meanwhile
+      int o = (cur_pass * BPP + warp) * NB + lane;
+      o = o < p.n_out ? o : p.n_out - 1;
+      cp_async_16(&etab[warp * NB + lane], &p.outs[o]);
+    }
     mbar_wait(&full[st], (uint32_t) ((c / STAGES) & 1));
     {
       const float *xrow = xs + st * XS_STAGE + lane * 4;
@@ -528,47 +542,87 @@ __global__ void __launch_bounds__(BPP * 32, 16 / BPP) espb_resample_kernel(const
 
     // ---- end of pass: blend, store, clear
     if (pass_done) {
+      cp_async_wait_all();
+      __syncwarp();
       const int o0 = (cur_pass * BPP + warp) * NB;
-      int64_t out_off[4];
-      bool live[4];
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int series = group * SGN + lane * 4 + e;
-        live[e] = series < p.n_series;
-        const int sidx = series / p.channels, ch = series - sidx * p.channels;
-        out_off[e] = (int64_t) sidx * p.out_ss + (int64_t) ch * p.out_cs;
-      }
+      const OutEntry *et = etab + warp * NB;
+      float v[4][NB];
 #pragma unroll
       for (int n = 0; n < NB; ++n) {
-        const int o = o0 + n;
-        if (o < p.n_out) {
-          const OutEntry en = p.outs[o];
-          float vt[4];
+        const OutEntry en = et[n];  // one broadcast LDS.128
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            float v, sum1, sum2;
-            if constexpr (EXACT) {
-              sum1 = acc1[e][n][0];
-              sum2 = acc1[e][n][1];
-            } else {
-              sum1 = acc2[e][n].x;
-              sum2 = acc2[e][n].y;
-            }
-            if (en.kind == kKindBlend) {  // art_resampler.cpp:450, un-fused
-              v = __fadd_rn(__fmul_rn(sum2, en.w), __fmul_rn(sum1, __fsub_rn(1.0f, en.w)));
-            } else if (en.kind == kKindSingle) {
-              v = sum1;
-            } else {  // pass-through: *source (art_resampler.cpp:426,440) = tap numTaps/2-1 of the window
-              v = xt_group[(int64_t) (en.ws + T / 2 - 1 + T) * SGN + lane * 4 + e];
-            }
-            if constexpr (TM)
-              vt[e] = v;
-            else if (live[e])
-              p.out[out_off[e] + (int64_t) o * p.out_fs] = v;
+        for (int e = 0; e < 4; ++e) {
+          float sum1, sum2;
+          if constexpr (EXACT) {
+            sum1 = acc1[e][n][0];
+            sum2 = acc1[e][n][1];
+          } else {
+            sum1 = acc2[e][n].x;
+            sum2 = acc2[e][n].y;
           }
-          if constexpr (TM)  // time-major scratch for a following in-library stage: one 16-byte store per lane
-            *reinterpret_cast<float4 *>(p.out_tm + ((int64_t) group * p.out_tm_rows + o) * SGN + lane * 4) =
-                make_float4(vt[0], vt[1], vt[2], vt[3]);
+          if (en.kind == kKindBlend) {  // art_resampler.cpp:450, un-fused
+            v[e][n] = __fadd_rn(__fmul_rn(sum2, en.w), __fmul_rn(sum1, __fsub_rn(1.0f, en.w)));
+          } else if (en.kind == kKindSingle) {
+            v[e][n] = sum1;
+          } else {  // pass-through: *source (art_resampler.cpp:426,440) = tap numTaps/2-1 of the window
+            v[e][n] = p.xt[((int64_t) group * p.xt_rows + (en.ws + T / 2 - 1 + T)) * SGN + lane * 4 + e];
+          }
+        }
+      }
+      const int series0 = group * SGN + lane * 4;
+      if constexpr (TM) {  // time-major scratch for a following in-library stage: one 16-byte store per lane
+        float *dst = p.out_tm + ((int64_t) group * p.out_tm_rows + o0) * SGN + lane * 4;
+#pragma unroll
+        for (int n = 0; n < NB; ++n)
+          if (o0 + n < p.n_out)
+            *reinterpret_cast<float4 *>(dst + n * SGN) = make_float4(v[0][n], v[1][n], v[2][n], v[3][n]);
+      } else if (p.out_vec == kOutVecStereo && o0 + NB <= p.n_out) {
+        // interleaved stereo: a lane owns two streams x 8 frames x 2 channels = 2 x 64 contiguous bytes
+        float *dst = p.out + (int64_t) (series0 >> 1) * p.out_ss + (int64_t) o0 * 2;
+        if (series0 < p.n_series) {
+#pragma unroll
+          for (int k = 0; k < NB / 2; ++k)
+            reinterpret_cast<float4 *>(dst)[k] = make_float4(v[0][2 * k], v[1][2 * k], v[0][2 * k + 1], v[1][2 * k + 1]);
+        }
+        if (series0 + 2 < p.n_series) {
+          dst += p.out_ss;
+#pragma unroll
+          for (int k = 0; k < NB / 2; ++k)
+            reinterpret_cast<float4 *>(dst)[k] = make_float4(v[2][2 * k], v[3][2 * k], v[2][2 * k + 1], v[3][2 * k + 1]);
+        }
+      } else if (p.out_vec == kOutVecFrame4 && o0 + NB <= p.n_out) {
+        // interleaved, channel count a multiple of 4: the lane's 4 series are 16 contiguous bytes of every frame
+        if (series0 < p.n_series) {
+          const int sidx = series0 / p.channels, ch = series0 - sidx * p.channels;
+          float *dst = p.out + (int64_t) sidx * p.out_ss + ch + (int64_t) o0 * p.channels;
+#pragma unroll
+          for (int n = 0; n < NB; ++n)
+            *reinterpret_cast<float4 *>(dst + n * p.channels) = make_float4(v[0][n], v[1][n], v[2][n], v[3][n]);
+        }
+      } else if (p.out_vec == kOutVecPlanar && o0 + NB <= p.n_out) {
+        // frames contiguous per series (planar, or interleaved mono): 8 frames = 32 contiguous bytes per series
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int series = series0 + e;
+          if (series < p.n_series) {
+            const int sidx = series / p.channels, ch = series - sidx * p.channels;
+            float4 *dst = reinterpret_cast<float4 *>(p.out + (int64_t) sidx * p.out_ss + (int64_t) ch * p.out_cs + o0);
+            dst[0] = make_float4(v[e][0], v[e][1], v[e][2], v[e][3]);
+            dst[1] = make_float4(v[e][4], v[e][5], v[e][6], v[e][7]);
+          }
+        }
+      } else {  // any layout, partial blocks
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int series = series0 + e;
+          if (series < p.n_series) {
+            const int sidx = series / p.channels, ch = series - sidx * p.channels;
+            float *dst = p.out + (int64_t) sidx * p.out_ss + (int64_t) ch * p.out_cs + (int64_t) o0 * p.out_fs;
+#pragma unroll
+            for (int n = 0; n < NB; ++n)
+              if (o0 + n < p.n_out)
+                dst[(int64_t) n * p.out_fs] = v[e][n];
+          }
         }
       }
       clear_acc();
@@ -585,7 +639,7 @@ size_t resample_smem_bytes(int bpp) {
   const int stages = resample_stages(bpp);
   return (size_t) stages * (CJ * bpp * kGRowFloats + CJ * SGN) * sizeof(float) + stages * sizeof(uint64_t) +
          2 * stages * sizeof(int) + max_chunks_per_cta(bpp) * sizeof(ChunkEntry) +
-         (size_t) kMaxPassesPerCta * bpp * sizeof(int2);
+         (size_t) kMaxPassesPerCta * bpp * sizeof(int2) + (size_t) bpp * NB * sizeof(OutEntry);
 }
 
 size_t g_chunk_floats(int bpp) { return (size_t) CJ * bpp * kGRowFloats; }
@@ -770,11 +824,21 @@ cudaError_t launch_resample(const ResampleParams &p, int bpp, bool exact, cudaSt
     return cudaSuccess;
   const int n_ctas_y = (n_passes + p.passes_per_cta - 1) / p.passes_per_cta;
   const bool tm = p.out_tm != nullptr;
+  ResampleParams q = p;
+  q.out_vec = kOutVecNone;  // 128-bit stores when the caller's layout keeps a lane's results contiguous and aligned
+  if (!tm && (uintptr_t) p.out % 16 == 0 && p.out_ss % 4 == 0) {
+    if (p.out_fs == 1 && p.out_cs % 4 == 0)
+      q.out_vec = kOutVecPlanar;
+    else if (p.out_cs == 1 && p.out_fs == p.channels && p.channels == 2)
+      q.out_vec = kOutVecStereo;
+    else if (p.out_cs == 1 && p.out_fs == p.channels && p.channels % 4 == 0)
+      q.out_vec = kOutVecFrame4;
+  }
 #define ESPB_LAUNCH(BPP_, NST_)                                                                        \
-  (exact ? (tm ? launch_resample_t<BPP_, NST_, true, true>(p, n_groups, n_ctas_y, stream)              \
-               : launch_resample_t<BPP_, NST_, true, false>(p, n_groups, n_ctas_y, stream))            \
-         : (tm ? launch_resample_t<BPP_, NST_, false, true>(p, n_groups, n_ctas_y, stream)             \
-               : launch_resample_t<BPP_, NST_, false, false>(p, n_groups, n_ctas_y, stream)))
+  (exact ? (tm ? launch_resample_t<BPP_, NST_, true, true>(q, n_groups, n_ctas_y, stream)              \
+               : launch_resample_t<BPP_, NST_, true, false>(q, n_groups, n_ctas_y, stream))            \
+         : (tm ? launch_resample_t<BPP_, NST_, false, true>(q, n_groups, n_ctas_y, stream)             \
+               : launch_resample_t<BPP_, NST_, false, false>(q, n_groups, n_ctas_y, stream)))
   if (bpp == 8)
     return ESPB_LAUNCH(8, 3);
   if (bpp == 4)

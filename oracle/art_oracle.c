@@ -408,6 +408,33 @@ uint32_t orc_float_to_quantized(const float *in, uint8_t *out, uint32_t n, uint8
 }
 
 /* ------------------------------------------------------------------------- */
+/* Q15 mix / volume — src/dsp/dsps_add_s16_ansi.c, src/dsp/dsps_mulc_s16_ansi.c */
+/* ------------------------------------------------------------------------- */
+
+/* dsps_add_s16_ansi.c:10-27 — 32-bit sum, arithmetic shift, truncated to int16 */
+int orc_add_s16(const int16_t *in1, const int16_t *in2, int16_t *out, int len, int step1, int step2, int step_out,
+                int shift) {
+  if (!in1 || !in2 || !out)
+    return -1;
+  for (int i = 0; i < len; i++) {
+    int32_t acc = (int32_t) in1[i * step1] + (int32_t) in2[i * step2];
+    out[i * step_out] = (int16_t) (acc >> shift);
+  }
+  return 0;
+}
+
+/* dsps_mulc_s16_ansi.c:18-31 — Q15 multiply by a constant */
+int orc_mulc_s16(const int16_t *in, int16_t *out, int len, int16_t c, int step_in, int step_out) {
+  if (!in || !out)
+    return -1;
+  for (int i = 0; i < len; i++) {
+    int32_t acc = (int32_t) in[i * step_in] * (int32_t) c;
+    out[i * step_out] = (int16_t) (acc >> 15);
+  }
+  return 0;
+}
+
+/* ------------------------------------------------------------------------- */
 /* Resampler wrapper — src/resample/resampler.cpp, include/resampler.h         */
 /* ------------------------------------------------------------------------- */
 

@@ -68,6 +68,11 @@ float orc_biquad_apply_sample(OrcBiquad *f, float x);
 void orc_quantized_to_float(const uint8_t *in, float *out, uint32_t n, uint8_t bits, float gain_db);
 uint32_t orc_float_to_quantized(const float *in, uint8_t *out, uint32_t n, uint8_t bits);
 
+/* include/dsp.h:66-93 — Q15 helpers downstream of the path; 0 = ESP_OK, -1 = ESP_FAIL */
+int orc_add_s16(const int16_t *in1, const int16_t *in2, int16_t *out, int len, int step1, int step2, int step_out,
+                int shift);
+int orc_mulc_s16(const int16_t *in, int16_t *out, int len, int16_t c, int step_in, int step_out);
+
 /* include/resampler.h:15-80 — pipeline policy + per-chunk composition */
 typedef struct OrcWrapper OrcWrapper;
 OrcWrapper *orc_wrapper_create(size_t in_samples, size_t out_samples, float src_rate, float dst_rate, int src_bits,

@@ -21,6 +21,7 @@
 
 #include "art_biquad.h"
 #include "art_resampler.h"
+#include "dsp.h"
 #include "quantization_utils.h"
 #include "resampler.h"
 
@@ -86,6 +87,15 @@ void ref_quantized_to_float(const uint8_t *in, float *out, uint32_t n, uint8_t b
 }
 uint32_t ref_float_to_quantized(const float *in, uint8_t *out, uint32_t n, uint8_t bits) {
   return quantization_utils::float_to_quantized(in, out, n, bits);
+}
+
+// ---- dsp.h Q15 helpers (portable C versions) ---------------------------------
+int ref_add_s16(const int16_t *in1, const int16_t *in2, int16_t *out, int len, int step1, int step2, int step_out,
+                int shift) {
+  return dsps_add_s16_ansi(in1, in2, out, len, step1, step2, step_out, shift);
+}
+int ref_mulc_s16(const int16_t *in, int16_t *out, int len, int16_t c, int step_in, int step_out) {
+  return dsps_mulc_s16_ansi(in, out, len, c, step_in, step_out);
 }
 
 // ---- resampler::Resampler wrapper -----------------------------------------

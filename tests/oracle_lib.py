@@ -24,6 +24,7 @@ INCLUDE_LOWPASS = 0x4
 
 _f32p = np.ctypeslib.ndpointer(np.float32, flags="C_CONTIGUOUS")
 _u8p = np.ctypeslib.ndpointer(np.uint8, flags="C_CONTIGUOUS")
+_i16p = np.ctypeslib.ndpointer(np.int16, flags="C_CONTIGUOUS")
 
 
 def build_oracle():
@@ -86,6 +87,19 @@ class _Backend:
         h = self.f["w_create"](in_samples, out_samples, src_rate, dst_rate, src_bits, dst_bits, channels,
                                int(use_filter), int(interpolate), taps, filters)
         return WrapperContext(self, h, channels, src_bits, dst_bits) if h else None
+
+    # ---- Q15 helpers ----
+    def add_s16(self, a, b, n, step1=1, step2=1, step_out=1, shift=0):
+        a, b = np.ascontiguousarray(a, np.int16), np.ascontiguousarray(b, np.int16)
+        out = np.zeros(max(n * step_out, 1), np.int16)
+        rc = self.f["add_s16"](a, b, out, n, step1, step2, step_out, shift)
+        return out, rc
+
+    def mulc_s16(self, a, n, c, step_in=1, step_out=1):
+        a = np.ascontiguousarray(a, np.int16)
+        out = np.zeros(max(n * step_out, 1), np.int16)
+        rc = self.f["mulc_s16"](a, out, n, c, step_in, step_out)
+        return out, rc
 
     def bench_resample(self, n_threads, channels, taps, filters, lowpass, flags, advance, x, n_out, ratio):
         """x: (n_streams, n_in*channels) float32.  Returns (seconds, frames_generated, out)."""
@@ -236,6 +250,8 @@ def _table(n):
         "w_resample": (n["w_resample"], None, [_vp, _u8p, _u8p, C.c_size_t, C.c_size_t, _f,
                                                C.POINTER(C.c_uint64)]),
         "bench": (n["bench"], C.c_double, _BENCH_ARGS),
+        "add_s16": (n["add_s16"], _i, [_i16p, _i16p, _i16p, _i, _i, _i, _i, _i]),
+        "mulc_s16": (n["mulc_s16"], _i, [_i16p, _i16p, _i, C.c_int16, _i, _i]),
     }
 
 
@@ -253,7 +269,7 @@ class Oracle(_Backend):
                      bq_highpass="biquad_highpass", bq_init="biquad_init", bq_apply="biquad_apply_buffer",
                      bq_sample="biquad_apply_sample", q2f="quantized_to_float", f2q="float_to_quantized",
                      w_create="wrapper_create", w_free="wrapper_free", w_resample="wrapper_resample",
-                     bench="bench_resample")
+                     bench="bench_resample", add_s16="add_s16", mulc_s16="mulc_s16")
         self.f = _bind(self.lib, "orc_", _table(names))
         self.lib.orc_wrapper_policy.restype = _i
         self.lib.orc_wrapper_policy.argtypes = [_vp, _f32p, C.POINTER(C.c_float), C.POINTER(C.c_float),
@@ -282,7 +298,7 @@ class Reference(_Backend):
                      bq_highpass="biquad_highpass", bq_init="biquad_init", bq_apply="biquad_apply_buffer",
                      bq_sample="biquad_apply_sample", q2f="quantized_to_float", f2q="float_to_quantized",
                      w_create="wrapper_create", w_free="wrapper_free", w_resample="wrapper_resample",
-                     bench="bench_resample")
+                     bench="bench_resample", add_s16="add_s16", mulc_s16="mulc_s16")
         self.f = _bind(self.lib, "ref_", _table(names))
 
 
