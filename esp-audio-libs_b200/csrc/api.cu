@@ -301,6 +301,7 @@ struct EspbResampleBatch {
   ArtState state{};
   int mode = ESPB_MODE_FAST;
   int bpp = 8;  // output blocks (warps) per pass
+  int chunk_rows = kChunkRows;  // input rows per pipeline stage (32, or 16 with twice the stages)
   std::vector<float> bank_host;
   DevBuf bank;
   // time-major input staging xt[group][row][128]: rows [0, taps) = frames carried over from the
@@ -361,7 +362,7 @@ int prepare_call(EspbResampleBatch *c, int n_in, int n_out, float ratio, cudaStr
   c->plan_on_device = false;
   c->g_resident_first = c->g_resident_end = -1;
   build_schedule(c->geo, c->state, n_in, n_out, ratio, c->sched, /*finalize=*/false);  // pass 2 runs on the device
-  build_pass_plan(c->sched, c->geo.taps, c->bpp, c->plan);
+  build_pass_plan(c->sched, c->geo.taps, c->bpp, c->chunk_rows, c->plan);
   c->key = k;
   if (c->sched.generated == 0) {
     c->plan_on_device = true;
@@ -389,7 +390,7 @@ int prepare_call(EspbResampleBatch *c, int n_in, int n_out, float ratio, cudaStr
 // Number of passes per time slab so that the expanded coefficients fit the G budget.
 int passes_per_slab(const EspbResampleBatch *c) {
   const int n_passes = c->plan.n_passes();
-  const size_t chunk_bytes = g_chunk_floats(c->bpp) * sizeof(float);
+  const size_t chunk_bytes = g_chunk_floats(c->bpp, c->chunk_rows) * sizeof(float);
   const size_t total = c->plan.chunks.size() * chunk_bytes;
   if (total <= c->g_budget_bytes || n_passes <= 1)
     return n_passes;
@@ -402,11 +403,11 @@ int passes_per_slab(const EspbResampleBatch *c) {
 int ensure_g(EspbResampleBatch *c, int chunk_first, int chunk_end, cudaStream_t stream) {
   if (c->g_resident_first == chunk_first && c->g_resident_end == chunk_end)
     return ESPB_OK;
-  const size_t chunk_floats = g_chunk_floats(c->bpp);
+  const size_t chunk_floats = g_chunk_floats(c->bpp, c->chunk_rows);
   CU_TRY(c->d_G.reserve((size_t) (chunk_end - chunk_first) * chunk_floats * sizeof(float)), "cudaMalloc G");
   CU_TRY(launch_expand(c->bank.as<float>(), c->d_outs.as<OutEntry>(), c->d_chunks.as<ChunkEntry>(),
                        c->d_G.as<float>(), chunk_first, chunk_end - chunk_first, (int) c->sched.generated,
-                       c->geo.taps, c->bpp, stream),
+                       c->geo.taps, c->bpp, c->chunk_rows, stream),
          "expand kernel");
   c->g_resident_first = chunk_first;
   c->g_resident_end = chunk_end;
@@ -619,7 +620,7 @@ int run_series_range(EspbResampleBatch *c, int series_first, int n_series, const
         ev_after = c->ev_pool[c->ev_used + 1];
         c->ev_used += 2;
       }
-      CU_TRY(launch_resample(p, c->bpp, c->mode == ESPB_MODE_EXACT, stream), "resample kernel");
+      CU_TRY(launch_resample(p, c->bpp, c->chunk_rows, c->mode == ESPB_MODE_EXACT, stream), "resample kernel");
       if (ev_after)
         CU_TRY(cudaEventRecord(ev_after, stream), "cudaEventRecord");
     }
@@ -715,6 +716,7 @@ EspbResampleBatch *espb_resampleInit(int num_streams, int numChannels, int numTa
   // 4 output blocks (warps) per pass, four CTAs per SM: measured 5 % faster than 8 x 2 at C2 (shorter passes
   // leave less idle time at the pass edges); ESPB_BPP=8 selects the other variant
   c->bpp = env_long("ESPB_BPP", 4) == 8 ? 8 : 4;
+  c->chunk_rows = env_long("ESPB_CHUNK_ROWS", 32) == 16 ? 16 : 32;
   long gb = env_long("ESPB_G_MBYTES", 0);
   if (gb > 0)
     c->g_budget_bytes = (size_t) gb << 20;

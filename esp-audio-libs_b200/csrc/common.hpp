@@ -6,7 +6,7 @@ namespace espb {
 
 // Tile geometry of the resampler kernel (see DESIGN.md "Resampler kernel").
 constexpr int kOutputsPerBlock = 8;   // NB: outputs accumulated per thread
-constexpr int kChunkRows = 32;        // CJ: input frames staged per pipeline stage
+constexpr int kChunkRows = 32;        // most input frames staged per pipeline stage (the kernel variants use 32 or 16)
 constexpr int kSeriesPerRow = 128;    // series (stream x channel) per warp row: 32 lanes x 4
 constexpr int kGRowFloats = 2 * kOutputsPerBlock;  // 16 coefficients per (row, output block)
 // chunk-table entries a CTA caches in shared memory (fewer for the 4-warp variant: four CTAs share an SM)

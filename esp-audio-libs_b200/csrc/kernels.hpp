@@ -27,12 +27,13 @@ struct ResampleParams {
 };
 enum OutVec : int { kOutVecNone = 0, kOutVecPlanar = 1, kOutVecStereo = 2, kOutVecFrame4 = 3 };
 
-size_t resample_smem_bytes(int bpp);
-size_t g_chunk_floats(int bpp);
+size_t resample_smem_bytes(int bpp, int chunk_rows);
+size_t g_chunk_floats(int bpp, int chunk_rows);
 cudaError_t launch_finalize(OutEntry *outs, int n, int n_filters, bool lowpass, bool interp, cudaStream_t stream);
 cudaError_t launch_expand(const float *bank, const OutEntry *outs, const ChunkEntry *chunks, float *G,
-                          int chunk_first, int n_chunks, int n_out, int taps, int bpp, cudaStream_t stream);
-cudaError_t launch_resample(const ResampleParams &p, int bpp, bool exact, cudaStream_t stream);
+                          int chunk_first, int n_chunks, int n_out, int taps, int bpp, int chunk_rows,
+                          cudaStream_t stream);
+cudaError_t launch_resample(const ResampleParams &p, int bpp, int chunk_rows, bool exact, cudaStream_t stream);
 cudaError_t launch_transpose(const float *in, int64_t in_ss, int64_t in_cs, int64_t in_fs, int channels, int n_series,
                              int n_in, float *xt, int64_t rows_cap, int row_first, int pad_rows,
                              cudaStream_t stream);

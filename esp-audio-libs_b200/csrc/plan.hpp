@@ -79,14 +79,14 @@ unsigned expected_output(const ArtGeometry &g, ArtState st, int n_in, float rati
 float position_of(const ArtGeometry &g, ArtState st);                                   // :348
 
 // Pass / chunk tables for the kernel: pass p covers outputs [p*opp, (p+1)*opp) and
-// sweeps input rows [ws(first), ws(last)+taps) in chunks of kChunkRows.
+// sweeps input rows [ws(first), ws(last)+taps) in chunks of chunk_rows (<= kChunkRows).
 struct PassPlan {
   int outputs_per_pass = 0;
   PodBuffer<ChunkEntry> chunks;
   PodBuffer<int32_t> pass_chunk_begin;  // n_passes + 1 prefix
   int n_passes() const { return (int) pass_chunk_begin.size() - 1; }
 };
-void build_pass_plan(const Schedule &s, int taps, int blocks_per_pass, PassPlan &p);
+void build_pass_plan(const Schedule &s, int taps, int blocks_per_pass, int chunk_rows, PassPlan &p);
 
 // art_biquad.cpp:16-38 (design in double, stored as float).
 struct BiquadCoeffs {

@@ -44,9 +44,8 @@ namespace espb {
 namespace {
 
 constexpr int NB = kOutputsPerBlock;  // 8
-constexpr int CJ = kChunkRows;        // 32
 constexpr int SGN = kSeriesPerRow;    // 128
-constexpr int kLastChunkOfPass = 1 << 30;
+constexpr uint32_t kPassDone = 1u << 9;  // rtab flag next to r0 (bits 0-3), r1 (4-7)
 constexpr int RG = 4;  // rows per skip group / inner unroll
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t) __cvta_generic_to_shared(p); }
@@ -151,7 +150,7 @@ __global__ void __launch_bounds__(256)
 __global__ void __launch_bounds__(256) espb_expand_kernel(const float *__restrict__ bank,
                                                           const OutEntry *__restrict__ outs,
                                                           const ChunkEntry *__restrict__ chunks, float *__restrict__ G,
-                                                          int chunk_first, int n_out, int taps, int bpp) {
+                                                          int chunk_first, int n_out, int taps, int bpp, int CJ) {
   const int gc = chunk_first + blockIdx.x;
   const ChunkEntry ce = chunks[gc];
   const int quads_per_row = bpp * (kGRowFloats / 4);  // float4 per row
@@ -373,11 +372,12 @@ __global__ void __launch_bounds__(256)
 // TM: write the output time-major (scratch for a following library stage) instead of the caller's layout.
 // BPP: output blocks (= warps) per pass; NST: ring stages.  <8,3>: two 8-warp CTAs per SM; <4,2>: four 4-warp
 // CTAs per SM (shorter passes: less idle time at the pass edges, twice the x traffic from L2).
-template <int BPP, int NST, bool EXACT, bool TM>
+template <int BPP, int NST, int CJ, bool EXACT, bool TM>
 __global__ void __launch_bounds__(BPP * 32, 16 / BPP) espb_resample_kernel(const ResampleParams p) {
   constexpr int NTHREADS = BPP * 32;
   constexpr int STAGES = NST;
-  constexpr int MAXC = max_chunks_per_cta(BPP), MAXP = kMaxPassesPerCta;
+  constexpr int MAXC = max_chunks_per_cta(BPP);
+  static_assert(kMaxPassesPerCta * BPP * sizeof(int2) <= (size_t) NST * CJ * SGN * sizeof(float), "set-up table");
   constexpr int XS_STAGE = CJ * SGN;                // floats
   constexpr int GS_STAGE = CJ * BPP * kGRowFloats;  // floats
   constexpr uint32_t X_BYTES = XS_STAGE * sizeof(float), G_BYTES = GS_STAGE * sizeof(float);
@@ -387,10 +387,12 @@ __global__ void __launch_bounds__(BPP * 32, 16 / BPP) espb_resample_kernel(const
   float *xs = gs + STAGES * GS_STAGE;                                     // [STAGES][CJ][128]
   uint64_t *full = reinterpret_cast<uint64_t *>(xs + STAGES * XS_STAGE);  // [STAGES] TMA landed
   int *done = reinterpret_cast<int *>(full + STAGES);                     // [2*STAGES] warps done with a stage
-  ChunkEntry *ctab = reinterpret_cast<ChunkEntry *>(done + 2 * STAGES);   // [MAXC] this CTA's chunks
-  int2 *wtab = reinterpret_cast<int2 *>(ctab + MAXC);  // [MAXP][BPP] window [lo, hi) per (pass, warp)
+  int32_t *jtab = reinterpret_cast<int32_t *>(done + 2 * STAGES);         // [MAXC] first input row of each chunk
+  // [MAXC][BPP] what warp w does in chunk c: row groups [r0, r1), end-of-pass flag
+  uint16_t *rtab = reinterpret_cast<uint16_t *>(jtab + MAXC);
   // [BPP][NB] schedule entries of the block each warp is finishing, fetched by cp.async during the pass's last chunk
-  OutEntry *etab = reinterpret_cast<OutEntry *>(wtab + MAXP * BPP);
+  OutEntry *etab = reinterpret_cast<OutEntry *>(rtab + MAXC * BPP);
+  int2 *wtab = reinterpret_cast<int2 *>(smem_raw);  // set-up only (the ring is not in use yet): [MAXP][BPP] windows
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int group = blockIdx.x;
@@ -404,14 +406,8 @@ __global__ void __launch_bounds__(BPP * 32, 16 / BPP) espb_resample_kernel(const
   const int chunk_first = p.pass_chunk_begin[pass_first], chunk_last = p.pass_chunk_begin[pass_last];
   const int n_chunks = __shfl_sync(0xffffffffu, chunk_last - chunk_first, 0);  // warp-uniform by construction
 
-  // ---- cache the signal-independent tables this CTA needs (no global loads in the main loop)
-  for (int i = tid; i < n_chunks; i += NTHREADS) {  // .pass gets bit 30 set on the last chunk of its pass
-    ChunkEntry ce = p.chunks[chunk_first + i];
-    if (i + 1 == n_chunks || p.chunks[chunk_first + i + 1].pass != ce.pass)
-      ce.pass |= kLastChunkOfPass;
-    ctab[i] = ce;
-  }
-  for (int i = tid; i < (pass_last - pass_first) * BPP; i += NTHREADS) {
+  // ---- build the signal-independent tables this CTA needs (no global loads, no index arithmetic in the main loop)
+  for (int i = tid; i < (pass_last - pass_first) * BPP; i += NTHREADS) {  // window [lo, hi) of (pass, warp)
     const int o0 = ((pass_first + i / BPP) * BPP + (i % BPP)) * NB;
     int2 w = make_int2(0, 0);
     if (o0 < p.n_out) {
@@ -430,6 +426,25 @@ __global__ void __launch_bounds__(BPP * 32, 16 / BPP) espb_resample_kernel(const
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   __syncthreads();
+  for (int i = tid; i < n_chunks; i += NTHREADS) {
+    const ChunkEntry ce = p.chunks[chunk_first + i];
+    const bool last_of_pass = (i + 1 == n_chunks) || (p.chunks[chunk_first + i + 1].pass != ce.pass);
+    jtab[i] = ce.j_start;
+    // rows of this chunk inside each warp's window, in groups of RG (rows outside it only multiply zeros)
+#pragma unroll
+    for (int w = 0; w < BPP; ++w) {
+      const int2 win = wtab[(ce.pass - pass_first) * BPP + w];
+      int r0 = win.x - ce.j_start, r1 = win.y - ce.j_start;
+      r0 = r0 < 0 ? 0 : (r0 / RG);
+      r1 = r1 > CJ ? CJ / RG : ((r1 + RG - 1) / RG);
+      if (r0 > CJ / RG)
+        r0 = CJ / RG;
+      if (r1 < r0)
+        r1 = r0;
+      rtab[i * BPP + w] = (uint16_t) (r0 | (r1 << 4) | (last_of_pass ? kPassDone : 0));
+    }
+  }
+  __syncthreads();
 
   // Fill stage c % STAGES with chunk c: two TMA bulk copies (16 KB of G, 16 KB of x) on one mbarrier.
   // (Addresses are rebuilt from the parameters here — one lane runs this once per chunk — rather than held in
@@ -441,7 +456,7 @@ __global__ void __launch_bounds__(BPP * 32, 16 / BPP) espb_resample_kernel(const
         p.G + (size_t) (p.pass_chunk_begin[p.pass_first + blockIdx.y * p.passes_per_cta] - p.g_chunk_base) * GS_STAGE;
     mbar_expect_tx(&full[st], X_BYTES + G_BYTES);
     tma_bulk_g2s(gs + st * GS_STAGE, g_base + (size_t) c * GS_STAGE, G_BYTES, &full[st]);
-    tma_bulk_g2s(xs + st * XS_STAGE, xt_group + (int64_t) (ctab[c].j_start + T) * SGN, X_BYTES, &full[st]);
+    tma_bulk_g2s(xs + st * XS_STAGE, xt_group + (int64_t) (jtab[c] + T) * SGN, X_BYTES, &full[st]);
   };
   if (tid == 0)
     for (int c = 0; c < STAGES && c < n_chunks; ++c)
@@ -467,23 +482,12 @@ __global__ void __launch_bounds__(BPP * 32, 16 / BPP) espb_resample_kernel(const
   };
   clear_acc();
 
-  int cur_pass = -1, win_lo = 0, win_hi = 0;  // this warp's window [win_lo, win_hi) in input frames
+  int cur_pass = pass_first;
   for (int c = 0; c < n_chunks; ++c) {
     const int st = c % STAGES;
-    ChunkEntry ce = ctab[c];
-    const bool pass_done = (ce.pass & kLastChunkOfPass) != 0;
-    ce.pass &= ~kLastChunkOfPass;
-    if (ce.pass != cur_pass) {
-      cur_pass = ce.pass;
-      const int2 w = wtab[(cur_pass - pass_first) * BPP + warp];
-      win_lo = w.x;
-      win_hi = w.y;
-    }
-    // rows of this chunk inside the warp's window, in groups of RG (rows outside it only multiply zeros)
-    int r0 = win_lo - ce.j_start, r1 = win_hi - ce.j_start;
-    r0 = r0 < 0 ? 0 : (r0 / RG);
-    r1 = r1 > CJ ? CJ / RG : ((r1 + RG - 1) / RG);
-
+    const uint32_t role = rtab[c * BPP + warp];
+    const bool pass_done = (role & kPassDone) != 0;
+    const int r0 = role & 15, r1 = (role >> 4) & 15;
     if (pass_done && lane < NB) {  // the epilogue's schedule entries: global -> shared, no register held meanwhile
       int o = (cur_pass * BPP + warp) * NB + lane;
       o = o < p.n_out ? o : p.n_out - 1;
@@ -530,7 +534,8 @@ __global__ void __launch_bounds__(BPP * 32, 16 / BPP) espb_resample_kernel(const
     }
 
     // Release the stage.  The last of the BPP warps to get here re-arms it and issues the refill
-    // (chunk c + STAGES); nobody waits for anybody.
+    // (chunk c + STAGES); nobody waits for anybody.  (A designated refilling warp that waits for the others on an
+    // "empty" mbarrier was measured 17 % slower: it cannot run ahead while it waits.)
     __syncwarp();
     if (lane == 0) {
       if (smem_arrive(&done[st]) == BPP - 1) {
@@ -626,6 +631,7 @@ __global__ void __launch_bounds__(BPP * 32, 16 / BPP) espb_resample_kernel(const
         }
       }
       clear_acc();
+      ++cur_pass;
     }
   }
 }
@@ -633,16 +639,16 @@ __global__ void __launch_bounds__(BPP * 32, 16 / BPP) espb_resample_kernel(const
 // ---------------------------------------------------------------------------------
 // launchers
 // ---------------------------------------------------------------------------------
-int resample_stages(int bpp) { return bpp == 8 ? 3 : 2; }
+int resample_stages(int bpp, int CJ) { return (bpp == 8 ? 3 : 2) * (kChunkRows / CJ); }
 
-size_t resample_smem_bytes(int bpp) {
-  const int stages = resample_stages(bpp);
+size_t resample_smem_bytes(int bpp, int CJ) {
+  const int stages = resample_stages(bpp, CJ);
   return (size_t) stages * (CJ * bpp * kGRowFloats + CJ * SGN) * sizeof(float) + stages * sizeof(uint64_t) +
-         2 * stages * sizeof(int) + max_chunks_per_cta(bpp) * sizeof(ChunkEntry) +
-         (size_t) kMaxPassesPerCta * bpp * sizeof(int2) + (size_t) bpp * NB * sizeof(OutEntry);
+         stages * sizeof(uint64_t) + max_chunks_per_cta(bpp) * (sizeof(int32_t) + bpp * sizeof(uint16_t)) +
+         (size_t) bpp * NB * sizeof(OutEntry);
 }
 
-size_t g_chunk_floats(int bpp) { return (size_t) CJ * bpp * kGRowFloats; }
+size_t g_chunk_floats(int bpp, int CJ) { return (size_t) CJ * bpp * kGRowFloats; }
 
 cudaError_t launch_finalize(OutEntry *outs, int n, int n_filters, bool lowpass, bool interp, cudaStream_t stream) {
   if (n <= 0)
@@ -653,10 +659,11 @@ cudaError_t launch_finalize(OutEntry *outs, int n, int n_filters, bool lowpass, 
 }
 
 cudaError_t launch_expand(const float *bank, const OutEntry *outs, const ChunkEntry *chunks, float *G,
-                          int chunk_first, int n_chunks, int n_out, int taps, int bpp, cudaStream_t stream) {
+                          int chunk_first, int n_chunks, int n_out, int taps, int bpp, int chunk_rows,
+                          cudaStream_t stream) {
   if (n_chunks <= 0)
     return cudaSuccess;
-  espb_expand_kernel<<<n_chunks, 256, 0, stream>>>(bank, outs, chunks, G, chunk_first, n_out, taps, bpp);
+  espb_expand_kernel<<<n_chunks, 256, 0, stream>>>(bank, outs, chunks, G, chunk_first, n_out, taps, bpp, chunk_rows);
   count_launch();
   return cudaGetLastError();
 }
@@ -787,37 +794,37 @@ cudaError_t launch_untranspose(const float *tm, int64_t rows_cap, int row_first,
   return cudaGetLastError();
 }
 
-template <int BPP, int NST, bool EXACT, bool TM>
+template <int BPP, int NST, int CJ, bool EXACT, bool TM>
 static cudaError_t launch_resample_t(const ResampleParams &p, int n_groups, int n_ctas_y, cudaStream_t stream) {
-  const size_t smem = resample_smem_bytes(BPP);
+  const size_t smem = resample_smem_bytes(BPP, CJ);
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(espb_resample_kernel<BPP, NST, EXACT, TM>,
+    cudaError_t e = cudaFuncSetAttribute(espb_resample_kernel<BPP, NST, CJ, EXACT, TM>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
     if (e != cudaSuccess)
       return e;
     // two CTAs per SM need the full 228 KB carve-out (the default heuristic sizes it for one)
-    e = cudaFuncSetAttribute(espb_resample_kernel<BPP, NST, EXACT, TM>, cudaFuncAttributePreferredSharedMemoryCarveout,
+    e = cudaFuncSetAttribute(espb_resample_kernel<BPP, NST, CJ, EXACT, TM>, cudaFuncAttributePreferredSharedMemoryCarveout,
                              (int) cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess)
       return e;
     configured = true;
     if (getenv("ESPB_DEBUG")) {
       int nb = 0;
-      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, espb_resample_kernel<BPP, NST, EXACT, TM>, BPP * 32, smem);
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, espb_resample_kernel<BPP, NST, CJ, EXACT, TM>, BPP * 32, smem);
       cudaFuncAttributes fa;
-      cudaFuncGetAttributes(&fa, espb_resample_kernel<BPP, NST, EXACT, TM>);
-      fprintf(stderr, "[espb] resample<%d,%d,%d,%d>: smem %zu B, %d regs, occupancy %d CTA/SM\n", BPP, NST,
+      cudaFuncGetAttributes(&fa, espb_resample_kernel<BPP, NST, CJ, EXACT, TM>);
+      fprintf(stderr, "[espb] resample<%d,%d,%d,%d,%d>: smem %zu B, %d regs, occupancy %d CTA/SM\n", BPP, NST, CJ,
               (int) EXACT, (int) TM, smem, fa.numRegs, nb);
     }
   }
   dim3 grid(n_groups, n_ctas_y);
-  espb_resample_kernel<BPP, NST, EXACT, TM><<<grid, BPP * 32, smem, stream>>>(p);
+  espb_resample_kernel<BPP, NST, CJ, EXACT, TM><<<grid, BPP * 32, smem, stream>>>(p);
   count_launch();
   return cudaGetLastError();
 }
 
-cudaError_t launch_resample(const ResampleParams &p, int bpp, bool exact, cudaStream_t stream) {
+cudaError_t launch_resample(const ResampleParams &p, int bpp, int chunk_rows, bool exact, cudaStream_t stream) {
   const int n_groups = (p.n_series + SGN - 1) / SGN;
   const int n_passes = p.pass_end - p.pass_first;
   if (n_groups <= 0 || n_passes <= 0)
@@ -834,15 +841,19 @@ cudaError_t launch_resample(const ResampleParams &p, int bpp, bool exact, cudaSt
     else if (p.out_cs == 1 && p.out_fs == p.channels && p.channels % 4 == 0)
       q.out_vec = kOutVecFrame4;
   }
-#define ESPB_LAUNCH(BPP_, NST_)                                                                        \
-  (exact ? (tm ? launch_resample_t<BPP_, NST_, true, true>(q, n_groups, n_ctas_y, stream)              \
-               : launch_resample_t<BPP_, NST_, true, false>(q, n_groups, n_ctas_y, stream))            \
-         : (tm ? launch_resample_t<BPP_, NST_, false, true>(q, n_groups, n_ctas_y, stream)             \
-               : launch_resample_t<BPP_, NST_, false, false>(q, n_groups, n_ctas_y, stream)))
-  if (bpp == 8)
-    return ESPB_LAUNCH(8, 3);
-  if (bpp == 4)
-    return ESPB_LAUNCH(4, 2);
+#define ESPB_LAUNCH(BPP_, NST_, CJ_)                                                                   \
+  (exact ? (tm ? launch_resample_t<BPP_, NST_, CJ_, true, true>(q, n_groups, n_ctas_y, stream)         \
+               : launch_resample_t<BPP_, NST_, CJ_, true, false>(q, n_groups, n_ctas_y, stream))       \
+         : (tm ? launch_resample_t<BPP_, NST_, CJ_, false, true>(q, n_groups, n_ctas_y, stream)        \
+               : launch_resample_t<BPP_, NST_, CJ_, false, false>(q, n_groups, n_ctas_y, stream)))
+  if (bpp == 8 && chunk_rows == 32)
+    return ESPB_LAUNCH(8, 3, 32);
+  if (bpp == 4 && chunk_rows == 32)
+    return ESPB_LAUNCH(4, 2, 32);
+  if (bpp == 8 && chunk_rows == 16)
+    return ESPB_LAUNCH(8, 6, 16);
+  if (bpp == 4 && chunk_rows == 16)
+    return ESPB_LAUNCH(4, 4, 16);
 #undef ESPB_LAUNCH
   return cudaErrorInvalidValue;
 }
