@@ -392,6 +392,7 @@ __global__ void __launch_bounds__(BPP * 32, 16 / BPP) espb_resample_kernel(const
   uint16_t *rtab = reinterpret_cast<uint16_t *>(jtab + MAXC);
   // [BPP][NB] schedule entries of the block each warp is finishing, fetched by cp.async during the pass's last chunk
   OutEntry *etab = reinterpret_cast<OutEntry *>(rtab + MAXC * BPP);
+  int32_t *hdr = reinterpret_cast<int32_t *>(etab + BPP * NB);  // [4] CTA constants for the refilling lane
   int2 *wtab = reinterpret_cast<int2 *>(smem_raw);  // set-up only (the ring is not in use yet): [MAXP][BPP] windows
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -423,6 +424,7 @@ __global__ void __launch_bounds__(BPP * 32, 16 / BPP) espb_resample_kernel(const
       mbar_init(&full[s], 1);
       done[s] = 0;
     }
+    hdr[0] = chunk_first - p.g_chunk_base;
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   __syncthreads();
@@ -452,10 +454,8 @@ __global__ void __launch_bounds__(BPP * 32, 16 / BPP) espb_resample_kernel(const
   auto issue_chunk = [&](int c) {
     const int st = c % STAGES;
     const float *xt_group = p.xt + (int64_t) blockIdx.x * p.xt_rows * SGN;
-    const float *g_base =
-        p.G + (size_t) (p.pass_chunk_begin[p.pass_first + blockIdx.y * p.passes_per_cta] - p.g_chunk_base) * GS_STAGE;
     mbar_expect_tx(&full[st], X_BYTES + G_BYTES);
-    tma_bulk_g2s(gs + st * GS_STAGE, g_base + (size_t) c * GS_STAGE, G_BYTES, &full[st]);
+    tma_bulk_g2s(gs + st * GS_STAGE, p.G + (size_t) (hdr[0] + c) * GS_STAGE, G_BYTES, &full[st]);
     tma_bulk_g2s(xs + st * XS_STAGE, xt_group + (int64_t) (jtab[c] + T) * SGN, X_BYTES, &full[st]);
   };
   if (tid == 0)
@@ -483,9 +483,10 @@ __global__ void __launch_bounds__(BPP * 32, 16 / BPP) espb_resample_kernel(const
   clear_acc();
 
   int cur_pass = pass_first;
+  uint32_t role_next = rtab[warp];
   for (int c = 0; c < n_chunks; ++c) {
     const int st = c % STAGES;
-    const uint32_t role = rtab[c * BPP + warp];
+    const uint32_t role = role_next;
     const bool pass_done = (role & kPassDone) != 0;
     const int r0 = role & 15, r1 = (role >> 4) & 15;
     if (pass_done && lane < NB) {  // the epilogue's schedule entries: global -> shared, no register held meanwhile
@@ -536,6 +537,7 @@ __global__ void __launch_bounds__(BPP * 32, 16 / BPP) espb_resample_kernel(const
     // Release the stage.  The last of the BPP warps to get here re-arms it and issues the refill
     // (chunk c + STAGES); nobody waits for anybody.  (A designated refilling warp that waits for the others on an
     // "empty" mbarrier was measured 17 % slower: it cannot run ahead while it waits.)
+    role_next = rtab[(c + 1) * BPP + warp];  // (one entry past the CTA's last chunk is still inside the table)
     __syncwarp();
     if (lane == 0) {
       if (smem_arrive(&done[st]) == BPP - 1) {
@@ -645,7 +647,7 @@ size_t resample_smem_bytes(int bpp, int CJ) {
   const int stages = resample_stages(bpp, CJ);
   return (size_t) stages * (CJ * bpp * kGRowFloats + CJ * SGN) * sizeof(float) + stages * sizeof(uint64_t) +
          stages * sizeof(uint64_t) + max_chunks_per_cta(bpp) * (sizeof(int32_t) + bpp * sizeof(uint16_t)) +
-         (size_t) bpp * NB * sizeof(OutEntry);
+         (size_t) bpp * NB * sizeof(OutEntry) + 4 * sizeof(int32_t);
 }
 
 size_t g_chunk_floats(int bpp, int CJ) { return (size_t) CJ * bpp * kGRowFloats; }
