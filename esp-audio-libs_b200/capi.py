@@ -133,6 +133,8 @@ def lib():
                                    C.POINTER(i), vp, vp, vp, vp]),
         "espb_plan_policy": (i, [C.POINTER(_Config), C.POINTER(_Coeffs), C.POINTER(f), C.POINTER(f), C.POINTER(i)]),
         "espb_checksum_u32": (i, [vp, u64, vp, vp]),
+        "espb_dsps_add_s16": (i, [vp, vp, vp, i64, i, i, i, i, vp]),
+        "espb_dsps_mulc_s16": (i, [vp, vp, i64, C.c_int16, i, i, vp]),
         "espb_measure_fp32_fma_peak": (i, [C.POINTER(C.c_double), C.POINTER(C.c_double)]),
         "espb_measure_fp32_fma_peak2": (i, [C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     }
@@ -480,6 +482,37 @@ def float_to_quantized(x, bits):
     d_in.free()
     d_out.free()
     return out, int(clipped)
+
+
+def dsps_add_s16(a, b, n, step1=1, step2=1, step_out=1, shift=0, out_init=None):
+    """numpy convenience over espb_dsps_add_s16: (out int16[max(n*step_out,1)], rc).  Elements of `out` the call does
+    not write keep `out_init` (default zeros), as a caller-owned buffer would."""
+    a, b = np.ascontiguousarray(a, np.int16), np.ascontiguousarray(b, np.int16)
+    out = np.zeros(max(n * step_out, 1), np.int16) if out_init is None else np.ascontiguousarray(out_init, np.int16)
+    d_a, d_b, d_o = (DeviceBuffer.from_numpy(x if x.size else np.zeros(1, np.int16)) for x in (a, b, out))
+    rc = lib().espb_dsps_add_s16(d_a.ptr, d_b.ptr, d_o.ptr, n, step1, step2, step_out, shift, None)
+    res = d_o.download(np.int16, out.size)
+    for d in (d_a, d_b, d_o):
+        d.free()
+    return res, rc
+
+
+def dsps_mulc_s16(a, n, c, step_in=1, step_out=1, out_init=None):
+    """numpy convenience over espb_dsps_mulc_s16: (out int16[max(n*step_out,1)], rc)."""
+    a = np.ascontiguousarray(a, np.int16)
+    out = np.zeros(max(n * step_out, 1), np.int16) if out_init is None else np.ascontiguousarray(out_init, np.int16)
+    d_a, d_o = (DeviceBuffer.from_numpy(x if x.size else np.zeros(1, np.int16)) for x in (a, out))
+    rc = lib().espb_dsps_mulc_s16(d_a.ptr, d_o.ptr, n, c, step_in, step_out, None)
+    res = d_o.download(np.int16, out.size)
+    d_a.free()
+    d_o.free()
+    return res, rc
+
+
+class _Q15Backend:
+    """Same call shape as the test oracle's Q15 helpers (tests run golden cases through either)."""
+    add_s16 = staticmethod(lambda a, b, n, s1=1, s2=1, so=1, shift=0: dsps_add_s16(a, b, n, s1, s2, so, shift))
+    mulc_s16 = staticmethod(lambda a, n, c, si=1, so=1: dsps_mulc_s16(a, n, c, si, so))
 
 
 def checksum_u32(d_ptr, num_words, stream=None):

@@ -1266,6 +1266,31 @@ int espb_checksum_u32(const void *buf, uint64_t num_words, uint64_t *sum_dev, vo
   return ESPB_OK;
 }
 
+// dsps_add_s16_ansi.c:10-27 / dsps_mulc_s16_ansi.c:18-31 on device buffers.  The reference returns ESP_FAIL for a
+// NULL buffer and ESP_OK otherwise (len <= 0 is a no-op there: the loop does not run).
+int espb_dsps_add_s16(const int16_t *input1, const int16_t *input2, int16_t *output, int64_t len, int step1,
+                      int step2, int step_out, int shift, void *stream) {
+  if (!input1 || !input2 || !output)
+    return fail(ESPB_ERR_ARG, "dsps_add_s16: NULL buffer (ESP_FAIL in the reference)");
+  if (shift < 0 || shift > 31)
+    return fail(ESPB_ERR_ARG, "dsps_add_s16: shift must be 0..31 (undefined in the reference otherwise)");
+  if (len <= 0)
+    return ESPB_OK;
+  CU_TRY(launch_add_s16(input1, input2, output, (uint64_t) len, step1, step2, step_out, shift, as_stream(stream)),
+         "add_s16 kernel");
+  return ESPB_OK;
+}
+
+int espb_dsps_mulc_s16(const int16_t *input, int16_t *output, int64_t len, int16_t C, int step_in, int step_out,
+                       void *stream) {
+  if (!input || !output)
+    return fail(ESPB_ERR_ARG, "dsps_mulc_s16: NULL buffer (ESP_FAIL in the reference)");
+  if (len <= 0)
+    return ESPB_OK;
+  CU_TRY(launch_mulc_s16(input, output, (uint64_t) len, C, step_in, step_out, as_stream(stream)), "mulc_s16 kernel");
+  return ESPB_OK;
+}
+
 int espb_measure_fp32_fma_peak(double *tflops, double *sm_clock_mhz_estimate) {
   if (!tflops)
     return fail(ESPB_ERR_ARG, "measure_fp32_fma_peak: NULL");

@@ -25,7 +25,7 @@ struct ResampleParams {
   int pass_first, pass_end, passes_per_cta, g_chunk_base;
   int out_vec;  // OutVec: set by launch_resample from the output layout
 };
-enum OutVec : int { kOutVecNone = 0, kOutVecPlanar = 1, kOutVecStereo = 2, kOutVecFrame4 = 3 };
+enum OutVec : int { kOutVecNone = 0, kOutVecPlanar = 1, kOutVecStereo = 2, kOutVecFrame4 = 3, kOutVecTimeMajor = 4 };
 
 size_t resample_smem_bytes(int bpp, int chunk_rows);
 size_t g_chunk_floats(int bpp, int chunk_rows);
@@ -73,6 +73,12 @@ cudaError_t launch_biquad_tm(const float *src, float *dst, int64_t rows_cap, int
 cudaError_t launch_untranspose(const float *tm, int64_t rows_cap, int row_first, int n_rows, float *out,
                                int64_t out_ss, int64_t out_cs, int64_t out_fs, int channels, int n_series,
                                cudaStream_t stream);
+
+// dsp.h Q15 helpers (element strides; any of the buffers may alias as in the reference)
+cudaError_t launch_add_s16(const int16_t *a, const int16_t *b, int16_t *out, uint64_t n, int64_t s1, int64_t s2,
+                           int64_t so, int shift, cudaStream_t stream);
+cudaError_t launch_mulc_s16(const int16_t *a, int16_t *out, uint64_t n, int16_t c, int64_t si, int64_t so,
+                            cudaStream_t stream);
 
 // utilities
 cudaError_t launch_checksum(const uint32_t *words, uint64_t n, unsigned long long *sum_dev, cudaStream_t stream);

@@ -369,10 +369,9 @@ __global__ void __launch_bounds__(256)
 // ---------------------------------------------------------------------------------
 // Resampler
 // ---------------------------------------------------------------------------------
-// TM: write the output time-major (scratch for a following library stage) instead of the caller's layout.
 // BPP: output blocks (= warps) per pass; NST: ring stages.  <8,3>: two 8-warp CTAs per SM; <4,2>: four 4-warp
 // CTAs per SM (shorter passes: less idle time at the pass edges, twice the x traffic from L2).
-template <int BPP, int NST, int CJ, bool EXACT, bool TM>
+template <int BPP, int NST, int CJ, bool EXACT, bool TMCAP>
 __global__ void __launch_bounds__(BPP * 32, 16 / BPP) espb_resample_kernel(const ResampleParams p) {
   constexpr int NTHREADS = BPP * 32;
   constexpr int STAGES = NST;
@@ -577,7 +576,7 @@ __global__ void __launch_bounds__(BPP * 32, 16 / BPP) espb_resample_kernel(const
         }
       }
       const int series0 = group * SGN + lane * 4;
-      if constexpr (TM) {  // time-major scratch for a following in-library stage: one 16-byte store per lane
+      if (TMCAP && p.out_vec == kOutVecTimeMajor) {  // scratch for a following in-library stage: one 16-byte store per lane
         float *dst = p.out_tm + ((int64_t) group * p.out_tm_rows + o0) * SGN + lane * 4;
 #pragma unroll
         for (int n = 0; n < NB; ++n)
@@ -796,32 +795,32 @@ cudaError_t launch_untranspose(const float *tm, int64_t rows_cap, int row_first,
   return cudaGetLastError();
 }
 
-template <int BPP, int NST, int CJ, bool EXACT, bool TM>
+template <int BPP, int NST, int CJ, bool EXACT, bool TMCAP>
 static cudaError_t launch_resample_t(const ResampleParams &p, int n_groups, int n_ctas_y, cudaStream_t stream) {
   const size_t smem = resample_smem_bytes(BPP, CJ);
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(espb_resample_kernel<BPP, NST, CJ, EXACT, TM>,
+    cudaError_t e = cudaFuncSetAttribute(espb_resample_kernel<BPP, NST, CJ, EXACT, TMCAP>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
     if (e != cudaSuccess)
       return e;
     // two CTAs per SM need the full 228 KB carve-out (the default heuristic sizes it for one)
-    e = cudaFuncSetAttribute(espb_resample_kernel<BPP, NST, CJ, EXACT, TM>, cudaFuncAttributePreferredSharedMemoryCarveout,
+    e = cudaFuncSetAttribute(espb_resample_kernel<BPP, NST, CJ, EXACT, TMCAP>, cudaFuncAttributePreferredSharedMemoryCarveout,
                              (int) cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess)
       return e;
     configured = true;
     if (getenv("ESPB_DEBUG")) {
       int nb = 0;
-      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, espb_resample_kernel<BPP, NST, CJ, EXACT, TM>, BPP * 32, smem);
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, espb_resample_kernel<BPP, NST, CJ, EXACT, TMCAP>, BPP * 32, smem);
       cudaFuncAttributes fa;
-      cudaFuncGetAttributes(&fa, espb_resample_kernel<BPP, NST, CJ, EXACT, TM>);
+      cudaFuncGetAttributes(&fa, espb_resample_kernel<BPP, NST, CJ, EXACT, TMCAP>);
       fprintf(stderr, "[espb] resample<%d,%d,%d,%d,%d>: smem %zu B, %d regs, occupancy %d CTA/SM\n", BPP, NST, CJ,
-              (int) EXACT, (int) TM, smem, fa.numRegs, nb);
+              (int) EXACT, (int) TMCAP, smem, fa.numRegs, nb);
     }
   }
   dim3 grid(n_groups, n_ctas_y);
-  espb_resample_kernel<BPP, NST, CJ, EXACT, TM><<<grid, BPP * 32, smem, stream>>>(p);
+  espb_resample_kernel<BPP, NST, CJ, EXACT, TMCAP><<<grid, BPP * 32, smem, stream>>>(p);
   count_launch();
   return cudaGetLastError();
 }
@@ -834,7 +833,8 @@ cudaError_t launch_resample(const ResampleParams &p, int bpp, int chunk_rows, bo
   const int n_ctas_y = (n_passes + p.passes_per_cta - 1) / p.passes_per_cta;
   const bool tm = p.out_tm != nullptr;
   ResampleParams q = p;
-  q.out_vec = kOutVecNone;  // 128-bit stores when the caller's layout keeps a lane's results contiguous and aligned
+  q.out_vec = tm ? kOutVecTimeMajor : kOutVecNone;
+  // 128-bit stores when the caller's layout keeps a lane's results contiguous and aligned
   if (!tm && (uintptr_t) p.out % 16 == 0 && p.out_ss % 4 == 0) {
     if (p.out_fs == 1 && p.out_cs % 4 == 0)
       q.out_vec = kOutVecPlanar;
@@ -843,10 +843,12 @@ cudaError_t launch_resample(const ResampleParams &p, int bpp, int chunk_rows, bo
     else if (p.out_cs == 1 && p.out_fs == p.channels && p.channels % 4 == 0)
       q.out_vec = kOutVecFrame4;
   }
-#define ESPB_LAUNCH(BPP_, NST_, CJ_)                                                                   \
-  (exact ? (tm ? launch_resample_t<BPP_, NST_, CJ_, true, true>(q, n_groups, n_ctas_y, stream)         \
-               : launch_resample_t<BPP_, NST_, CJ_, true, false>(q, n_groups, n_ctas_y, stream))       \
-         : (tm ? launch_resample_t<BPP_, NST_, CJ_, false, true>(q, n_groups, n_ctas_y, stream)        \
+  // TMCAP: the variant that can also write time-major scratch (kept apart: folding that branch into the
+  // caller-layout variant costs it 1.4 % through register allocation)
+#define ESPB_LAUNCH(BPP_, NST_, CJ_)                                                               \
+  (exact ? (tm ? launch_resample_t<BPP_, NST_, CJ_, true, true>(q, n_groups, n_ctas_y, stream)     \
+               : launch_resample_t<BPP_, NST_, CJ_, true, false>(q, n_groups, n_ctas_y, stream))   \
+         : (tm ? launch_resample_t<BPP_, NST_, CJ_, false, true>(q, n_groups, n_ctas_y, stream)    \
                : launch_resample_t<BPP_, NST_, CJ_, false, false>(q, n_groups, n_ctas_y, stream)))
   if (bpp == 8 && chunk_rows == 32)
     return ESPB_LAUNCH(8, 3, 32);

@@ -253,6 +253,17 @@ int espb_plan_schedule(int numTaps, int numFilters, int flags, float outputOffse
 int espb_plan_policy(const EspbResamplerConfiguration *config, EspbBiquadCoefficients *coeffs, float *sample_ratio,
                      float *art_lowpass, int *art_flags);
 
+/* ---- dsp.h Q15 helpers: replace include/dsp.h:66-93 (portable C versions) ------------- */
+/* dsps_add_s16 (src/dsp/dsps_add_s16_ansi.c:10-27): out[i*step_out] = (int16)((in1[i*step1] + in2[i*step2]) >> shift),
+ * the sum taken in 32 bits, the shift arithmetic, the result truncated (not saturated) — the mixer step that
+ * follows float_to_quantized in ESPHome.  Device buffers; `len` may cover a whole batch (int64).  Returns ESPB_OK, or
+ * ESPB_ERR_ARG where the reference returns ESP_FAIL (a NULL buffer). */
+int espb_dsps_add_s16(const int16_t *input1, const int16_t *input2, int16_t *output, int64_t len, int step1,
+                      int step2, int step_out, int shift, void *stream);
+/* dsps_mulc_s16 (src/dsp/dsps_mulc_s16_ansi.c:18-31): out[i*step_out] = (int16)((in[i*step_in] * C) >> 15), Q15 volume. */
+int espb_dsps_mulc_s16(const int16_t *input, int16_t *output, int64_t len, int16_t C, int step_in, int step_out,
+                       void *stream);
+
 /* ---- batch utilities -------------------------------------------------------------- */
 /* Order-independent checksum of a float/byte buffer: wrapping 64-bit sum of the 32-bit
  * words (bytes for the u8 variant) — what each rank contributes to the NCCL gather. */
