@@ -133,6 +133,21 @@ def lib():
                                    C.POINTER(i), vp, vp, vp, vp]),
         "espb_plan_policy": (i, [C.POINTER(_Config), C.POINTER(_Coeffs), C.POINTER(f), C.POINTER(f), C.POINTER(i)]),
         "espb_checksum_u32": (i, [vp, u64, vp, vp]),
+        "espb_wav_decoder_create": (vp, []),
+        "espb_wav_decoder_free": (None, [vp]),
+        "espb_wav_decoder_decode_header": (i, [vp, vp, sz]),
+        "espb_wav_decoder_next": (i, [vp, vp]),
+        "espb_wav_decoder_reset": (None, [vp]),
+        "espb_wav_decoder_state": (i, [vp]),
+        "espb_wav_decoder_bytes_processed": (sz, [vp]),
+        "espb_wav_decoder_bytes_to_skip": (sz, [vp]),
+        "espb_wav_decoder_bytes_needed": (sz, [vp]),
+        "espb_wav_decoder_chunk_name": (vp, [vp]),  # 4 raw bytes (may hold NULs)
+        "espb_wav_decoder_chunk_bytes_left": (sz, [vp]),
+        "espb_wav_decoder_sample_rate": (u32, [vp]),
+        "espb_wav_decoder_num_channels": (C.c_uint16, [vp]),
+        "espb_wav_decoder_bits_per_sample": (C.c_uint16, [vp]),
+        "espb_wav_write_header": (sz, [vp, u32, C.c_uint16, C.c_uint16, u32]),
         "espb_dsps_add_s16": (i, [vp, vp, vp, i64, i, i, i, i, vp]),
         "espb_dsps_mulc_s16": (i, [vp, vp, i64, C.c_int16, i, i, vp]),
         "espb_measure_fp32_fma_peak": (i, [C.POINTER(C.c_double), C.POINTER(C.c_double)]),
@@ -507,6 +522,51 @@ def dsps_mulc_s16(a, n, c, step_in=1, step_out=1, out_init=None):
     d_a.free()
     d_o.free()
     return res, rc
+
+
+class WavDecoder:
+    """include/wav_decoder.h:54-89 over the C ABI (host only; works without a GPU)."""
+
+    def __init__(self):
+        self.h = lib().espb_wav_decoder_create()
+        if not self.h:
+            raise EspbError("espb_wav_decoder_create failed")
+
+    def decode_header(self, data):
+        buf = np.frombuffer(bytes(data), np.uint8) if len(data) else np.zeros(1, np.uint8)
+        return lib().espb_wav_decoder_decode_header(self.h, buf.ctypes.data, len(data))
+
+    def next(self, data):
+        buf = np.frombuffer(bytes(data) + b"\0" * 16, np.uint8)
+        return lib().espb_wav_decoder_next(self.h, buf.ctypes.data)
+
+    def reset(self):
+        lib().espb_wav_decoder_reset(self.h)
+
+    def snapshot(self):
+        L = lib()
+        return (L.espb_wav_decoder_state(self.h), L.espb_wav_decoder_bytes_processed(self.h),
+                L.espb_wav_decoder_bytes_needed(self.h), L.espb_wav_decoder_bytes_to_skip(self.h),
+                L.espb_wav_decoder_chunk_bytes_left(self.h), L.espb_wav_decoder_sample_rate(self.h),
+                L.espb_wav_decoder_num_channels(self.h), L.espb_wav_decoder_bits_per_sample(self.h),
+                C.string_at(L.espb_wav_decoder_chunk_name(self.h), 4))
+
+    def free(self):
+        if getattr(self, "h", None):
+            lib().espb_wav_decoder_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def wav_write_header(sample_rate, channels, bits, data_bytes):
+    out = np.zeros(44, np.uint8)
+    n = lib().espb_wav_write_header(out.ctypes.data, sample_rate, channels, bits, data_bytes)
+    return out[:n].tobytes()
 
 
 class _Q15Backend:

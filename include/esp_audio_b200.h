@@ -264,6 +264,43 @@ int espb_dsps_add_s16(const int16_t *input1, const int16_t *input2, int16_t *out
 int espb_dsps_mulc_s16(const int16_t *input, int16_t *output, int64_t len, int16_t C, int step_in, int step_out,
                        void *stream);
 
+/* ---- WAV header parse / emit: replaces include/wav_decoder.h:32-90 (host only) --------- */
+/* WAVDecoderState (include/wav_decoder.h:34-43) and WAVDecoderResult (:45-52), same values */
+#define ESPB_WAV_DECODER_BEFORE_RIFF 0
+#define ESPB_WAV_DECODER_BEFORE_WAVE 1
+#define ESPB_WAV_DECODER_BEFORE_FMT 2
+#define ESPB_WAV_DECODER_IN_FMT 3
+#define ESPB_WAV_DECODER_BEFORE_DATA 4
+#define ESPB_WAV_DECODER_IN_DATA 5
+#define ESPB_WAV_DECODER_SUCCESS_NEXT 0
+#define ESPB_WAV_DECODER_SUCCESS_IN_DATA 1
+#define ESPB_WAV_DECODER_WARNING_INCOMPLETE_DATA 2
+#define ESPB_WAV_DECODER_ERROR_NO_RIFF 3
+#define ESPB_WAV_DECODER_ERROR_NO_WAVE 4
+#define ESPB_WAV_DECODER_ERROR_FAILED 5
+typedef struct EspbWavDecoder EspbWavDecoder; /* class WAVDecoder (:54-89) */
+EspbWavDecoder *espb_wav_decoder_create(void);
+void espb_wav_decoder_free(EspbWavDecoder *d);
+/* WAVDecoder::decode_header (src/decode/wav_decoder.cpp:8-46): parse as much of the header as `buffer` holds;
+ * returns a result code; bytes_processed() says how far it got. */
+int espb_wav_decoder_decode_header(EspbWavDecoder *d, const uint8_t *buffer, size_t bytes_available);
+/* WAVDecoder::next (:48-149): one step — the caller skipped bytes_to_skip() and read bytes_needed() bytes */
+int espb_wav_decoder_next(EspbWavDecoder *d, const uint8_t *buffer);
+void espb_wav_decoder_reset(EspbWavDecoder *d); /* :151-161 (does not restore bytes_needed, like the reference) */
+int espb_wav_decoder_state(const EspbWavDecoder *d);
+size_t espb_wav_decoder_bytes_processed(const EspbWavDecoder *d);
+size_t espb_wav_decoder_bytes_to_skip(const EspbWavDecoder *d);
+size_t espb_wav_decoder_bytes_needed(const EspbWavDecoder *d);
+const char *espb_wav_decoder_chunk_name(const EspbWavDecoder *d); /* 4 characters + NUL */
+size_t espb_wav_decoder_chunk_bytes_left(const EspbWavDecoder *d);
+uint32_t espb_wav_decoder_sample_rate(const EspbWavDecoder *d);
+uint16_t espb_wav_decoder_num_channels(const EspbWavDecoder *d);
+uint16_t espb_wav_decoder_bits_per_sample(const EspbWavDecoder *d);
+/* canonical 44-byte PCM header (RIFF/WAVE/fmt /data) for `data_bytes` of samples; returns 44.  The reference
+ * only parses; this is the matching emitter for test and bench I/O. */
+size_t espb_wav_write_header(uint8_t *dst44, uint32_t sample_rate, uint16_t num_channels, uint16_t bits_per_sample,
+                             uint32_t data_bytes);
+
 /* ---- batch utilities -------------------------------------------------------------- */
 /* Order-independent checksum of a float/byte buffer: wrapping 64-bit sum of the 32-bit
  * words (bytes for the u8 variant) — what each rank contributes to the NCCL gather. */

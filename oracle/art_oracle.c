@@ -435,6 +435,141 @@ int orc_mulc_s16(const int16_t *in, int16_t *out, int len, int16_t c, int step_i
 }
 
 /* ------------------------------------------------------------------------- */
+/* WAV header parser — src/decode/wav_decoder.cpp                                */
+/* ------------------------------------------------------------------------- */
+
+/* include/wav_decoder.h:78-88 — member initialisers (bytes_processed_ has none) */
+void orc_wav_init(OrcWav *w) {
+  memset(w, 0, sizeof *w);
+  w->state = 0;
+  w->bytes_needed = 8;
+}
+
+/* wav_decoder.cpp:61-65 etc.: memcpy of a uint32 into a size_t member — only the low four bytes change — then the
+ * RIFF pad byte */
+static void wav_chunk_size(OrcWav *w, const uint8_t *p) {
+  uint32_t v;
+  memcpy(&v, p, 4);
+  memcpy(&w->chunk_bytes_left, &v, 4);
+  if (w->chunk_bytes_left % 2 != 0)
+    w->chunk_bytes_left++;
+}
+
+/* wav_decoder.cpp:48-149 */
+int orc_wav_next(OrcWav *w, const uint8_t *buffer) {
+  w->bytes_to_skip = 0;
+  switch (w->state) {
+    case 0: /* BEFORE_RIFF :52-68 */
+      memcpy(w->chunk_name, buffer, 4);
+      if (memcmp(w->chunk_name, "RIFF", 4) != 0)
+        return 3;
+      wav_chunk_size(w, buffer + 4);
+      w->state = 1;
+      w->bytes_needed = 4;
+      break;
+    case 1: /* BEFORE_WAVE :70-80 */
+      memcpy(w->chunk_name, buffer, 4);
+      if (memcmp(w->chunk_name, "WAVE", 4) != 0)
+        return 4;
+      w->state = 2;
+      w->bytes_needed = 8;
+      break;
+    case 2: /* BEFORE_FMT :82-100 */
+      memcpy(w->chunk_name, buffer, 4);
+      wav_chunk_size(w, buffer + 4);
+      if (memcmp(w->chunk_name, "fmt ", 4) == 0) {
+        w->state = 3;
+        w->bytes_needed = w->chunk_bytes_left;
+      } else {
+        w->bytes_to_skip = w->chunk_bytes_left;
+        w->bytes_needed = 8;
+      }
+      break;
+    case 3: /* IN_FMT :102-120 */
+      memcpy(&w->num_channels, buffer + 2, 2);
+      memcpy(&w->sample_rate, buffer + 4, 4);
+      memcpy(&w->bits_per_sample, buffer + 14, 2);
+      w->state = 4;
+      w->bytes_needed = 8;
+      break;
+    case 4: /* BEFORE_DATA :122-141 */
+      memcpy(w->chunk_name, buffer, 4);
+      wav_chunk_size(w, buffer + 4);
+      if (memcmp(w->chunk_name, "data", 4) == 0) {
+        w->state = 5;
+        w->bytes_needed = 0;
+        return 1;
+      }
+      w->bytes_to_skip = w->chunk_bytes_left;
+      w->bytes_needed = 8;
+      break;
+    default: /* IN_DATA :143-146 */
+      return 1;
+  }
+  return 0;
+}
+
+/* wav_decoder.cpp:8-46 */
+int orc_wav_decode_header(OrcWav *w, const uint8_t *buffer, size_t bytes_available) {
+  size_t to_skip = w->bytes_to_skip, to_read = w->bytes_needed;
+  w->bytes_processed = 0;
+  while (to_skip + to_read > 0) {
+    if (to_skip > bytes_available || to_read > bytes_available)
+      return 2;
+    if (to_skip > 0) {
+      buffer += to_skip;
+      w->bytes_processed += to_skip;
+      bytes_available -= to_skip;
+      to_skip = 0;
+    } else if (to_read > 0) {
+      int r = orc_wav_next(w, buffer);
+      buffer += to_read;
+      w->bytes_processed += to_read;
+      bytes_available -= to_read;
+      if (r == 1)
+        return r;
+      if (r != 0)
+        return r;
+      to_skip = w->bytes_to_skip;
+      to_read = w->bytes_needed;
+    }
+  }
+  return 5;
+}
+
+/* wav_decoder.cpp:151-161 — bytes_needed_ and bytes_processed_ are NOT restored */
+void orc_wav_reset(OrcWav *w) {
+  w->state = 0;
+  w->bytes_to_skip = 0;
+  memset(w->chunk_name, 0, sizeof w->chunk_name);
+  w->chunk_bytes_left = 0;
+  w->sample_rate = 0;
+  w->num_channels = 0;
+  w->bits_per_sample = 0;
+}
+
+void *orc_wav_create(void) {
+  OrcWav *w = (OrcWav *) malloc(sizeof *w);
+  if (w)
+    orc_wav_init(w);
+  return w;
+}
+void orc_wav_free(void *w) { free(w); }
+void orc_wav_snapshot(const void *p, uint64_t out[8], char name[5]) {
+  const OrcWav *w = (const OrcWav *) p;
+  out[0] = (uint64_t) w->state;
+  out[1] = w->bytes_processed;
+  out[2] = w->bytes_needed;
+  out[3] = w->bytes_to_skip;
+  out[4] = w->chunk_bytes_left;
+  out[5] = w->sample_rate;
+  out[6] = w->num_channels;
+  out[7] = w->bits_per_sample;
+  memcpy(name, w->chunk_name, 4);
+  name[4] = 0;
+}
+
+/* ------------------------------------------------------------------------- */
 /* Resampler wrapper — src/resample/resampler.cpp, include/resampler.h         */
 /* ------------------------------------------------------------------------- */
 

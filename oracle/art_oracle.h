@@ -73,6 +73,24 @@ int orc_add_s16(const int16_t *in1, const int16_t *in2, int16_t *out, int len, i
                 int shift);
 int orc_mulc_s16(const int16_t *in, int16_t *out, int len, int16_t c, int step_in, int step_out);
 
+/* include/wav_decoder.h:32-90, src/decode/wav_decoder.cpp — WAV header state machine.
+ * States 0..5 = WAV_DECODER_BEFORE_RIFF .. IN_DATA; results 0..5 = SUCCESS_NEXT .. ERROR_FAILED. */
+typedef struct {
+  int state;
+  size_t bytes_processed, bytes_needed, bytes_to_skip, chunk_bytes_left;
+  char chunk_name[5];
+  uint32_t sample_rate;
+  uint16_t num_channels, bits_per_sample;
+} OrcWav;
+void orc_wav_init(OrcWav *w);
+int orc_wav_next(OrcWav *w, const uint8_t *buffer);
+int orc_wav_decode_header(OrcWav *w, const uint8_t *buffer, size_t bytes_available);
+void orc_wav_reset(OrcWav *w);
+/* test-binding helpers: heap handle + snapshot {state, processed, needed, skip, chunk_left, rate, channels, bits} */
+void *orc_wav_create(void);
+void orc_wav_free(void *w);
+void orc_wav_snapshot(const void *w, uint64_t out[8], char name[5]);
+
 /* include/resampler.h:15-80 — pipeline policy + per-chunk composition */
 typedef struct OrcWrapper OrcWrapper;
 OrcWrapper *orc_wrapper_create(size_t in_samples, size_t out_samples, float src_rate, float dst_rate, int src_bits,

@@ -24,6 +24,7 @@
 #include "dsp.h"
 #include "quantization_utils.h"
 #include "resampler.h"
+#include "wav_decoder.h"
 
 using namespace esp_audio_libs;
 namespace art = esp_audio_libs::art_resampler;
@@ -96,6 +97,29 @@ int ref_add_s16(const int16_t *in1, const int16_t *in2, int16_t *out, int len, i
 }
 int ref_mulc_s16(const int16_t *in, int16_t *out, int len, int16_t c, int step_in, int step_out) {
   return dsps_mulc_s16_ansi(in, out, len, c, step_in, step_out);
+}
+
+// ---- wav_decoder::WAVDecoder --------------------------------------------------
+void *ref_wav_create(void) { return new esp_audio_libs::wav_decoder::WAVDecoder(); }
+void ref_wav_free(void *w) { delete (esp_audio_libs::wav_decoder::WAVDecoder *) w; }
+int ref_wav_next(void *w, const uint8_t *buffer) { return (int) ((esp_audio_libs::wav_decoder::WAVDecoder *) w)->next(buffer); }
+int ref_wav_decode_header(void *w, const uint8_t *buffer, size_t n) {
+  return (int) ((esp_audio_libs::wav_decoder::WAVDecoder *) w)->decode_header(buffer, n);
+}
+void ref_wav_reset(void *w) { ((esp_audio_libs::wav_decoder::WAVDecoder *) w)->reset(); }
+void ref_wav_snapshot(void *p, uint64_t out[8], char name[5]) {
+  esp_audio_libs::wav_decoder::WAVDecoder *w = (esp_audio_libs::wav_decoder::WAVDecoder *) p;
+  out[0] = (uint64_t) w->state();
+  out[1] = w->bytes_processed();
+  out[2] = w->bytes_needed();
+  out[3] = w->bytes_to_skip();
+  out[4] = w->chunk_bytes_left();
+  out[5] = w->sample_rate();
+  out[6] = w->num_channels();
+  out[7] = w->bits_per_sample();
+  std::string n = w->chunk_name();
+  memset(name, 0, 5);
+  memcpy(name, n.data(), n.size() < 4 ? n.size() : 4);
 }
 
 // ---- resampler::Resampler wrapper -----------------------------------------

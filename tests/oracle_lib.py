@@ -101,6 +101,10 @@ class _Backend:
         rc = self.f["mulc_s16"](a, out, n, c, step_in, step_out)
         return out, rc
 
+    # ---- WAV header parser ----
+    def wav(self):
+        return WavContext(self)
+
     def bench_resample(self, n_threads, channels, taps, filters, lowpass, flags, advance, x, n_out, ratio):
         """x: (n_streams, n_in*channels) float32.  Returns (seconds, frames_generated, out)."""
         x = np.ascontiguousarray(x, np.float32)
@@ -255,8 +259,51 @@ def _table(n):
     }
 
 
+class WavContext:
+    """WAVDecoder handle of a backend; snapshot() = (state, processed, needed, skip, chunk_left, rate, channels,
+    bits, chunk_name)."""
+
+    def __init__(self, backend):
+        self.L, self.pre = backend.lib, backend.prefix
+        g = lambda n: getattr(self.L, self.pre + "wav_" + n)  # noqa: E731
+        g("create").restype = _vp
+        g("create").argtypes = []
+        g("free").argtypes = [_vp]
+        g("next").restype = _i
+        g("next").argtypes = [_vp, _u8p]
+        g("decode_header").restype = _i
+        g("decode_header").argtypes = [_vp, _u8p, C.c_size_t]
+        g("reset").argtypes = [_vp]
+        g("snapshot").argtypes = [_vp, C.POINTER(C.c_uint64), C.c_char_p]
+        self.g = g
+        self.h = g("create")()
+
+    def decode_header(self, data):
+        buf = np.frombuffer(bytes(data), np.uint8) if len(data) else np.zeros(1, np.uint8)
+        return self.g("decode_header")(self.h, np.ascontiguousarray(buf), len(data))
+
+    def next(self, data):
+        return self.g("next")(self.h, np.frombuffer(bytes(data) + b"\0" * 16, np.uint8).copy())
+
+    def reset(self):
+        self.g("reset")(self.h)
+
+    def snapshot(self):
+        out = (C.c_uint64 * 8)()
+        name = C.create_string_buffer(5)
+        self.g("snapshot")(self.h, out, name)
+        return tuple(int(v) for v in out) + (name.raw[:4],)
+
+    def __del__(self):
+        try:
+            self.g("free")(self.h)
+        except Exception:
+            pass
+
+
 class Oracle(_Backend):
     name = "oracle-port"
+    prefix = "orc_"
 
     def __init__(self):
         if not os.path.exists(ORACLE_SO):
@@ -285,6 +332,7 @@ class Oracle(_Backend):
 
 class Reference(_Backend):
     name = "reference"
+    prefix = "ref_"
 
     def __init__(self):
         if not os.path.exists(REF_SO):
