@@ -133,6 +133,14 @@ def lib():
                                    C.POINTER(i), vp, vp, vp, vp]),
         "espb_plan_policy": (i, [C.POINTER(_Config), C.POINTER(_Coeffs), C.POINTER(f), C.POINTER(f), C.POINTER(i)]),
         "espb_checksum_u32": (i, [vp, u64, vp, vp]),
+        "espb_resampleGroupsInit": (vp, [i, C.POINTER(i), i, i, i, f, i]),
+        "espb_resampleGroupsFree": (None, [vp]),
+        "espb_resampleGroupsCount": (i, [vp]),
+        "espb_resampleGroupsFirstStream": (i, [vp, i]),
+        "espb_resampleGroupsContext": (vp, [vp, i]),
+        "espb_resampleGroupsSetMode": (i, [vp, i]),
+        "espb_resampleGroupsProcessInterleaved": (i, [vp, vp, i64, C.POINTER(i), vp, i64, C.POINTER(i), C.POINTER(f),
+                                                      C.POINTER(_Result), vp]),
         "espb_wav_decoder_create": (vp, []),
         "espb_wav_decoder_free": (None, [vp]),
         "espb_wav_decoder_decode_header": (i, [vp, vp, sz]),
@@ -412,6 +420,61 @@ class ResampleBatch:
         d_in.free()
         d_out.free()
         return y, int(r.input_used), int(r.output_generated)
+
+
+class ResampleGroups:
+    """Ratio groups (ASRC): one batch context per group of streams that share a clock."""
+
+    def __init__(self, streams_per_group, channels, taps, filters, lowpass_ratio, flags, mode=MODE_FAST):
+        self.sizes = [int(v) for v in streams_per_group]
+        arr = (C.c_int * len(self.sizes))(*self.sizes)
+        self.h = lib().espb_resampleGroupsInit(len(self.sizes), arr, channels, taps, filters, lowpass_ratio, flags)
+        if not self.h:
+            raise EspbError(f"espb_resampleGroupsInit returned NULL: {_err()}")
+        self.channels, self.num_streams = channels, sum(self.sizes)
+        _check(lib().espb_resampleGroupsSetMode(self.h, mode), "resampleGroupsSetMode")
+
+    def context(self, k):
+        return lib().espb_resampleGroupsContext(self.h, k)
+
+    def advance(self, k, delta):
+        lib().espb_resampleAdvancePosition(self.context(k), delta)
+
+    def state(self, k):
+        off, idx = C.c_float(0), C.c_int(0)
+        lib().espb_resampleGetState(self.context(k), C.byref(off), C.byref(idx))
+        return np.float32(off.value), int(idx.value)
+
+    def process_interleaved(self, x, n_in, n_out, ratios):
+        """x: (num_streams, row) float32 with row >= max(n_in)*channels; n_in / n_out / ratios: one entry per
+        group.  Returns (y (num_streams, max(n_out)*channels), [(used, generated)] per group)."""
+        x = np.ascontiguousarray(x, np.float32)
+        row = x.shape[1]
+        out_row = max(max(n_out), 1) * self.channels
+        d_in = DeviceBuffer.from_numpy(x if x.size else np.zeros(1, np.float32))
+        d_out = DeviceBuffer(self.num_streams * out_row * 4)
+        d_out.zero()
+        k = len(self.sizes)
+        res = (_Result * k)()
+        _check(lib().espb_resampleGroupsProcessInterleaved(
+            self.h, d_in.ptr, row, (C.c_int * k)(*[int(v) for v in n_in]), d_out.ptr, out_row,
+            (C.c_int * k)(*[int(v) for v in n_out]), (C.c_float * k)(*[float(v) for v in ratios]), res, None),
+            "resampleGroupsProcessInterleaved")
+        y = d_out.download(np.float32).reshape(self.num_streams, out_row)
+        d_in.free()
+        d_out.free()
+        return y, [(int(r.input_used), int(r.output_generated)) for r in res]
+
+    def free(self):
+        if getattr(self, "h", None):
+            lib().espb_resampleGroupsFree(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
 
 
 def biquad_lowpass(frequency):

@@ -135,6 +135,28 @@ EspbResampleResult espb_resampleProcessInterleavedHost(EspbResampleBatch *cxt, c
                                                        int64_t in_stream_stride, int numInputFrames, float *out,
                                                        int64_t out_stream_stride, int numOutputFrames, float ratio);
 
+/* ---- ratio groups: per-stream / time-varying ratios (ASRC) ------------------------------
+ * The reference takes `ratio` per call and per context (art_resampler.cpp:57-62), so streams may drift apart.
+ * Streams that share a clock (same ratio trajectory and chunking) form a group; a group set is one batch
+ * context per group, processed concurrently on internal CUDA streams forked from and joined to the caller's
+ * stream.  Group k's streams are rows [first_k, first_k + streams_per_group[k]) of the buffers, first_k being
+ * the running sum.  Each group keeps its own device-side history and position between calls. */
+typedef struct EspbResampleGroups EspbResampleGroups;
+EspbResampleGroups *espb_resampleGroupsInit(int num_groups, const int *streams_per_group, int numChannels, int numTaps,
+                                            int numFilters, float lowpassRatio, int flags);
+void espb_resampleGroupsFree(EspbResampleGroups *g);
+int espb_resampleGroupsCount(const EspbResampleGroups *g);
+int espb_resampleGroupsFirstStream(const EspbResampleGroups *g, int group);
+/* the group's batch context, for resampleAdvancePosition / Reset / GetPosition / GetRequiredSamples / ... */
+EspbResampleBatch *espb_resampleGroupsContext(EspbResampleGroups *g, int group);
+int espb_resampleGroupsSetMode(EspbResampleGroups *g, int mode);
+/* resampleProcessInterleaved for every group with its own frame counts and ratio (arrays of num_groups
+ * entries); results[k] is group k's {input_used, output_generated}.  Asynchronous on `stream`. */
+int espb_resampleGroupsProcessInterleaved(EspbResampleGroups *g, const float *in, int64_t in_stream_stride,
+                                          const int *numInputFrames, float *out, int64_t out_stream_stride,
+                                          const int *numOutputFrames, const float *ratios, EspbResampleResult *results,
+                                          void *stream);
+
 /* ---- art_biquad: replaces include/art_biquad.h:19-36 --------------------------- */
 typedef struct { /* include/art_biquad.h:19-21 */
   float a0, a1, a2, b1, b2;

@@ -476,3 +476,51 @@ def test_full_size_batch_properties(oracle):
         yo, _, _ = oo.process_interleaved(base[s], cap, ratio)
         assert np.max(np.abs(y[s, : gen * ch].astype(np.float64) - yo)) <= TOL
     assert np.all(y[:, gen * ch:] == 0)  # nothing written past the generated frames
+
+
+@pytest.mark.parametrize("mode", ["exact", "fast"])
+def test_ratio_groups_drifting_ratios_chunked(oracle, mode):
+    """per-group, per-call ratios (ASRC) with persistent device-side state.  Three groups of
+    streams follow three clocks; every call each group gets its own chunk sizes and a slightly different ratio.
+    Each stream is compared with its own reference-style context fed the same sequence of calls."""
+    ch, taps, filters, flags = 2, 64, 128, 3
+    sizes = [5, 130, 1]
+    base = [f32(48000) / f32(44100), f32(44100) / f32(48000) * f32(0.999), f32(2.0)]
+    g = espb.ResampleGroups(sizes, ch, taps, filters, 1.0, flags,
+                            mode=espb.MODE_EXACT if mode == "exact" else espb.MODE_FAST)
+    ns = sum(sizes)
+    group_of = np.repeat(np.arange(len(sizes)), sizes)
+    orc = [oracle.resampler(ch, taps, filters, 1.0, flags) for _ in range(ns)]
+    for k in range(len(sizes)):
+        g.advance(k, taps / 2)
+    for o in orc:
+        o.advance(taps / 2)
+    rng = np.random.default_rng(42)
+    total = 2600
+    x = np.stack([noise(total, ch, stream=300 + s, amp=0.7) for s in range(ns)])
+    pos = [0] * len(sizes)
+    worst = 0.0
+    for call in range(9):
+        n_in = [int(min(rng.integers(0, 400), total - pos[k])) for k in range(len(sizes))]
+        n_out = [int(rng.integers(0, 700)) for _ in sizes]
+        ratios = [f32(base[k] * f32(1.0 + 2e-4 * np.sin(call + k))) for k in range(len(sizes))]
+        row = max(max(n_in), 1) * ch
+        xin = np.zeros((ns, row), f32)
+        for s in range(ns):
+            k = group_of[s]
+            xin[s, : n_in[k] * ch] = x[s, pos[k] * ch:(pos[k] + n_in[k]) * ch]
+        y, res = g.process_interleaved(xin, n_in, n_out, ratios)
+        for s in range(ns):
+            k = group_of[s]
+            yo, uo, go = orc[s].process_interleaved(xin[s, : n_in[k] * ch], n_out[k], ratios[k], n_in=n_in[k])
+            assert res[k] == (uo, go), (call, s, res[k], uo, go)
+            got = y[s, : go * ch]
+            if mode == "exact":
+                assert bits_equal(got, yo), (call, s)
+            elif go:
+                worst = max(worst, float(np.max(np.abs(got.astype(np.float64) - yo))))
+        for k in range(len(sizes)):
+            pos[k] += res[k][0]
+            assert g.state(k) == orc[int(np.argmax(group_of == k))].state()
+    assert worst <= 1e-6  # fast mode: the north star's tolerance (max-abs, full scale)
+    g.free()
