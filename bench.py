@@ -255,6 +255,7 @@ def main():
     # ---- FP32 FMA peak of this device, measured now (roofline denominator)
     fma_tflops, fma_clock = espb.measure_fp32_fma_peak()  # best of the scalar FFMA and packed FFMA2 probes
     fma_scalar, fma_packed = espb.measure_fp32_fma_peak2()
+    tile_tf = espb.measure_fp32_tile_pattern()
 
     ctx = espb.ResampleBatch(ns, CHANNELS, TAPS, FILTERS, 1.0, FLAGS, mode=espb.MODE_FAST)
     ctx.set_option(espb.OPT_PLAN_CACHE, 0)  # every step re-plans: schedule, upload and expansion are timed
@@ -333,12 +334,16 @@ def main():
     except Exception:
         pass
     roofline = {
-        "kernel": "espb_resample_kernel<4,2,false,false>", "bound": "fp32_fma", "achieved": achieved_tf,
+        "kernel": "espb_resample_kernel<BPP=4,STAGES=2,CHUNK_ROWS=32,EXACT=false,TMCAP=false>", "bound": "fp32_fma", "achieved": achieved_tf,
         "peak": fma_tflops, "unit": "TFLOP/s", "frac": achieved_tf / fma_tflops if fma_tflops else None,
         "peak_source": "FMA-only probes (espb_measure_fp32_fma_peak: best of scalar FFMA and packed FFMA2) on this "
                        "GPU in this run; nominal 148 SM x 128 lanes x 2 x 1.965 GHz = 74.4",
         "peak_probe_ffma_tflops": fma_scalar, "peak_probe_ffma2_tflops": fma_packed,
         "peak_implied_sm_mhz": fma_clock,
+        # the kernel's inner loop alone (register tile fed from shared memory at the kernel's occupancy; no TMA,
+        # barriers or epilogue): the practical ceiling of this loop structure, for reading `frac`
+        "inner_loop_probe_tflops": tile_tf,
+        "frac_of_inner_loop_probe": achieved_tf / tile_tf if tile_tf else None,
         "traffic": (traffic or {}).get("dram_bytes_per_launch") if ns == STREAMS_PER_GPU else None,
         "traffic_source": (traffic or {}).get("source"),
         "algorithmic_bytes_per_launch": bytes_per_launch,

@@ -160,6 +160,7 @@ def lib():
         "espb_dsps_mulc_s16": (i, [vp, vp, i64, C.c_int16, i, i, vp]),
         "espb_measure_fp32_fma_peak": (i, [C.POINTER(C.c_double), C.POINTER(C.c_double)]),
         "espb_measure_fp32_fma_peak2": (i, [C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+        "espb_measure_fp32_tile_pattern": (i, [C.POINTER(C.c_double)]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -232,6 +233,12 @@ def plan_policy(src_rate, dst_rate, src_bits, dst_bits, channels, use_filter, in
     return dict(filter={0: "none", 1: "pre", 2: "post"}[kind],
                 coeffs=np.array([c.a0, c.a1, c.a2, c.b1, c.b2], np.float32), sample_ratio=np.float32(ratio.value),
                 art_lowpass=np.float32(lp.value), art_flags=int(flags.value))
+
+
+def measure_fp32_tile_pattern():
+    tf = C.c_double(0)
+    _check(lib().espb_measure_fp32_tile_pattern(C.byref(tf)), "measure_fp32_tile_pattern")
+    return tf.value
 
 
 def measure_fp32_fma_peak2():

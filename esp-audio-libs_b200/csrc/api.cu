@@ -1298,6 +1298,13 @@ int espb_measure_fp32_fma_peak(double *tflops, double *sm_clock_mhz_estimate) {
   return ESPB_OK;
 }
 
+int espb_measure_fp32_tile_pattern(double *tflops) {
+  if (!tflops)
+    return fail(ESPB_ERR_ARG, "measure_fp32_tile_pattern: NULL");
+  CU_TRY(run_tile_probe(tflops), "tile probe");
+  return ESPB_OK;
+}
+
 int espb_measure_fp32_fma_peak2(double *tflops_scalar_ffma, double *tflops_packed_ffma2) {
   double top = 0.0;
   CU_TRY(run_fma_probe(&top, nullptr, tflops_scalar_ffma, tflops_packed_ffma2), "fma probe");

@@ -82,6 +82,7 @@ cudaError_t launch_mulc_s16(const int16_t *a, int16_t *out, uint64_t n, int16_t 
 
 // utilities
 cudaError_t launch_checksum(const uint32_t *words, uint64_t n, unsigned long long *sum_dev, cudaStream_t stream);
+cudaError_t run_tile_probe(double *tflops);
 cudaError_t run_fma_probe(double *tflops, double *clock_mhz, double *tflops_scalar, double *tflops_packed);
 
 }  // namespace espb

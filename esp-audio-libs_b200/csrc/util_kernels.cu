@@ -66,7 +66,99 @@ __global__ void __launch_bounds__(256) espb_fma2_probe_kernel(float *out, float 
   out[(size_t) blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+// The resampler's inner loop on its own: a 4 series x 8 outputs x 2 filters register tile fed from shared memory by
+// one per-lane and four warp-uniform 128-bit loads per input row (32 FFMA2 per row), at the kernel's occupancy
+// (four 128-thread CTAs of <= 128 registers per SM) — no TMA, no barriers, no epilogue.  What this reaches is the
+// practical ceiling of that loop; the distance from it to the FMA-only probes is the cost of the operand pattern
+// and of running 4 warps per sub-partition.
+constexpr int kTileRows = 32, kTileBpp = 4;
+__global__ void __launch_bounds__(128, 4) espb_tile_probe_kernel(float *out, int iters, float seed) {
+  extern __shared__ __align__(128) float tile_smem[];
+  float *gs = tile_smem;                                // [rows][bpp][16]
+  float *xs = tile_smem + kTileRows * kTileBpp * 16;    // [rows][128]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < kTileRows * kTileBpp * 16 + kTileRows * 128; i += blockDim.x)
+    tile_smem[i] = seed * (float) (i % 7) * 1e-3f;
+  __syncthreads();
+  float2 acc[4][8];
+#pragma unroll
+  for (int e = 0; e < 4; ++e)
+#pragma unroll
+    for (int n = 0; n < 8; ++n)
+      acc[e][n] = make_float2(0.f, 0.f);
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll 1
+    for (int jb = 0; jb < kTileRows / 4; ++jb) {
+      const float *xb = xs + lane * 4 + jb * 4 * 128;
+      const float *gb = gs + warp * 16 + jb * 4 * kTileBpp * 16;
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) {
+        const float4 xv = *reinterpret_cast<const float4 *>(xb + jj * 128);
+        const float4 *gp = reinterpret_cast<const float4 *>(gb + jj * kTileBpp * 16);
+        const float4 g0 = gp[0], g1 = gp[1], g2 = gp[2], g3 = gp[3];
+        const float x4[4] = {xv.x, xv.y, xv.z, xv.w};
+        const float2 gg[8] = {make_float2(g0.x, g0.y), make_float2(g0.z, g0.w), make_float2(g1.x, g1.y),
+                              make_float2(g1.z, g1.w), make_float2(g2.x, g2.y), make_float2(g2.z, g2.w),
+                              make_float2(g3.x, g3.y), make_float2(g3.z, g3.w)};
+#pragma unroll
+        for (int n = 0; n < 8; ++n)
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            acc[e][n] = __ffma2_rn(gg[n], make_float2(x4[e], x4[e]), acc[e][n]);
+      }
+    }
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int e = 0; e < 4; ++e)
+#pragma unroll
+    for (int n = 0; n < 8; ++n)
+      s += acc[e][n].x + acc[e][n].y;
+  out[(size_t) blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 }  // namespace
+
+cudaError_t run_tile_probe(double *tflops) {
+  int dev = 0, sms = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess)
+    return e;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int blocks = sms * 4 * 8, iters = 200;
+  const size_t smem = (size_t) (kTileRows * kTileBpp * 16 + kTileRows * 128) * sizeof(float) * 2;  // the 2-stage ring
+  e = cudaFuncSetAttribute(espb_tile_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(espb_tile_probe_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                             (int) cudaSharedmemCarveoutMaxShared);
+  float *out = nullptr;
+  if (e == cudaSuccess)
+    e = cudaMalloc(&out, (size_t) blocks * 128 * sizeof(float));
+  if (e != cudaSuccess)
+    return e;
+  cudaEvent_t t0, t1;
+  cudaEventCreate(&t0);
+  cudaEventCreate(&t1);
+  double best = 0.0;
+  for (int rep = 0; rep < 5 && e == cudaSuccess; ++rep) {  // first two are warm-up
+    cudaEventRecord(t0, 0);
+    espb_tile_probe_kernel<<<blocks, 128, smem>>>(out, iters, 1e-3f);
+    count_launch();
+    cudaEventRecord(t1, 0);
+    e = cudaEventSynchronize(t1);
+    float ms = 0.0f;
+    cudaEventElapsedTime(&ms, t0, t1);
+    const double flop = 4.0 * 32.0 * 32.0 * kTileRows * (double) iters * blocks * 4.0;  // 32 FFMA2 x 32 lanes x 4 flop
+    if (e == cudaSuccess && rep >= 2 && flop / (ms * 1e-3) / 1e12 > best)
+      best = flop / (ms * 1e-3) / 1e12;
+  }
+  cudaEventDestroy(t0);
+  cudaEventDestroy(t1);
+  cudaFree(out);
+  if (e == cudaSuccess)
+    *tflops = best;
+  return e != cudaSuccess ? e : cudaGetLastError();
+}
 
 cudaError_t launch_checksum(const uint32_t *words, uint64_t n, unsigned long long *sum_dev, cudaStream_t stream) {
   if (n == 0)

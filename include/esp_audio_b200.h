@@ -332,6 +332,9 @@ int espb_measure_fp32_fma_peak(double *tflops, double *sm_clock_mhz_estimate);
 /* the two probes separately: scalar FFMA and packed FFMA2 (fma.rn.f32x2); espb_measure_fp32_fma_peak returns the
  * larger */
 int espb_measure_fp32_fma_peak2(double *tflops_scalar_ffma, double *tflops_packed_ffma2);
+/* the resampler's inner loop alone (register tile fed from shared memory, the kernel's occupancy, no TMA /
+ * barriers / epilogue): the practical ceiling of that loop, reported next to the FMA-only peak */
+int espb_measure_fp32_tile_pattern(double *tflops);
 
 #ifdef __cplusplus
 }

@@ -80,8 +80,44 @@ def run_wrapper(name, ns, ch, src, dst, sb, db, taps, filters, frames, mode=espb
     r.free()
 
 
+def run_streaming(ns, ch, frames, calls=200):
+    """Real-time use: small chunks (10 ms) through the float resampler, state carried on the device from call to
+    call; every call has a new fractional position, so nothing is reused from the plan cache.  Host wall clock per
+    call (schedule + uploads + launches) next to the device time."""
+    taps = filters = 256
+    ratio = f32(48000) / f32(44100)
+    b = espb.ResampleBatch(ns, ch, taps, filters, 1.0, 3)
+    b.advance(taps / 2)
+    cap = int(frames * float(ratio)) + 8
+    x = np.random.default_rng(2).uniform(-0.5, 0.5, (ns, frames * ch)).astype(f32)
+    d_in, d_out = espb.DeviceBuffer.from_numpy(x), espb.DeviceBuffer(ns * cap * ch * 4)
+    for _ in range(20):
+        b.process_interleaved_dev(d_in.ptr, frames * ch, frames, d_out.ptr, cap * ch, cap, ratio)
+    L.espb_device_sync()
+    ev0, ev1 = L.espb_event_create(), L.espb_event_create()
+    L.espb_event_record(ev0, None)
+    t0 = time.perf_counter()
+    gen = 0
+    for _ in range(calls):
+        gen += b.process_interleaved_dev(d_in.ptr, frames * ch, frames, d_out.ptr, cap * ch, cap, ratio)[1]
+    t_host = time.perf_counter() - t0
+    L.espb_event_record(ev1, None)
+    ms = espb.capi.C.c_float(0)
+    L.espb_event_elapsed_ms(ev0, ev1, espb.capi.C.byref(ms))
+    print(json.dumps(dict(config=f"streaming {ns} x {ch}ch float, 44.1->48 kHz, {frames}-frame chunks", calls=calls,
+                          host_us_per_call=t_host / calls * 1e6, device_us_per_call=ms.value / calls * 1e3,
+                          msamples_per_s=gen * ch * ns / ms.value / 1e3,
+                          realtime_factor=(frames / 44100.0) / (ms.value / calls / 1e3))), flush=True)
+    b.free()
+
+
 def main():
     which = [a for a in sys.argv[1:] if not a.startswith("--")] or ["c3", "c4", "c5"]
+    if "stream" in which:
+        espb.set_device(0)
+        run_streaming(1024, 2, 441)
+        run_streaming(4096, 2, 441)
+        run_streaming(64, 2, 441)
     scale = 1.0
     if "--scale" in sys.argv:
         scale = float(sys.argv[sys.argv.index("--scale") + 1])
