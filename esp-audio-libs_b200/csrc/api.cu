@@ -301,7 +301,7 @@ struct EspbResampleBatch {
   ArtState state{};
   int mode = ESPB_MODE_FAST;
   int bpp = 8;  // output blocks (warps) per pass
-  int chunk_rows = kChunkRows;  // input rows per pipeline stage (32, or 16 with twice the stages)
+  int chunk_rows = 32;  // input rows per pipeline stage (kernel variants: 32 default; 16, 24, 36 selectable)
   std::vector<float> bank_host;
   DevBuf bank;
   // time-major input staging xt[group][row][128]: rows [0, taps) = frames carried over from the
@@ -437,8 +437,8 @@ int pick_passes_per_cta(const EspbResampleBatch *c, int n_series, int pass_first
     if (n > max_chunks)
       max_chunks = n;
   }
-  if (ppc * max_chunks > max_chunks_per_cta(c->bpp))
-    ppc = max_chunks_per_cta(c->bpp) / max_chunks;
+  if (ppc * max_chunks > max_chunks_per_cta(c->bpp, c->chunk_rows))
+    ppc = max_chunks_per_cta(c->bpp, c->chunk_rows) / max_chunks;
   if (ppc < 1)
     ppc = 1;  // a single pass longer than the table cannot happen: taps <= 1024 gives <= 40 chunks per pass
   return (int) ppc;
@@ -716,7 +716,10 @@ EspbResampleBatch *espb_resampleInit(int num_streams, int numChannels, int numTa
   // 4 output blocks (warps) per pass, four CTAs per SM: measured 5 % faster than 8 x 2 at C2 (shorter passes
   // leave less idle time at the pass edges); ESPB_BPP=8 selects the other variant
   c->bpp = env_long("ESPB_BPP", 4) == 8 ? 8 : 4;
-  c->chunk_rows = env_long("ESPB_CHUNK_ROWS", 32) == 16 ? 16 : 32;
+  {
+    const long cr = env_long("ESPB_CHUNK_ROWS", 32);
+    c->chunk_rows = (cr == 16 || ((cr == 24 || cr == 36) && c->bpp == 4)) ? (int) cr : 32;
+  }
   long gb = env_long("ESPB_G_MBYTES", 0);
   if (gb > 0)
     c->g_budget_bytes = (size_t) gb << 20;

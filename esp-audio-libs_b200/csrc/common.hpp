@@ -6,7 +6,7 @@ namespace espb {
 
 // Tile geometry of the resampler kernel (see DESIGN.md "Resampler kernel").
 constexpr int kOutputsPerBlock = 8;   // NB: outputs accumulated per thread
-constexpr int kChunkRows = 32;        // most input frames staged per pipeline stage (the kernel variants use 32 or 16)
+constexpr int kChunkRows = 40;        // most input frames staged per pipeline stage (the kernel variants use 32 or 16)
 constexpr int kSeriesPerRow = 128;    // series (stream x channel) per warp row: 32 lanes x 4
 constexpr int kGRowFloats = 2 * kOutputsPerBlock;  // 16 coefficients per (row, output block)
 // chunk-table entries a CTA caches in shared memory (fewer for the 4-warp variant: four CTAs share an SM)
@@ -15,7 +15,10 @@ constexpr int kGRowFloats = 2 * kOutputsPerBlock;  // 16 coefficients per (row, 
 #else
 #define ESPB_HD
 #endif
-ESPB_HD constexpr int max_chunks_per_cta(int bpp) { return bpp == 8 ? 768 : 320; }
+// (the 24-row, 3-stage variant of the 4-warp kernel leaves only ~1.4 KB for tables next to its ring)
+ESPB_HD constexpr int max_chunks_per_cta(int bpp, int chunk_rows) {
+  return bpp == 8 ? 768 : (chunk_rows == 24 || chunk_rows == 36 ? 120 : 320);
+}
 constexpr int kMaxPassesPerCta = 64;
 
 // What the reference does for one output sample (art_resampler.cpp:421-451).

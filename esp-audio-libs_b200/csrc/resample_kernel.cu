@@ -375,7 +375,7 @@ template <int BPP, int NST, int CJ, bool EXACT, bool TMCAP>
 __global__ void __launch_bounds__(BPP * 32, 16 / BPP) espb_resample_kernel(const ResampleParams p) {
   constexpr int NTHREADS = BPP * 32;
   constexpr int STAGES = NST;
-  constexpr int MAXC = max_chunks_per_cta(BPP);
+  constexpr int MAXC = max_chunks_per_cta(BPP, CJ);
   static_assert(kMaxPassesPerCta * BPP * sizeof(int2) <= (size_t) NST * CJ * SGN * sizeof(float), "set-up table");
   constexpr int XS_STAGE = CJ * SGN;                // floats
   constexpr int GS_STAGE = CJ * BPP * kGRowFloats;  // floats
@@ -640,12 +640,12 @@ __global__ void __launch_bounds__(BPP * 32, 16 / BPP) espb_resample_kernel(const
 // ---------------------------------------------------------------------------------
 // launchers
 // ---------------------------------------------------------------------------------
-int resample_stages(int bpp, int CJ) { return (bpp == 8 ? 3 : 2) * (kChunkRows / CJ); }
+int resample_stages(int bpp, int CJ) { return CJ == 24 ? 3 : (CJ == 36 ? 2 : (bpp == 8 ? 3 : 2) * (32 / CJ)); }
 
 size_t resample_smem_bytes(int bpp, int CJ) {
   const int stages = resample_stages(bpp, CJ);
   return (size_t) stages * (CJ * bpp * kGRowFloats + CJ * SGN) * sizeof(float) + stages * sizeof(uint64_t) +
-         stages * sizeof(uint64_t) + max_chunks_per_cta(bpp) * (sizeof(int32_t) + bpp * sizeof(uint16_t)) +
+         stages * sizeof(uint64_t) + max_chunks_per_cta(bpp, CJ) * (sizeof(int32_t) + bpp * sizeof(uint16_t)) +
          (size_t) bpp * NB * sizeof(OutEntry) + 4 * sizeof(int32_t);
 }
 
@@ -858,6 +858,10 @@ cudaError_t launch_resample(const ResampleParams &p, int bpp, int chunk_rows, bo
     return ESPB_LAUNCH(8, 6, 16);
   if (bpp == 4 && chunk_rows == 16)
     return ESPB_LAUNCH(4, 4, 16);
+  if (bpp == 4 && chunk_rows == 24)
+    return ESPB_LAUNCH(4, 3, 24);
+  if (bpp == 4 && chunk_rows == 36)
+    return ESPB_LAUNCH(4, 2, 36);
 #undef ESPB_LAUNCH
   return cudaErrorInvalidValue;
 }
