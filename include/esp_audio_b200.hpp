@@ -11,6 +11,7 @@
 
 #include <cstddef>
 #include <cstdint>
+#include <string>
 
 #include "esp_audio_b200.h"
 
@@ -131,4 +132,64 @@ class Resampler {
 };
 
 }  // namespace resampler
+namespace wav_decoder {
+
+// include/wav_decoder.h:34-52 — same enumerators, same values
+enum WAVDecoderState {
+  WAV_DECODER_BEFORE_RIFF = ESPB_WAV_DECODER_BEFORE_RIFF,
+  WAV_DECODER_BEFORE_WAVE = ESPB_WAV_DECODER_BEFORE_WAVE,
+  WAV_DECODER_BEFORE_FMT = ESPB_WAV_DECODER_BEFORE_FMT,
+  WAV_DECODER_IN_FMT = ESPB_WAV_DECODER_IN_FMT,
+  WAV_DECODER_BEFORE_DATA = ESPB_WAV_DECODER_BEFORE_DATA,
+  WAV_DECODER_IN_DATA = ESPB_WAV_DECODER_IN_DATA,
+};
+enum WAVDecoderResult {
+  WAV_DECODER_SUCCESS_NEXT = ESPB_WAV_DECODER_SUCCESS_NEXT,
+  WAV_DECODER_SUCCESS_IN_DATA = ESPB_WAV_DECODER_SUCCESS_IN_DATA,
+  WAV_DECODER_WARNING_INCOMPLETE_DATA = ESPB_WAV_DECODER_WARNING_INCOMPLETE_DATA,
+  WAV_DECODER_ERROR_NO_RIFF = ESPB_WAV_DECODER_ERROR_NO_RIFF,
+  WAV_DECODER_ERROR_NO_WAVE = ESPB_WAV_DECODER_ERROR_NO_WAVE,
+  WAV_DECODER_ERROR_FAILED = ESPB_WAV_DECODER_ERROR_FAILED,
+};
+
+// include/wav_decoder.h:54-89 (host code; no device involved)
+class WAVDecoder {
+ public:
+  WAVDecoder() : impl_(espb_wav_decoder_create()) {}
+  ~WAVDecoder() { espb_wav_decoder_free(impl_); }
+  WAVDecoder(const WAVDecoder &) = delete;
+  WAVDecoder &operator=(const WAVDecoder &) = delete;
+
+  WAVDecoderState state() { return (WAVDecoderState) espb_wav_decoder_state(impl_); }
+  std::size_t bytes_processed() { return espb_wav_decoder_bytes_processed(impl_); }
+  std::size_t bytes_to_skip() { return espb_wav_decoder_bytes_to_skip(impl_); }
+  std::size_t bytes_needed() { return espb_wav_decoder_bytes_needed(impl_); }
+  std::string chunk_name() { return std::string(espb_wav_decoder_chunk_name(impl_), 4); }
+  std::size_t chunk_bytes_left() { return espb_wav_decoder_chunk_bytes_left(impl_); }
+  uint32_t sample_rate() { return espb_wav_decoder_sample_rate(impl_); }
+  uint16_t num_channels() { return espb_wav_decoder_num_channels(impl_); }
+  uint16_t bits_per_sample() { return espb_wav_decoder_bits_per_sample(impl_); }
+
+  WAVDecoderResult decode_header(const uint8_t *buffer, size_t bytes_available) {
+    return (WAVDecoderResult) espb_wav_decoder_decode_header(impl_, buffer, bytes_available);
+  }
+  WAVDecoderResult next(const uint8_t *buffer) { return (WAVDecoderResult) espb_wav_decoder_next(impl_, buffer); }
+  void reset() { espb_wav_decoder_reset(impl_); }
+
+ protected:
+  EspbWavDecoder *impl_;
+};
+
+}  // namespace wav_decoder
+
+// include/dsp.h:66-93,109-115 — the portable-C Q15 helpers on device buffers; 0 = ESP_OK, -1 = ESP_FAIL
+inline int dsps_add_s16(const int16_t *input1, const int16_t *input2, int16_t *output, int64_t len, int step1,
+                        int step2, int step_out, int shift, void *stream = nullptr) {
+  return espb_dsps_add_s16(input1, input2, output, len, step1, step2, step_out, shift, stream) == ESPB_OK ? 0 : -1;
+}
+inline int dsps_mulc_s16(const int16_t *input, int16_t *output, int64_t len, int16_t C, int step_in, int step_out,
+                         void *stream = nullptr) {
+  return espb_dsps_mulc_s16(input, output, len, C, step_in, step_out, stream) == ESPB_OK ? 0 : -1;
+}
+
 }  // namespace esp_audio_libs_b200

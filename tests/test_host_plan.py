@@ -181,6 +181,12 @@ def test_cpp_shim_compiles_and_links(tmp_path):
                    "namespace b = esp_audio_libs_b200;\n"
                    "int main() { b::resampler::Resampler r(4, 1024, 4096); (void) r;\n"
                    "  b::art_resampler::BiquadCoefficients c; b::art_resampler::biquad_lowpass(&c, 0.2274);\n"
+                   "  unsigned char h[44]; espb_wav_write_header(h, 48000, 2, 16, 960);\n"
+                   "  b::wav_decoder::WAVDecoder d;\n"
+                   "  if (d.decode_header(h, 44) != b::wav_decoder::WAV_DECODER_SUCCESS_IN_DATA) return 2;\n"
+                   "  if (d.sample_rate() != 48000 || d.num_channels() != 2 || d.bits_per_sample() != 16 ||\n"
+                   "      d.chunk_name() != \"data\" || d.chunk_bytes_left() != 960 || d.bytes_processed() != 44) return 3;\n"
+                   "  if (b::dsps_add_s16(nullptr, nullptr, nullptr, 4, 1, 1, 1, 0) != -1) return 4;\n"
                    "  return (espb_abi_version() == ESPB_ABI_VERSION && c.a0 > 0.25f && c.a0 < 0.26f) ? 0 : 1; }\n")
     exe = tmp_path / "shim"
     libdir = os.path.dirname(espb.library_path())
