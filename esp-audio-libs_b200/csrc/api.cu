@@ -222,10 +222,10 @@ inline cudaError_t copy_rows_async(void *dst, size_t dpitch, const void *src, si
 
 struct ScheduleKey {
   uint32_t offset_bits = 0, ratio_bits = 0;
-  int index = -1, n_in = -1, n_out = -1;
+  int index = -1, n_in = -1, n_out = -1, split = 0;
   bool operator==(const ScheduleKey &o) const {
     return offset_bits == o.offset_bits && ratio_bits == o.ratio_bits && index == o.index && n_in == o.n_in &&
-           n_out == o.n_out;
+           n_out == o.n_out && split == o.split;
   }
 };
 
@@ -325,6 +325,9 @@ struct EspbResampleBatch {
   // device staging + CUDA streams of the host-buffer entry point
   DevBuf stage_in, stage_out;
   HostPipe pipe;
+  // direct input (interleaved stereo float, see espb_resample_kernel<..., DIRECT>): decided per call
+  bool direct_ok = false;    // ESPB_DIRECT=1 switches it on
+  bool direct_call = false;  // this call's plan is split at input frame 0 and its input is read through TMA
   // options
   bool plan_cache = true;   // reuse schedule / tables / G when a call repeats (state, n_in, n_out, ratio)
   bool kernel_timing = false;
@@ -341,28 +344,36 @@ namespace {
 int ensure_xt(EspbResampleBatch *c, int64_t rows);
 
 // Build (or reuse) the schedule + pass plan for this call and upload the tables.
-int prepare_call(EspbResampleBatch *c, int n_in, int n_out, float ratio, cudaStream_t stream) {
+int prepare_call(EspbResampleBatch *c, int n_in, int n_out, float ratio, cudaStream_t stream,
+                 bool want_direct = false) {
   if (c->state_event_pending) {  // order this call after an asynchronous reset issued on another stream
     CU_TRY(cudaStreamWaitEvent(stream, c->state_event, 0), "cudaStreamWaitEvent");
     c->state_event_pending = false;
   }
-  {
-    int rc = ensure_xt(c, (int64_t) c->geo.taps + n_in + kChunkRows);
-    if (rc != ESPB_OK)
-      return rc;
-  }
+  // direct input needs the default kernel geometry and a carry that lies inside this call's input
+  want_direct = want_direct && c->direct_ok && c->bpp == 4 && c->chunk_rows == 32 && n_in >= c->geo.taps;
   ScheduleKey k;
   k.offset_bits = f2u(c->state.offset);
   k.ratio_bits = f2u(ratio);
   k.index = c->state.index;
   k.n_in = n_in;
   k.n_out = n_out;
-  if (c->plan_cache && c->plan_on_device && k == c->key)
-    return ESPB_OK;
+  k.split = want_direct ? 1 : 0;
+  if (c->plan_cache && c->plan_on_device && k == c->key && c->direct_call == want_direct) {
+    int rc = ensure_xt(c, (int64_t) c->geo.taps + (c->direct_call ? 0 : n_in) + kChunkRows);
+    return rc;
+  }
   c->plan_on_device = false;
   c->g_resident_first = c->g_resident_end = -1;
   build_schedule(c->geo, c->state, n_in, n_out, ratio, c->sched, /*finalize=*/false);  // pass 2 runs on the device
-  build_pass_plan(c->sched, c->geo.taps, c->bpp, c->chunk_rows, c->plan);
+  c->direct_call = want_direct && (int) c->sched.used >= c->geo.taps;
+  k.split = c->direct_call ? 1 : 0;
+  {
+    int rc = ensure_xt(c, (int64_t) c->geo.taps + (c->direct_call ? 0 : n_in) + kChunkRows);
+    if (rc != ESPB_OK)
+      return rc;
+  }
+  build_pass_plan(c->sched, c->geo.taps, c->bpp, c->chunk_rows, c->plan, c->direct_call);
   c->key = k;
   if (c->sched.generated == 0) {
     c->plan_on_device = true;
@@ -407,7 +418,7 @@ int ensure_g(EspbResampleBatch *c, int chunk_first, int chunk_end, cudaStream_t 
   CU_TRY(c->d_G.reserve((size_t) (chunk_end - chunk_first) * chunk_floats * sizeof(float)), "cudaMalloc G");
   CU_TRY(launch_expand(c->bank.as<float>(), c->d_outs.as<OutEntry>(), c->d_chunks.as<ChunkEntry>(),
                        c->d_G.as<float>(), chunk_first, chunk_end - chunk_first, (int) c->sched.generated,
-                       c->geo.taps, c->bpp, c->chunk_rows, stream),
+                       c->geo.taps, c->bpp, c->chunk_rows, c->direct_call, stream),
          "expand kernel");
   c->g_resident_first = chunk_first;
   c->g_resident_end = chunk_end;
@@ -455,6 +466,10 @@ int ensure_xt(EspbResampleBatch *c, int64_t rows) {
   cudaError_t e = nb[0].reserve(bytes);
   if (e == cudaSuccess)
     e = nb[1].reserve(bytes);
+  if (e == cudaSuccess)  // rows nobody has written yet must still be finite (they meet zero coefficients)
+    e = cudaMemset(nb[0].p, 0, bytes);
+  if (e == cudaSuccess)
+    e = cudaMemset(nb[1].p, 0, bytes);
   if (e == cudaSuccess && c->xt_rows > 0)  // carry rows -> rows [0, taps) of the new current buffer
     e = cudaMemcpy2D(nb[0].p, rows * row_bytes, c->xt[c->xt_cur].as<float>() + (size_t) c->carry_row * kSeriesPerRow,
                      c->xt_rows * row_bytes, taps * row_bytes, c->n_groups(), cudaMemcpyDeviceToDevice);
@@ -502,6 +517,46 @@ struct StageFilter {
   int block_rows = 0, warm_rows = 0;     // time-block mode of the biquad kernel (0 = sequential)
 };
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point (the library does not link libcuda, so it still
+// loads on a machine without a driver — where nothing can be computed anyway).
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void *ptr = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qr) == cudaSuccess &&
+        qr == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+// Can `in` (interleaved float) be read by the resampler kernel directly?  Stereo, 16-byte aligned rows.
+bool direct_input_layout(const EspbResampleBatch *c, const float *in, const EspbLayout &il) {
+  return c->channels == 2 && il.channel_stride == 1 && il.frame_stride == 2 && ((uintptr_t) in % 16) == 0 &&
+         il.stream_stride % 4 == 0 && il.stream_stride > 0 && encode_tiled_fn() != nullptr;
+}
+
+// dim0 = frame x channel floats of a stream, dim1 = stream; box = 16 stereo frames (128 bytes) x 64 streams with the
+// 128-byte swizzle; coordinates outside [0, 2 n_in) x [0, n_streams) read as zero.
+int make_input_map(CUtensorMap *map, const float *in, int64_t stream_stride, int n_in, int n_streams) {
+  const cuuint64_t dims[2] = {(cuuint64_t) n_in * 2, (cuuint64_t) n_streams};
+  const cuuint64_t strides[1] = {(cuuint64_t) stream_stride * sizeof(float)};
+  const cuuint32_t box[2] = {32, (cuuint32_t) (kSeriesPerRow / 2)};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = encode_tiled_fn()(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(in), dims, strides,
+                                       box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                       CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(ESPB_ERR_CUDA, "cuTensorMapEncodeTiled failed");
+  return ESPB_OK;
+}
+
 // Stage + resample series [series_first, series_first + n_series) of the batch (series_first is a
 // multiple of 128).  The carried frames and the new input go to the spare staging buffer.  `pre`
 // filters the staged input in place (time-major); with `post` the resampler writes time-major
@@ -516,6 +571,12 @@ int run_series_range(EspbResampleBatch *c, int series_first, int n_series, const
   const size_t row_bytes = kSeriesPerRow * sizeof(float);
   const float *x_old = c->xt[c->xt_cur].as<float>() + (size_t) g0 * rows * kSeriesPerRow;
   float *x_new = c->xt[1 - c->xt_cur].as<float>() + (size_t) g0 * rows * kSeriesPerRow;
+  // direct input: nothing is staged — the kernel reads the carried frames where they lie and the new frames from
+  // the caller's buffer; afterwards the frames [used - taps, used) become rows [0, taps) of the other buffer
+  const bool direct = c->direct_call && !pre && !post && !pcm_in && !pcm_out;
+  if (c->direct_call && !direct)
+    return fail(ESPB_ERR_STATE, "direct-input plan with library stages around the resampler");
+  if (!direct)
   CU_TRY(cudaMemcpy2DAsync(x_new, rows * row_bytes, x_old + (size_t) c->carry_row * kSeriesPerRow, rows * row_bytes,
                            taps * row_bytes, ng, cudaMemcpyDeviceToDevice, stream),
          "carry copy");
@@ -552,7 +613,9 @@ int run_series_range(EspbResampleBatch *c, int series_first, int n_series, const
   };
   const bool pre_on = pre && pre->params && n_in > 0;
   const bool pre_blocks = pre_on && pre->block_rows > 0 && n_in > pre->block_rows;
-  if (pre_blocks) {
+  if (direct) {
+    // (no staging)
+  } else if (pre_blocks) {
     // time-block pre-filter is out of place: the raw frames go to the other staging buffer (its carry rows
     // were copied above, the rest is free), the filter writes the rows the resampler reads
     float *x_raw = c->xt[c->xt_cur].as<float>() + (size_t) g0 * rows * kSeriesPerRow;
@@ -581,8 +644,15 @@ int run_series_range(EspbResampleBatch *c, int series_first, int n_series, const
     ResampleParams p{};
     p.out_tm = y_tm;
     p.out_tm_rows = c->yt_rows;
-    p.xt = x_new;
+    p.xt = direct ? x_old + (size_t) c->carry_row * kSeriesPerRow : x_new;
     p.xt_rows = rows;
+    DirectInput din{};
+    if (direct) {
+      din.in = in;
+      din.in_ss = il.stream_stride;
+      if (int rc = make_input_map(&din.map, in, il.stream_stride, n_in, n_series / c->channels))
+        return rc;
+    }
     p.out = out;
     p.out_ss = ol.stream_stride;
     p.out_cs = ol.channel_stride;
@@ -620,10 +690,17 @@ int run_series_range(EspbResampleBatch *c, int series_first, int n_series, const
         ev_after = c->ev_pool[c->ev_used + 1];
         c->ev_used += 2;
       }
-      CU_TRY(launch_resample(p, c->bpp, c->chunk_rows, c->mode == ESPB_MODE_EXACT, stream), "resample kernel");
+      CU_TRY(launch_resample(p, c->bpp, c->chunk_rows, c->mode == ESPB_MODE_EXACT, stream, direct ? &din : nullptr),
+             "resample kernel");
       if (ev_after)
         CU_TRY(cudaEventRecord(ev_after, stream), "cudaEventRecord");
     }
+  }
+  if (direct) {  // the next call's carry: frames [used - taps, used), time-major, rows [0, taps) of the other buffer
+    const int used = (int) c->sched.used;
+    CU_TRY(launch_transpose(in + (int64_t) (used - taps) * il.frame_stride, il.stream_stride, il.channel_stride,
+                            il.frame_stride, c->channels, n_series, taps, x_new, rows, 0, 0, stream),
+           "carry transpose");
   }
   if (tm_out) {
     const int gen = (int) c->sched.generated;
@@ -685,7 +762,7 @@ int ensure_yt(EspbResampleBatch *c, int64_t rows, bool second) {
 void finish_call(EspbResampleBatch *c) {
   // the frames [used - taps, used) of this call are the next call's carry: rows [used, used + taps)
   c->xt_cur = 1 - c->xt_cur;
-  c->carry_row = (int) c->sched.used;
+  c->carry_row = c->direct_call ? 0 : (int) c->sched.used;  // (direct input: the carry was written to rows [0, taps))
   c->state = c->sched.end;
 }
 
@@ -717,6 +794,9 @@ EspbResampleBatch *espb_resampleInit(int num_streams, int numChannels, int numTa
   // leave less idle time at the pass edges); ESPB_BPP=8 selects the other variant
   c->bpp = env_long("ESPB_BPP", 4) == 8 ? 8 : 4;
   {
+    // direct input (no staging pass for interleaved stereo float) is opt-in: measured equal per step at C2 (the kernel
+    // is 8 % slower, the 0.58 ms transposition disappears), it only saves the staging memory
+    c->direct_ok = env_long("ESPB_DIRECT", 0) != 0;
     const long cr = env_long("ESPB_CHUNK_ROWS", 32);
     c->chunk_rows = (cr == 16 || ((cr == 24 || cr == 36) && c->bpp == 4)) ? (int) cr : 32;
   }
@@ -856,7 +936,8 @@ EspbResampleResult espb_resampleProcessLayout(EspbResampleBatch *c, const float 
   }
   if (numInputFrames < 0)
     numInputFrames = 0;
-  if (prepare_call(c, numInputFrames, numOutputFrames, ratio, as_stream(stream)) != ESPB_OK)
+  if (prepare_call(c, numInputFrames, numOutputFrames, ratio, as_stream(stream), direct_input_layout(c, in, *il)) !=
+      ESPB_OK)
     return res;
   if (run_series_range(c, 0, c->n_series(), in, *il, out, *ol, numInputFrames, as_stream(stream), false) != ESPB_OK)
     return res;
@@ -921,8 +1002,12 @@ EspbResampleResult espb_resampleProcessInterleavedHost(EspbResampleBatch *c, con
     return res;
   }
   cudaStream_t s0 = hs->pipe.s[0];
-  if (prepare_call(c, numInputFrames, numOutputFrames, ratio, s0) != ESPB_OK)
-    return res;
+  {
+    const EspbLayout stage_layout = {(int64_t) in_row, 1, ch};
+    if (prepare_call(c, numInputFrames, numOutputFrames, ratio, s0,
+                     direct_input_layout(c, hs->stage_in.as<float>(), stage_layout)) != ESPB_OK)
+      return res;
+  }
   const size_t out_row = (size_t) c->sched.generated * ch;
   const bool single_slab_g = passes_per_slab(c) >= c->plan.n_passes();
   if (c->sched.generated > 0 && single_slab_g) {

@@ -1,5 +1,6 @@
 // Launch wrappers for the sm_100a kernels (internal; the public boundary is include/esp_audio_b200.h).
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stddef.h>
 #include <stdint.h>
@@ -25,6 +26,19 @@ struct ResampleParams {
   int pass_first, pass_end, passes_per_cta, g_chunk_base;
   int out_vec;  // OutVec: set by launch_resample from the output layout
 };
+// Direct input (interleaved stereo float; resample_direct_kernel.cu): rows j >= 0 come from the caller's buffer
+// through a TMA tensor map (dim0 = frame x channel floats, dim1 = stream; box 32 floats x 64 streams, 128-byte
+// swizzle, zero fill outside).  Kept out of ResampleParams: the standard kernel's register allocation is sensitive
+// to the layout of its parameter block.
+struct DirectInput {
+  const float *in;  // the same buffer, for pass-through outputs
+  int64_t in_ss;    // its stream stride, floats
+  alignas(64) CUtensorMap map;
+};
+struct ResampleDirectParams {
+  ResampleParams p;
+  DirectInput d;
+};
 enum OutVec : int { kOutVecNone = 0, kOutVecPlanar = 1, kOutVecStereo = 2, kOutVecFrame4 = 3, kOutVecTimeMajor = 4 };
 
 size_t resample_smem_bytes(int bpp, int chunk_rows);
@@ -32,8 +46,12 @@ size_t g_chunk_floats(int bpp, int chunk_rows);
 cudaError_t launch_finalize(OutEntry *outs, int n, int n_filters, bool lowpass, bool interp, cudaStream_t stream);
 cudaError_t launch_expand(const float *bank, const OutEntry *outs, const ChunkEntry *chunks, float *G,
                           int chunk_first, int n_chunks, int n_out, int taps, int bpp, int chunk_rows,
-                          cudaStream_t stream);
-cudaError_t launch_resample(const ResampleParams &p, int bpp, int chunk_rows, bool exact, cudaStream_t stream);
+                          bool split_at_zero, cudaStream_t stream);
+cudaError_t launch_resample(const ResampleParams &p, int bpp, int chunk_rows, bool exact, cudaStream_t stream,
+                            const DirectInput *direct = nullptr);
+// direct-input form (BPP 4, 32-row chunks, caller-layout output); called by launch_resample when p.direct is set
+cudaError_t launch_resample_direct(const ResampleParams &p, const DirectInput &d, int n_groups, int n_ctas_y,
+                                   bool exact, cudaStream_t stream);
 cudaError_t launch_transpose(const float *in, int64_t in_ss, int64_t in_cs, int64_t in_fs, int channels, int n_series,
                              int n_in, float *xt, int64_t rows_cap, int row_first, int pad_rows,
                              cudaStream_t stream);

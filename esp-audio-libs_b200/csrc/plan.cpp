@@ -200,7 +200,8 @@ static inline int32_t entry_ws(const Schedule &s, int k) {
   return s.raw ? s.outs[k].ws + (int32_t) s.outs[k].w : s.outs[k].ws;  // raw: base + floor(offset)
 }
 
-void build_pass_plan(const Schedule &s, int taps, int blocks_per_pass, int chunk_rows, PassPlan &p) {
+void build_pass_plan(const Schedule &s, int taps, int blocks_per_pass, int chunk_rows, PassPlan &p,
+                     bool split_at_zero) {
   const int opp = blocks_per_pass * kOutputsPerBlock;
   const int n = (int) s.outs.size();
   p.outputs_per_pass = opp;
@@ -209,7 +210,7 @@ void build_pass_plan(const Schedule &s, int taps, int blocks_per_pass, int chunk
   if (n > 0) {  // windows advance monotonically: the last pass's span bounds the chunk count per pass well enough
     const size_t n_passes = ((size_t) n + opp - 1) / opp;
     const long long span = (long long) entry_ws(s, n - 1) - entry_ws(s, 0);
-    const size_t per_pass = (size_t) ((span / (long long) n_passes + taps) / chunk_rows + 3);
+    const size_t per_pass = (size_t) ((span / (long long) n_passes + taps) / chunk_rows + 4);
     p.chunks.reserve(n_passes * per_pass);
     p.pass_chunk_begin.reserve(n_passes + 1);
   }
@@ -217,8 +218,18 @@ void build_pass_plan(const Schedule &s, int taps, int blocks_per_pass, int chunk
   for (int first = 0, pass = 0; first < n; first += opp, ++pass) {
     const int last = (first + opp < n ? first + opp : n) - 1;
     const int j0 = entry_ws(s, first), j1 = entry_ws(s, last) + taps;
-    for (int j = j0; j < j1; j += chunk_rows)
-      p.chunks.push_back(ChunkEntry{j, pass});
+    if (split_at_zero && j0 < 0 && j1 > 0) {
+      const int j0a = -((-j0 + 3) / 4 * 4);  // floor to a multiple of 4: frame 0 then falls on a 4-row group
+      for (int j = j0a; j < 0; j += chunk_rows)
+        p.chunks.push_back(ChunkEntry{j, pass});
+      for (int j = 0; j < j1; j += chunk_rows)
+        p.chunks.push_back(ChunkEntry{j, pass});
+    } else {
+      // (direct input: TMA needs the box to start on a 16-byte boundary of the stream's row = an even stereo frame)
+      const int js = (split_at_zero && j0 > 0) ? (j0 & ~1) : j0;
+      for (int j = js; j < j1; j += chunk_rows)
+        p.chunks.push_back(ChunkEntry{j, pass});
+    }
     p.pass_chunk_begin.push_back((int32_t) p.chunks.size());
   }
 }

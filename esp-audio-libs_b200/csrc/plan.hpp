@@ -86,7 +86,11 @@ struct PassPlan {
   PodBuffer<int32_t> pass_chunk_begin;  // n_passes + 1 prefix
   int n_passes() const { return (int) pass_chunk_begin.size() - 1; }
 };
-void build_pass_plan(const Schedule &s, int taps, int blocks_per_pass, int chunk_rows, PassPlan &p);
+// split_at_zero: no chunk straddles input frame 0 — a pass that starts in the carried frames sweeps them in chunks
+// that begin on a multiple of 4 rows and then starts over at frame 0 (the kernel's direct-input form reads the two
+// sides from different places).
+void build_pass_plan(const Schedule &s, int taps, int blocks_per_pass, int chunk_rows, PassPlan &p,
+                     bool split_at_zero = false);
 
 // art_biquad.cpp:16-38 (design in double, stored as float).
 struct BiquadCoeffs {

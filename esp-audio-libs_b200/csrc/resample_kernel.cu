@@ -38,78 +38,10 @@
 
 #include "common.hpp"
 #include "kernels.hpp"
+#include "resample_device.cuh"
 
 namespace espb {
 
-namespace {
-
-constexpr int NB = kOutputsPerBlock;  // 8
-constexpr int SGN = kSeriesPerRow;    // 128
-constexpr uint32_t kPassDone = 1u << 9;  // rtab flag next to r0 (bits 0-3), r1 (4-7)
-constexpr int RG = 4;  // rows per skip group / inner unroll
-
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t) __cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes)
-               : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-  const uint32_t a = smem_u32(bar);
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "WAIT_%=:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra DONE_%=;\n"
-      "bra WAIT_%=;\n"
-      "DONE_%=:\n"
-      "}\n" ::"r"(a),
-      "r"(parity)
-      : "memory");
-}
-// TMA bulk copy global -> shared, completion counted on an mbarrier (SASS: UBLKCP).
-__device__ __forceinline__ void tma_bulk_g2s(void *dst_smem, const void *src, uint32_t bytes, uint64_t *bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
-                   smem_u32(dst_smem)),
-               "l"(src), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
-
-__device__ __forceinline__ void cp_async_16(void *dst_smem, const void *src) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;\n" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
-
-// Counting arrival on a shared-memory word.  Relaxed is enough: every shared-memory load of the stage
-// has already returned its value (the FMAs consumed them) when the warp gets here, so nothing of this
-// warp can still observe the refill; the refill itself is published by the mbarrier arrive (release).
-__device__ __forceinline__ int smem_arrive(int *counter) {
-  int old;
-  asm volatile("atom.relaxed.cta.shared::cta.add.s32 %0, [%1], 1;\n" : "=r"(old) : "r"(smem_u32(counter)) : "memory");
-  return old;
-}
-
-// Packed FP32 pairs (Blackwell FFMA2): two independent IEEE FMAs per lane per instruction — the same
-// results as two scalar FFMAs, half the issue slots.  A pair is (filter 0, filter 1) of one output, whose
-// coefficients are adjacent in G.
-// Fast mode only: ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 (unlike the scalar forms, whose
-// explicit .rn is honoured), so exact mode keeps scalar FMUL + FADD.
-__device__ __forceinline__ float2 fma2(float2 g, float x, float2 acc) {
-  return __ffma2_rn(g, make_float2(x, x), acc);  // SASS: FFMA2 acc, g.F32x2, x.F32 (scalar broadcast), acc
-}
-
-template <bool EXACT>
-__device__ __forceinline__ float mac(float g, float x, float acc) {
-  if (EXACT)
-    return __fadd_rn(acc, __fmul_rn(g, x));  // dsps_dotprod_f32_ansi.c:20 — separate multiply and add
-  return __fmaf_rn(g, x, acc);
-}
-
-}  // namespace
 
 // ---------------------------------------------------------------------------------
 // Second pass of the schedule on the device (twin of plan.cpp:finalize_entries; the same IEEE
@@ -150,7 +82,8 @@ __global__ void __launch_bounds__(256)
 __global__ void __launch_bounds__(256) espb_expand_kernel(const float *__restrict__ bank,
                                                           const OutEntry *__restrict__ outs,
                                                           const ChunkEntry *__restrict__ chunks, float *__restrict__ G,
-                                                          int chunk_first, int n_out, int taps, int bpp, int CJ) {
+                                                          int chunk_first, int n_out, int taps, int bpp, int CJ,
+                                                          int split_at_zero) {
   const int gc = chunk_first + blockIdx.x;
   const ChunkEntry ce = chunks[gc];
   const int quads_per_row = bpp * (kGRowFloats / 4);  // float4 per row
@@ -168,7 +101,8 @@ __global__ void __launch_bounds__(256) espb_expand_kernel(const float *__restric
       if (o < n_out) {
         const OutEntry e = outs[o];
         const int k = j - e.ws;
-        if (k >= 0 && k < taps && e.kind >= kKindSingle) {
+        // (split plan: a chunk of carried frames stops at input frame 0, the next chunk starts there)
+        if (k >= 0 && k < taps && e.kind >= kKindSingle && !(split_at_zero && ce.j_start < 0 && j >= 0)) {
           c0 = __ldg(bank + (size_t) e.phase * taps + k);
           if (e.kind == kKindBlend)
             c1 = __ldg(bank + (size_t) (e.phase + 1) * taps + k);
@@ -661,10 +595,11 @@ cudaError_t launch_finalize(OutEntry *outs, int n, int n_filters, bool lowpass, 
 
 cudaError_t launch_expand(const float *bank, const OutEntry *outs, const ChunkEntry *chunks, float *G,
                           int chunk_first, int n_chunks, int n_out, int taps, int bpp, int chunk_rows,
-                          cudaStream_t stream) {
+                          bool split_at_zero, cudaStream_t stream) {
   if (n_chunks <= 0)
     return cudaSuccess;
-  espb_expand_kernel<<<n_chunks, 256, 0, stream>>>(bank, outs, chunks, G, chunk_first, n_out, taps, bpp, chunk_rows);
+  espb_expand_kernel<<<n_chunks, 256, 0, stream>>>(bank, outs, chunks, G, chunk_first, n_out, taps, bpp, chunk_rows,
+                                                    split_at_zero ? 1 : 0);
   count_launch();
   return cudaGetLastError();
 }
@@ -825,7 +760,8 @@ static cudaError_t launch_resample_t(const ResampleParams &p, int n_groups, int 
   return cudaGetLastError();
 }
 
-cudaError_t launch_resample(const ResampleParams &p, int bpp, int chunk_rows, bool exact, cudaStream_t stream) {
+cudaError_t launch_resample(const ResampleParams &p, int bpp, int chunk_rows, bool exact, cudaStream_t stream,
+                            const DirectInput *direct) {
   const int n_groups = (p.n_series + SGN - 1) / SGN;
   const int n_passes = p.pass_end - p.pass_first;
   if (n_groups <= 0 || n_passes <= 0)
@@ -850,6 +786,11 @@ cudaError_t launch_resample(const ResampleParams &p, int bpp, int chunk_rows, bo
                : launch_resample_t<BPP_, NST_, CJ_, true, false>(q, n_groups, n_ctas_y, stream))   \
          : (tm ? launch_resample_t<BPP_, NST_, CJ_, false, true>(q, n_groups, n_ctas_y, stream)    \
                : launch_resample_t<BPP_, NST_, CJ_, false, false>(q, n_groups, n_ctas_y, stream)))
+  if (direct) {  // input rows straight from the caller's interleaved-stereo buffer (resample_direct_kernel.cu)
+    if (bpp != 4 || chunk_rows != 32 || tm)
+      return cudaErrorInvalidValue;
+    return launch_resample_direct(q, *direct, n_groups, n_ctas_y, exact, stream);
+  }
   if (bpp == 8 && chunk_rows == 32)
     return ESPB_LAUNCH(8, 3, 32);
   if (bpp == 4 && chunk_rows == 32)

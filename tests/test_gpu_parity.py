@@ -524,3 +524,40 @@ def test_ratio_groups_drifting_ratios_chunked(oracle, mode):
             assert g.state(k) == orc[int(np.argmax(group_of == k))].state()
     assert worst <= 1e-6  # fast mode: the north star's tolerance (max-abs, full scale)
     g.free()
+
+
+@pytest.mark.parametrize("mode", ["exact", "fast"])
+def test_direct_input_path_stereo(oracle, mode, monkeypatch):
+    """ESPB_DIRECT=1: interleaved stereo float input read by the kernel through a TMA tensor map (no staging pass),
+    carried frames from the time-major history.  Chunked calls with changing sizes (some below numTaps, which fall
+    back to the staged path and must hand the history over correctly), capacity-limited calls, a group tail."""
+    monkeypatch.setenv("ESPB_DIRECT", "1")
+    ch, taps, filters = 2, 64, 64
+    ns = 70  # one full group of 64 streams and a partial one
+    ratio = f32(48000) / f32(44100)
+    total = 5000
+    x = np.stack([noise(total, ch, stream=500 + s, amp=0.8) for s in range(ns)])
+    b = espb.ResampleBatch(ns, ch, taps, filters, 1.0, 3, mode=espb.MODE_EXACT if mode == "exact" else espb.MODE_FAST)
+    b.advance(taps / 2)
+    probes = [0, 31, 32, 63, 64, ns - 1]
+    orc = {s: oracle.resampler(ch, taps, filters, 1.0, 3) for s in probes}
+    for o in orc.values():
+        o.advance(taps / 2)
+    pos, worst = 0, 0.0
+    for n_in, cap in [(1000, 2000), (10, 50), (900, 300), (64, 500), (2, 9), (1500, 4000), (700, 4000)]:
+        n_in = min(n_in, total - pos)
+        seg = np.ascontiguousarray(x[:, pos * ch:(pos + n_in) * ch])
+        if n_in == 0:
+            seg = np.zeros((ns, 0), f32)
+        y, used, gen = b.process_interleaved(seg, cap, ratio, n_in=n_in)
+        for s in probes:
+            yo, uo, go = orc[s].process_interleaved(seg[s], cap, ratio, n_in=n_in)
+            assert (used, gen) == (uo, go)
+            if mode == "exact":
+                assert bits_equal(y[s], yo), (n_in, cap, s)
+            elif go:
+                worst = max(worst, float(np.max(np.abs(y[s].astype(np.float64) - yo))))
+        pos += used
+    assert b.state() == orc[0].state()
+    assert worst <= 1e-6
+    b.free()
