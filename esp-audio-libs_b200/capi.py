@@ -7,7 +7,8 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
-_SO = os.path.join(_HERE, "libesp_audio_b200.so")
+# (ESPB_LIBRARY: another build of the same library, e.g. a kernel variant under tools/sweep_kernel.sh)
+_SO = os.environ.get("ESPB_LIBRARY") or os.path.join(_HERE, "libesp_audio_b200.so")
 _HEADER = os.path.join(_ROOT, "include", "esp_audio_b200.h")
 
 SUBSAMPLE_INTERPOLATE, BLACKMAN_HARRIS, INCLUDE_LOWPASS = 0x1, 0x2, 0x4
