@@ -201,6 +201,26 @@ def protect_stdout():
     return real
 
 
+_ALL_CPUS = None  # the affinity mask before bind_to_gpu_cpus (the CPU baseline leg gets all cores back)
+
+
+def bind_to_gpu_cpus(gpu):
+    """Pin this process to the CPUs NVML reports as local to its GPU, so that the pinned host buffers of the
+    end-to-end path are allocated (first touch) on the GPU's NUMA node.  Returns a note for the JSON line."""
+    try:
+        import pynvml as nv
+        nv.nvmlInit()
+        h = nv.nvmlDeviceGetHandleByIndex(gpu)
+        global _ALL_CPUS
+        _ALL_CPUS = os.sched_getaffinity(0)
+        before = len(_ALL_CPUS)
+        nv.nvmlDeviceSetCpuAffinity(h)
+        after = len(os.sched_getaffinity(0))
+        return f"nvmlDeviceSetCpuAffinity: {before} -> {after} CPUs"
+    except Exception as exc:  # no NVML, no permission: run unpinned
+        return f"unpinned ({type(exc).__name__})"
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -234,6 +254,7 @@ def main():
     espb.set_device(local_rank)
     info = espb.device_info()
     L = espb.lib()
+    host_affinity = bind_to_gpu_cpus(local_rank)  # before the pinned buffers are allocated and touched
 
     ns = args.streams
     cap = int(N_IN * float(RATIO)) + 64
@@ -395,6 +416,8 @@ def main():
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        if _ALL_CPUS:
+            os.sched_setaffinity(0, _ALL_CPUS)
         threads = host_threads()
         cb = cpu_reference_arm(threads * 8, N_IN, threads)
         one = cpu_reference_arm(2, N_IN, 1)
@@ -415,7 +438,7 @@ def main():
                        "l2": "inputs+outputs 3.0 GB per step >> 126 MB L2 (no flush needed)",
                        "timed_region": "per step: reset, host schedule, table upload, coefficient expansion, "
                                        "resampler kernel, history carry (plan cache off)"},
-            "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches),
+            "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "host_affinity": host_affinity, "gpu_launches": int(launches),
             "clocks": clocks, "checksums": checksums, "checksum_of_checksums": espb.combine_checksums(checksums), "device": info["name"], "sm_count": info["sm_count"],
         }
         print(json.dumps(line), file=out, flush=True)

@@ -201,8 +201,8 @@ cudaError_t launch_tm(const float *src, float *dst, int64_t rows_cap, int row_fi
   const int n_blocks = block_rows > 0 ? (n_rows + block_rows - 1) / block_rows : 1;
   const dim3 grid((n_series + SGN - 1) / SGN, n_blocks);
   const size_t smem = sizeof(float) * BSTAGES * RB * SGN + BSTAGES * sizeof(uint64_t);
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce once;
+  if (once.first()) {
     cudaError_t e = cudaFuncSetAttribute(espb_biquad_tm_kernel<NSEC, true>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
     if (e == cudaSuccess)
@@ -210,7 +210,6 @@ cudaError_t launch_tm(const float *src, float *dst, int64_t rows_cap, int row_fi
                                (int) smem);
     if (e != cudaSuccess)
       return e;
-    configured = true;
   }
   if (c.first_order)
     espb_biquad_tm_kernel<NSEC, true><<<grid, SGN, smem, stream>>>(src, dst, rows_cap, row_first, n_rows, c, state,

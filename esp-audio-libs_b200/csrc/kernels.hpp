@@ -11,6 +11,20 @@ namespace espb {
 
 void count_launch();  // bumps the process-wide kernel-launch counter (api.cu)
 
+// Function attributes (dynamic shared-memory size, carve-out) are per device: one flag per device and kernel.
+struct PerDeviceOnce {
+  bool done[64] = {};
+  // true the first time it is asked on the current device
+  bool first() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64)
+      return true;
+    const bool was = done[dev];
+    done[dev] = true;
+    return !was;
+  }
+};
+
 struct ResampleParams {
   const float *xt;  // time-major input staging of the first group of this launch: [group][xt_rows][128]
   int64_t xt_rows;  // rows per group (row r = input frame r - taps)

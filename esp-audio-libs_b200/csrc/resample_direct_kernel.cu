@@ -388,8 +388,8 @@ template <bool EXACT>
 static cudaError_t launch_direct_t(const ResampleParams &p, const DirectInput &d, int n_groups, int n_ctas_y,
                                    cudaStream_t stream) {
   const size_t smem = resample_smem_bytes(4, 32);
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce once;
+  if (once.first()) {
     cudaError_t e = cudaFuncSetAttribute(espb_resample_direct_kernel<EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int) smem);
     if (e == cudaSuccess)  // four CTAs per SM need the full shared-memory carve-out
@@ -397,7 +397,6 @@ static cudaError_t launch_direct_t(const ResampleParams &p, const DirectInput &d
                                (int) cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess)
       return e;
-    configured = true;
     if (getenv("ESPB_DEBUG")) {
       int nb = 0;
       cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, espb_resample_direct_kernel<EXACT>, 128, smem);

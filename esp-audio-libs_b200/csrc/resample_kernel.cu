@@ -733,8 +733,8 @@ cudaError_t launch_untranspose(const float *tm, int64_t rows_cap, int row_first,
 template <int BPP, int NST, int CJ, bool EXACT, bool TMCAP>
 static cudaError_t launch_resample_t(const ResampleParams &p, int n_groups, int n_ctas_y, cudaStream_t stream) {
   const size_t smem = resample_smem_bytes(BPP, CJ);
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce once;
+  if (once.first()) {
     cudaError_t e = cudaFuncSetAttribute(espb_resample_kernel<BPP, NST, CJ, EXACT, TMCAP>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
     if (e != cudaSuccess)
@@ -744,7 +744,6 @@ static cudaError_t launch_resample_t(const ResampleParams &p, int n_groups, int 
                              (int) cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess)
       return e;
-    configured = true;
     if (getenv("ESPB_DEBUG")) {
       int nb = 0;
       cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, espb_resample_kernel<BPP, NST, CJ, EXACT, TMCAP>, BPP * 32, smem);
