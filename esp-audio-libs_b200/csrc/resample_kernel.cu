@@ -77,41 +77,54 @@ __global__ void __launch_bounds__(256)
 }
 
 // ---------------------------------------------------------------------------------
-// G expansion: one CTA per chunk, one float4 (two outputs x two filters) per thread-iteration.
+// G expansion.  CTAs stride over the chunks; within a chunk a warp takes 32 consecutive rows of one float4
+// (two outputs x two filters), so its reads of a filter row are one coalesced 128-byte line and the two schedule
+// entries are warp-uniform; the tile goes through (padded) shared memory and leaves as contiguous 16-byte stores.
 // ---------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) espb_expand_kernel(const float *__restrict__ bank,
-                                                          const OutEntry *__restrict__ outs,
-                                                          const ChunkEntry *__restrict__ chunks, float *__restrict__ G,
-                                                          int chunk_first, int n_out, int taps, int bpp, int CJ,
-                                                          int split_at_zero) {
-  const int gc = chunk_first + blockIdx.x;
-  const ChunkEntry ce = chunks[gc];
-  const int quads_per_row = bpp * (kGRowFloats / 4);  // float4 per row
+constexpr int kExpandThreads = 256;
+constexpr int kExpandTileFloat4 = 36 * 17 > 32 * 33 ? 36 * 17 : 32 * 33;  // rows x (float4 per row + 1 pad)
+
+__global__ void __launch_bounds__(kExpandThreads)
+    espb_expand_kernel(const float *__restrict__ bank, const OutEntry *__restrict__ outs,
+                       const ChunkEntry *__restrict__ chunks, float *__restrict__ G, int chunk_first, int n_chunks,
+                       int n_out, int taps, int bpp, int CJ, int split_at_zero) {
+  __shared__ float4 tile[kExpandTileFloat4];
+  const int quads_per_row = bpp * (kGRowFloats / 4);  // float4 per row: 16 (4 warps per pass) or 32
+  const int pitch = quads_per_row + 1;
   const int total = CJ * quads_per_row;
-  float4 *dst = reinterpret_cast<float4 *>(G + (size_t) blockIdx.x * CJ * bpp * kGRowFloats);
-  for (int i = threadIdx.x; i < total; i += blockDim.x) {
-    const int jj = i / quads_per_row, r = i - jj * quads_per_row;
-    const int b = r >> 2, pair = r & 3;  // block in pass, output pair within block
-    const int j = ce.j_start + jj;
-    float v[4];
+  for (int cc = blockIdx.x; cc < n_chunks; cc += gridDim.x) {
+    const ChunkEntry ce = chunks[chunk_first + cc];
+    for (int i = threadIdx.x; i < total; i += kExpandThreads) {
+      const int quad = i / CJ, jj = i - quad * CJ;  // rows fastest: a warp reads one filter row contiguously
+      const int b = quad >> 2, pair = quad & 3;     // block in pass, output pair within block
+      const int j = ce.j_start + jj;
+      float v[4];
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const int o = (ce.pass * bpp + b) * NB + pair * 2 + h;
-      float c0 = 0.0f, c1 = 0.0f;
-      if (o < n_out) {
-        const OutEntry e = outs[o];
-        const int k = j - e.ws;
-        // (split plan: a chunk of carried frames stops at input frame 0, the next chunk starts there)
-        if (k >= 0 && k < taps && e.kind >= kKindSingle && !(split_at_zero && ce.j_start < 0 && j >= 0)) {
-          c0 = __ldg(bank + (size_t) e.phase * taps + k);
-          if (e.kind == kKindBlend)
-            c1 = __ldg(bank + (size_t) (e.phase + 1) * taps + k);
+      for (int h = 0; h < 2; ++h) {
+        const int o = (ce.pass * bpp + b) * NB + pair * 2 + h;
+        float c0 = 0.0f, c1 = 0.0f;
+        if (o < n_out) {
+          const OutEntry e = outs[o];
+          const int k = j - e.ws;
+          // (split plan: a chunk of carried frames stops at input frame 0, the next chunk starts there)
+          if (k >= 0 && k < taps && e.kind >= kKindSingle && !(split_at_zero && ce.j_start < 0 && j >= 0)) {
+            c0 = __ldg(bank + (size_t) e.phase * taps + k);
+            if (e.kind == kKindBlend)
+              c1 = __ldg(bank + (size_t) (e.phase + 1) * taps + k);
+          }
         }
+        v[2 * h] = c0;
+        v[2 * h + 1] = c1;
       }
-      v[2 * h] = c0;
-      v[2 * h + 1] = c1;
+      tile[jj * pitch + quad] = make_float4(v[0], v[1], v[2], v[3]);
     }
-    dst[i] = make_float4(v[0], v[1], v[2], v[3]);
+    __syncthreads();
+    float4 *dst = reinterpret_cast<float4 *>(G + (size_t) cc * CJ * bpp * kGRowFloats);
+    for (int i = threadIdx.x; i < total; i += kExpandThreads) {
+      const int jj = i / quads_per_row, quad = i - jj * quads_per_row;
+      dst[i] = tile[jj * pitch + quad];
+    }
+    __syncthreads();
   }
 }
 
@@ -598,8 +611,12 @@ cudaError_t launch_expand(const float *bank, const OutEntry *outs, const ChunkEn
                           bool split_at_zero, cudaStream_t stream) {
   if (n_chunks <= 0)
     return cudaSuccess;
-  espb_expand_kernel<<<n_chunks, 256, 0, stream>>>(bank, outs, chunks, G, chunk_first, n_out, taps, bpp, chunk_rows,
-                                                    split_at_zero ? 1 : 0);
+  int sms = 148, dev = 0;
+  if (cudaGetDevice(&dev) == cudaSuccess)
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int grid = n_chunks < sms * 8 ? n_chunks : sms * 8;  // 8 resident CTAs of 256 threads per SM
+  espb_expand_kernel<<<grid, kExpandThreads, 0, stream>>>(bank, outs, chunks, G, chunk_first, n_chunks, n_out, taps,
+                                                          bpp, chunk_rows, split_at_zero ? 1 : 0);
   count_launch();
   return cudaGetLastError();
 }
