@@ -33,21 +33,44 @@ ArtState initial_state(int taps);  // art_resampler.cpp:135-136
 
 // Growable array of plain structs without value-initialisation (the schedule tables are written once,
 // front to back, right after sizing).
+// The owner may hook the (rare) moments the storage moves — the CUDA layer page-locks the tables so that their
+// uploads are asynchronous DMA copies instead of staged ones; this header itself stays free of CUDA.
 template <typename T>
 struct PodBuffer {
   T *ptr = nullptr;
   size_t count = 0, cap = 0;
+  void (*on_release)(void *p) = nullptr;               // called before the storage is moved or freed
+  void (*on_acquire)(void *p, size_t bytes) = nullptr;  // called after new storage has been obtained
   PodBuffer() = default;
   PodBuffer(const PodBuffer &) = delete;
   PodBuffer &operator=(const PodBuffer &) = delete;
-  ~PodBuffer() { free(ptr); }
+  ~PodBuffer() {
+    if (ptr && on_release)
+      on_release(ptr);
+    free(ptr);
+  }
   void reserve(size_t n) {
     if (n > cap) {
+      if (ptr && on_release)
+        on_release(ptr);
       ptr = static_cast<T *>(realloc(ptr, n * sizeof(T)));
       cap = n;
+      if (ptr && on_acquire)
+        on_acquire(ptr, cap * sizeof(T));
     }
   }
   void clear() { count = 0; }
+  void swap_storage(PodBuffer &o) {  // (both sides are expected to carry the same hooks)
+    T *p = ptr;
+    ptr = o.ptr;
+    o.ptr = p;
+    size_t t = count;
+    count = o.count;
+    o.count = t;
+    t = cap;
+    cap = o.cap;
+    o.cap = t;
+  }
   void push_back(const T &v) {
     if (count == cap)
       reserve(cap ? cap * 2 : 1024);
