@@ -141,8 +141,8 @@ constexpr int TF_THREADS = 256;
 
 // Fast path: interleaved input (channel stride 1, frame stride CH) with CH in {1,2,4,8}, or planar
 // input (frame stride 1; CH = 1 and one "stream" per series), 16-byte aligned rows, full tiles only.
-// 128-bit loads along time, index arithmetic by shifts only.
-template <int CH, bool PLANAR>
+// VEC-float loads along time (4, 2 or 1 as the alignment of the rows allows), index arithmetic by shifts only.
+template <int CH, bool PLANAR, int VEC>
 __global__ void __launch_bounds__(TF_THREADS)
     espb_transpose_fast_kernel(const float *__restrict__ in, int64_t in_ss, int64_t in_cs, int channels,
                                int n_series, float *__restrict__ xt, int64_t rows_cap, int row_first) {
@@ -151,12 +151,15 @@ __global__ void __launch_bounds__(TF_THREADS)
   const int j0 = blockIdx.y * TF_ROWS;
   const int tid = threadIdx.x;
   constexpr int UNITS = SGN / CH;         // contiguous runs per group (streams, or series when planar)
-  constexpr int V_PER_UNIT = TF_ROWS * CH / 4;  // float4 per run
+  constexpr int V_PER_UNIT = TF_ROWS * CH / VEC;  // vectors per run
 #pragma unroll 4
   for (int v = tid; v < UNITS * V_PER_UNIT; v += TF_THREADS) {
     const int unit = v / V_PER_UNIT, off4 = v % V_PER_UNIT;  // powers of two: shifts
     const int q0 = g * SGN + unit * CH;                       // first series of the run
-    float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+    float xv[VEC];
+#pragma unroll
+    for (int k = 0; k < VEC; ++k)
+      xv[k] = 0.0f;
     if (q0 < n_series) {
       const float *src;
       if (PLANAR) {
@@ -165,12 +168,19 @@ __global__ void __launch_bounds__(TF_THREADS)
       } else {
         src = in + (int64_t) (q0 / CH) * in_ss + (int64_t) j0 * CH;
       }
-      x = __ldg(reinterpret_cast<const float4 *>(src) + off4);
+      if constexpr (VEC == 4) {
+        const float4 x = __ldg(reinterpret_cast<const float4 *>(src) + off4);
+        xv[0] = x.x, xv[1] = x.y, xv[2] = x.z, xv[3] = x.w;
+      } else if constexpr (VEC == 2) {
+        const float2 x = __ldg(reinterpret_cast<const float2 *>(src) + off4);
+        xv[0] = x.x, xv[1] = x.y;
+      } else {
+        xv[0] = __ldg(src + off4);
+      }
     }
-    const int e0 = off4 * 4;
-    const float xv[4] = {x.x, x.y, x.z, x.w};
+    const int e0 = off4 * VEC;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
+    for (int k = 0; k < VEC; ++k) {
       const int e = e0 + k;
       tile[e / CH][unit * CH + (e % CH)] = xv[k];
     }
@@ -627,31 +637,42 @@ cudaError_t launch_transpose(const float *in, int64_t in_ss, int64_t in_cs, int6
   const int n_groups = (n_series + SGN - 1) / SGN;
   if (n_groups <= 0 || n_in + pad_rows <= 0)
     return cudaSuccess;
-  // full 64-row tiles through the fast kernel when the layout allows it
+  // full 64-row tiles through the fast kernel when the layout allows it, with the widest loads the alignment allows
   int fast_rows = 0;
-  const bool aligned = ((uintptr_t) in % 16 == 0) && (in_ss % 4 == 0);
   const bool interleaved = (in_cs == 1 && in_fs == channels);
-  const bool planar = (in_fs == 1) && (in_cs % 4 == 0);
-  if (aligned && n_in >= TF_ROWS) {
+  const bool planar = (in_fs == 1);
+  // rows start at in + stream * in_ss (+ channel * in_cs when planar) + a multiple of 64 frames
+  const bool cs_ok4 = interleaved || in_cs % 4 == 0, cs_ok2 = interleaved || in_cs % 2 == 0;
+  int vec = 1;
+  if ((uintptr_t) in % 16 == 0 && in_ss % 4 == 0 && cs_ok4)
+    vec = 4;
+  else if ((uintptr_t) in % 8 == 0 && in_ss % 2 == 0 && cs_ok2)
+    vec = 2;
+  if (n_in >= TF_ROWS) {
     dim3 grid(n_groups, n_in / TF_ROWS);
     bool done = true;
+#define ESPB_TR(CH_, PL_)                                                                                          \
+  (vec == 4 ? espb_transpose_fast_kernel<CH_, PL_, 4><<<grid, TF_THREADS, 0, stream>>>(in, in_ss, in_cs, channels,  \
+                                                                                      n_series, xt, rows_cap,     \
+                                                                                      row_first)                  \
+   : vec == 2                                                                                                      \
+       ? espb_transpose_fast_kernel<CH_, PL_, 2><<<grid, TF_THREADS, 0, stream>>>(in, in_ss, in_cs, channels,       \
+                                                                                 n_series, xt, rows_cap, row_first) \
+       : espb_transpose_fast_kernel<CH_, PL_, 1><<<grid, TF_THREADS, 0, stream>>>(in, in_ss, in_cs, channels,       \
+                                                                                 n_series, xt, rows_cap, row_first))
     if (interleaved && channels == 1)
-      espb_transpose_fast_kernel<1, false><<<grid, TF_THREADS, 0, stream>>>(in, in_ss, in_cs, channels, n_series, xt,
-                                                                            rows_cap, row_first);
+      ESPB_TR(1, false);
     else if (interleaved && channels == 2)
-      espb_transpose_fast_kernel<2, false><<<grid, TF_THREADS, 0, stream>>>(in, in_ss, in_cs, channels, n_series, xt,
-                                                                            rows_cap, row_first);
+      ESPB_TR(2, false);
     else if (interleaved && channels == 4)
-      espb_transpose_fast_kernel<4, false><<<grid, TF_THREADS, 0, stream>>>(in, in_ss, in_cs, channels, n_series, xt,
-                                                                            rows_cap, row_first);
+      ESPB_TR(4, false);
     else if (interleaved && channels == 8)
-      espb_transpose_fast_kernel<8, false><<<grid, TF_THREADS, 0, stream>>>(in, in_ss, in_cs, channels, n_series, xt,
-                                                                            rows_cap, row_first);
+      ESPB_TR(8, false);
     else if (planar)
-      espb_transpose_fast_kernel<1, true><<<grid, TF_THREADS, 0, stream>>>(in, in_ss, in_cs, channels, n_series, xt,
-                                                                           rows_cap, row_first);
+      ESPB_TR(1, true);
     else
       done = false;
+#undef ESPB_TR
     if (done) {
       count_launch();
       fast_rows = (n_in / TF_ROWS) * TF_ROWS;

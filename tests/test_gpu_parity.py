@@ -561,3 +561,36 @@ def test_direct_input_path_stereo(oracle, mode, monkeypatch):
     assert b.state() == orc[0].state()
     assert worst <= 1e-6
     b.free()
+
+
+@pytest.mark.parametrize("ch,pad,skew", [(2, 2, 0), (2, 1, 1), (1, 1, 0), (1, 3, 1), (4, 2, 2), (8, 4, 1)])
+def test_resampler_float_rows_of_any_alignment(oracle, ch, pad, skew):
+    """Stream rows that are 16-, 8- or only 4-byte aligned (row stride = frames*channels + pad floats, buffers offset
+    by `skew` floats) go through the vectorised, the 8-byte and the scalar form of the layout stages."""
+    taps, filters, ns, n_in = 64, 32, 9, 300
+    ratio = f32(1.25)
+    cap = int(n_in * 1.25) + 8
+    x = np.stack([noise(n_in, ch, stream=700 + s, amp=0.8) for s in range(ns)])
+    in_stride, out_stride = n_in * ch + pad, cap * ch + pad
+    hin = np.zeros(ns * in_stride + skew, f32)
+    for s in range(ns):
+        hin[skew + s * in_stride: skew + s * in_stride + n_in * ch] = x[s]
+    d_in = espb.DeviceBuffer.from_numpy(hin)
+    d_out = espb.DeviceBuffer((ns * out_stride + skew) * 4)
+    d_out.zero()
+    b = espb.ResampleBatch(ns, ch, taps, filters, 1.0, 3, mode=espb.MODE_EXACT)
+    b.advance(taps / 2)
+    used, gen = b.process_interleaved_dev(d_in.ptr + 4 * skew, in_stride, n_in, d_out.ptr + 4 * skew, out_stride, cap,
+                                          ratio)
+    got = d_out.download(f32)
+    for s in range(ns):
+        o = oracle.resampler(ch, taps, filters, 1.0, 3)
+        o.advance(taps / 2)
+        yo, uo, go = o.process_interleaved(x[s], cap, ratio)
+        assert (used, gen) == (uo, go)
+        row = got[skew + s * out_stride: skew + (s + 1) * out_stride]
+        assert bits_equal(row[: gen * ch], yo), (s, ch, pad, skew)
+        assert not row[gen * ch:].any()  # nothing written past the generated frames
+    b.free()
+    d_in.free()
+    d_out.free()
