@@ -230,6 +230,8 @@ def main():
     ap.add_argument("--streams", type=int, default=STREAMS_PER_GPU, help="streams per GPU (default: the metric's 4096)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--mode", default="fast", choices=["fast", "exact"],
+                    help="arithmetic of the dot products: fast = FFMA2 chain (the metric), exact = un-fused, bit-exact")
     args = ap.parse_args()
     out = protect_stdout()
     if args.impl == "reference":
@@ -278,7 +280,8 @@ def main():
     fma_scalar, fma_packed = espb.measure_fp32_fma_peak2()
     tile_tf = espb.measure_fp32_tile_pattern()
 
-    ctx = espb.ResampleBatch(ns, CHANNELS, TAPS, FILTERS, 1.0, FLAGS, mode=espb.MODE_FAST)
+    ctx = espb.ResampleBatch(ns, CHANNELS, TAPS, FILTERS, 1.0, FLAGS,
+                             mode=espb.MODE_EXACT if args.mode == "exact" else espb.MODE_FAST)
     ctx.set_option(espb.OPT_PLAN_CACHE, 0)  # every step re-plans: schedule, upload and expansion are timed
     ctx.set_option(espb.OPT_KERNEL_TIMING, 1)
 
@@ -432,7 +435,9 @@ def main():
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "streams_per_gpu": ns, "channels": CHANNELS, "taps": TAPS,
                        "filters": FILTERS, "ratio": float(RATIO), "frames_in": N_IN, "frames_out": gen,
-                       "mode": "fast (tap-order FMA chain per accumulator, packed FFMA2; <=1e-6 of the reference)",
+                       "mode": ("fast (tap-order FMA chain per accumulator, packed FFMA2; <=1e-6 of the reference)"
+                                if args.mode == "fast" else
+                                "exact (tap-order FMUL+FADD per accumulator: bit-exact with the reference)"),
                        "signals": f"{DISTINCT} distinct streams (multitone + uniform noise, A=0.5) tiled",
                        "parallelism": f"streams sharded by index over {world} GPU(s), no data-path collective",
                        "l2": "inputs+outputs 3.0 GB per step >> 126 MB L2 (no flush needed)",

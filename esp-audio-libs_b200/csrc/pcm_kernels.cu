@@ -68,6 +68,10 @@ __global__ void __launch_bounds__(256)
   float *orow = out + (int64_t) blockIdx.y * out_row_floats;
   const uint32_t groups = vec_ok ? n / 4 : 0;
   const uint32_t stride = gridDim.x * blockDim.x;
+  // (consecutive lanes take consecutive 4-sample groups, so the 128-bit stores of a warp are one contiguous 512 bytes;
+  //  a 16-samples-per-thread form with 128-bit loads was measured slower here — its stores are 64 bytes apart — while
+  //  it is the faster one for the encoder below, whose wide side is the load)
+#pragma unroll 4
   for (uint32_t g = blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += stride) {
     const uint32_t *wp = reinterpret_cast<const uint32_t *>(irow) + (size_t) g * NBYTES;
     uint32_t w[NBYTES];
@@ -147,7 +151,29 @@ __global__ void __launch_bounds__(256)
   const uint32_t groups = vec_ok ? n / 4 : 0;
   const uint32_t stride = gridDim.x * blockDim.x;
   uint32_t clipped = 0;
-  for (uint32_t g = blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += stride) {
+  // 16 samples per thread and iteration, 128-bit accesses only: four loads, NBYTES stores (vec_ok == 2)
+  const uint32_t wide = (vec_ok == 2) ? n / 16 : 0;
+  for (uint32_t g = blockIdx.x * blockDim.x + threadIdx.x; g < wide; g += stride) {
+    uint32_t w[4 * NBYTES];
+    float4 f[4];
+#pragma unroll
+    for (int h = 0; h < 4; ++h)
+      f[h] = __ldg(reinterpret_cast<const float4 *>(irow) + (size_t) g * 4 + h);
+#pragma unroll
+    for (int h = 0; h < 4; ++h) {
+      int32_t v[4];
+      v[0] = quantise_one(f[h].x, c, clipped);
+      v[1] = quantise_one(f[h].y, c, clipped);
+      v[2] = quantise_one(f[h].z, c, clipped);
+      v[3] = quantise_one(f[h].w, c, clipped);
+      encode_words<NBYTES>(v, w + h * NBYTES);
+    }
+    uint4 *wp = reinterpret_cast<uint4 *>(orow) + (size_t) g * NBYTES;
+#pragma unroll
+    for (int i = 0; i < NBYTES; ++i)
+      wp[i] = make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
+  }
+  for (uint32_t g = wide * 4 + blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += stride) {
     const float4 f = __ldg(reinterpret_cast<const float4 *>(irow) + g);
     int32_t v[4];
     v[0] = quantise_one(f.x, c, clipped);
@@ -338,8 +364,10 @@ cudaError_t launch_q2f(const uint8_t *in, int64_t in_row_bytes, float *out, int6
   if (rows <= 0 || row_samples == 0)
     return cudaSuccess;
   const int nbytes = (bits + 7) / 8;
-  const int vec_ok = ((uintptr_t) in % 4 == 0) && (in_row_bytes % 4 == 0 || rows == 1) &&
-                     ((uintptr_t) out % 16 == 0) && (out_row_floats % 4 == 0 || rows == 1);
+  int vec_ok = ((uintptr_t) in % 4 == 0) && (in_row_bytes % 4 == 0 || rows == 1) &&
+               ((uintptr_t) out % 16 == 0) && (out_row_floats % 4 == 0 || rows == 1);
+  if (vec_ok && (uintptr_t) in % 16 == 0 && (in_row_bytes % 16 == 0 || rows == 1))
+    vec_ok = 2;  // 128-bit loads on the PCM side too
   dim3 grid(grid_x_for(row_samples, rows), rows);
   switch (nbytes) {
     case 1:
@@ -371,8 +399,10 @@ cudaError_t launch_f2q(const float *in, int64_t in_row_floats, uint8_t *out, int
     return cudaSuccess;
   const int nbytes = (bits + 7) / 8;
   const F2QConst c = make_f2q_const(bits);
-  const int vec_ok = ((uintptr_t) out % 4 == 0) && (out_row_bytes % 4 == 0 || rows == 1) &&
-                     ((uintptr_t) in % 16 == 0) && (in_row_floats % 4 == 0 || rows == 1);
+  int vec_ok = ((uintptr_t) out % 4 == 0) && (out_row_bytes % 4 == 0 || rows == 1) &&
+               ((uintptr_t) in % 16 == 0) && (in_row_floats % 4 == 0 || rows == 1);
+  if (vec_ok && (uintptr_t) out % 16 == 0 && (out_row_bytes % 16 == 0 || rows == 1))
+    vec_ok = 2;  // 128-bit stores on the PCM side too
   dim3 grid(grid_x_for(row_samples, rows), rows);
   switch (nbytes) {
     case 1:

@@ -13,8 +13,21 @@ namespace {
 __global__ void __launch_bounds__(256)
     espb_checksum_kernel(const uint32_t *__restrict__ w, uint64_t n, unsigned long long *__restrict__ sum) {
   unsigned long long acc = 0;
-  const uint64_t stride = (uint64_t) gridDim.x * blockDim.x;
-  for (uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+  const uint64_t stride = (uint64_t) gridDim.x * blockDim.x, tid = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+  // 128-bit loads over the 16-byte aligned middle, words before and after it one by one
+  uint64_t head = ((16 - ((uintptr_t) w & 15)) & 15) / 4;
+  if (head > n)
+    head = n;
+  const uint64_t n_vec = (n - head) / 4;
+  const uint4 *v = reinterpret_cast<const uint4 *>(w + head);
+#pragma unroll 4
+  for (uint64_t i = tid; i < n_vec; i += stride) {
+    const uint4 q = __ldg(v + i);
+    acc += (unsigned long long) q.x + q.y + q.z + q.w;
+  }
+  for (uint64_t i = tid; i < head; i += stride)
+    acc += __ldg(w + i);
+  for (uint64_t i = head + n_vec * 4 + tid; i < n; i += stride)
     acc += __ldg(w + i);
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1)
