@@ -19,18 +19,20 @@
 //        once per call (espb_expand_kernel) and shared by every CTA.
 // With these, one chunk (32 input rows) of either operand is ONE contiguous 16 KB block.
 //
-// Kernel.  A CTA owns one group (128 series) and sweeps "passes" of BPP consecutive output
-// blocks (8 outputs each, one block per consumer warp) over the union of their windows in
-// chunks of 32 rows, streamed through a 3-stage shared-memory ring with two TMA bulk copies
-// per chunk (cp.async.bulk -> mbarrier complete_tx; SASS UBLKCP).  There is no producer
-// warp (a ninth warp would not fit twice per SM next to 128-register consumers): the last
-// warp to finish reading a stage re-arms its mbarrier and issues the refill.  The BPP
-// warps wait on the stage's "full" mbarrier, and per input row do the rank-1 update
+// Kernel.  A CTA (BPP warps: 4 by default, four CTAs per SM) owns one group (128 series) and sweeps "passes" of BPP
+// consecutive output blocks (8 outputs each, one block per warp) over the union of their windows in chunks of 32
+// rows, streamed through a 2-stage shared-memory ring (3 stages for the 8-warp variant) with two TMA bulk copies per
+// chunk (cp.async.bulk -> mbarrier complete_tx; SASS UBLKCP).  There is no producer warp (a fifth warp would not fit
+// four times per SM next to 128-register consumers): the last warp to finish reading a stage re-arms its mbarrier
+// and issues the refill.  At set-up the CTA builds a table of what each warp does in each chunk (first / last
+// 4-row group inside its window, end-of-pass flag), so the main loop has no window arithmetic and no global loads.
+// The warps wait on the stage's "full" mbarrier, and per input row do the rank-1 update
 //     acc[series e][n][f] += G[row][n][f] * x[row][series e]
-// of a 4-series x 8-output x 2-filter register tile: x is one per-lane 128-bit LDS, G four
-// warp-uniform 128-bit LDS (broadcast) -> 64 FFMA per 5 LDS, 8 shared-memory wavefronts
-// per 64 FFMA, every accumulator visiting its taps in order.  No block-wide barrier in the
-// main loop; warps whose window does not reach a chunk (or a group of 8 rows) skip it.
+// of a 4-series x 8-output x 2-filter register tile: x is one per-lane 128-bit LDS, G four warp-uniform 128-bit LDS
+// (broadcast) -> 32 packed FFMA2 (64 FMUL+FADD in exact mode) per 5 LDS, 8 shared-memory wavefronts per row, every
+// accumulator visiting its taps in order.  No block-wide barrier in the main loop; warps whose window does not reach
+// a chunk (or a group of 4 rows) skip it.  At the end of a pass the block's 8 schedule entries are already in shared
+// memory (cp.async issued at the top of the last chunk); blend, then 128-bit stores in the caller's layout.
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
