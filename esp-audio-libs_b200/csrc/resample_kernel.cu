@@ -811,7 +811,7 @@ cudaError_t launch_resample(const ResampleParams &p, int bpp, int chunk_rows, bo
   q.out_vec = tm ? kOutVecTimeMajor : kOutVecNone;
   // 128-bit stores when the caller's layout keeps a lane's results contiguous and aligned
   if (!tm && (uintptr_t) p.out % 16 == 0 && p.out_ss % 4 == 0) {
-    if (p.out_fs == 1 && p.out_cs % 4 == 0)
+    if (p.out_fs == 1 && (p.out_cs % 4 == 0 || p.channels == 1))  // planar, or mono (no second channel plane)
       q.out_vec = kOutVecPlanar;
     else if (p.out_cs == 1 && p.out_fs == p.channels && p.channels == 2)
       q.out_vec = kOutVecStereo;

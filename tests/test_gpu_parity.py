@@ -563,7 +563,8 @@ def test_direct_input_path_stereo(oracle, mode, monkeypatch):
     b.free()
 
 
-@pytest.mark.parametrize("ch,pad,skew", [(2, 2, 0), (2, 1, 1), (1, 1, 0), (1, 3, 1), (4, 2, 2), (8, 4, 1)])
+@pytest.mark.parametrize("ch,pad,skew", [(2, 2, 0), (2, 1, 1), (1, 1, 0), (1, 3, 1), (4, 2, 2), (8, 4, 1), (1, 4, 0), (2, 4, 0),
+                                         (4, 4, 0), (8, 8, 4)])
 def test_resampler_float_rows_of_any_alignment(oracle, ch, pad, skew):
     """Stream rows that are 16-, 8- or only 4-byte aligned (row stride = frames*channels + pad floats, buffers offset
     by `skew` floats) go through the vectorised, the 8-byte and the scalar form of the layout stages."""
