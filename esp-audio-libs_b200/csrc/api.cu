@@ -1377,6 +1377,31 @@ int espb_plan_schedule(int numTaps, int numFilters, int flags, float outputOffse
   return ESPB_OK;
 }
 
+int espb_plan_passes(int numTaps, int numFilters, int flags, float outputOffset, int inputIndex, int numInputFrames,
+                     int numOutputFrames, float ratio, int blocks_per_pass, int chunk_rows, int split_at_zero,
+                     int32_t *chunk_start, int32_t *chunk_pass, int max_chunks, int32_t *pass_chunk_begin,
+                     int max_passes) {
+  if ((numTaps & 3) || numTaps <= 0 || numTaps > 1024 || numFilters < 2 || numFilters > 1024 || blocks_per_pass <= 0 ||
+      chunk_rows <= 0 || chunk_rows > kChunkRows)
+    return fail(ESPB_ERR_ARG, "plan_passes: invalid argument");
+  Schedule s;
+  build_schedule(ArtGeometry{numTaps, numFilters, flags}, ArtState{outputOffset, inputIndex}, numInputFrames,
+                 numOutputFrames, ratio, s);
+  PassPlan plan;
+  build_pass_plan(s, numTaps, blocks_per_pass, chunk_rows, plan, split_at_zero != 0);
+  const int n_chunks = (int) plan.chunks.size(), n_passes = plan.n_passes();
+  for (int i = 0; i < n_chunks && i < max_chunks; ++i) {
+    if (chunk_start)
+      chunk_start[i] = plan.chunks[i].j_start;
+    if (chunk_pass)
+      chunk_pass[i] = plan.chunks[i].pass;
+  }
+  for (int i = 0; i <= n_passes && i < max_passes; ++i)
+    if (pass_chunk_begin)
+      pass_chunk_begin[i] = plan.pass_chunk_begin[i];
+  return n_chunks;
+}
+
 int espb_plan_policy(const EspbResamplerConfiguration *config, EspbBiquadCoefficients *coeffs, float *sample_ratio,
                      float *art_lowpass, int *art_flags) {
   if (!config)
