@@ -39,10 +39,12 @@ __global__ void __launch_bounds__(128, 4) probe(float *out, int iters, float see
 #pragma unroll
       for (int jj = 0; jj < RG; ++jj) {
         float4 xv, g0, g1, g2, g3;
-        if (MODE == 1) {
+        if (MODE == 1 || MODE == 3) {
           xv = *reinterpret_cast<const float4 *>(xb + jj * 128);
           const float4 *gp = reinterpret_cast<const float4 *>(gb + jj * BPP * 16);
           g0 = gp[0], g1 = gp[1], g2 = gp[2], g3 = gp[3];
+          if (MODE == 3)  // pin the row order of the FFMA2 blocks (volatile asm statements keep their order)
+            asm volatile("" : "+f"(xv.x), "+f"(xv.z), "+f"(g0.x));
         } else {
           xv = xr, g0 = gr[0], g1 = gr[1], g2 = gr[2], g3 = gr[3];
           asm volatile("" : "+f"(xr.x), "+f"(gr[jj & 3].x));  // keep the operands opaque
@@ -69,6 +71,47 @@ __global__ void __launch_bounds__(128, 4) probe(float *out, int iters, float see
 #pragma unroll
             for (int n = 0; n < 8; ++n)
               acc[e][n] = fma2(gg[n], x4[e], acc[e][n]);
+        } else if (ORDER >= 3 && ORDER <= 7) {
+          // pair = two series of one (output, filter): x is the 64-bit operand, the coefficient the broadcast scalar
+          const float g16[16] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w,
+                                 g2.x, g2.y, g2.z, g2.w, g3.x, g3.y, g3.z, g3.w};
+          const float2 xp[2] = {make_float2(xv.x, xv.y), make_float2(xv.z, xv.w)};
+          float2 *accp = &acc[0][0];  // 32 accumulators viewed as [pair p][k = 2n + f]
+          if (ORDER == 3) {
+#pragma unroll
+            for (int p = 0; p < 2; ++p)
+#pragma unroll
+              for (int k = 0; k < 16; ++k)
+                accp[p * 16 + k] = __ffma2_rn(xp[p], make_float2(g16[k], g16[k]), accp[p * 16 + k]);
+          } else if (ORDER == 5) {  // per G vector (4 scalars): both pairs
+#pragma unroll
+            for (int kb = 0; kb < 4; ++kb)
+#pragma unroll
+              for (int p = 0; p < 2; ++p)
+#pragma unroll
+                for (int k = kb * 4; k < kb * 4 + 4; ++k)
+                  accp[p * 16 + k] = __ffma2_rn(xp[p], make_float2(g16[k], g16[k]), accp[p * 16 + k]);
+          } else if (ORDER == 6) {  // per half of the G row (8 scalars): both pairs
+#pragma unroll
+            for (int kb = 0; kb < 2; ++kb)
+#pragma unroll
+              for (int p = 0; p < 2; ++p)
+#pragma unroll
+                for (int k = kb * 8; k < kb * 8 + 8; ++k)
+                  accp[p * 16 + k] = __ffma2_rn(xp[p], make_float2(g16[k], g16[k]), accp[p * 16 + k]);
+          } else if (ORDER == 7) {  // accumulators laid out [k][p] instead of [p][k]
+#pragma unroll
+            for (int p = 0; p < 2; ++p)
+#pragma unroll
+              for (int k = 0; k < 16; ++k)
+                accp[k * 2 + p] = __ffma2_rn(xp[p], make_float2(g16[k], g16[k]), accp[k * 2 + p]);
+          } else if (ORDER == 4) {
+#pragma unroll
+            for (int k = 0; k < 16; ++k)
+#pragma unroll
+              for (int p = 0; p < 2; ++p)
+                accp[p * 16 + k] = __ffma2_rn(xp[p], make_float2(g16[k], g16[k]), accp[p * 16 + k]);
+          }
         } else {  // 2x2 blocks: (n, n+1) x (e, e+1)
 #pragma unroll
           for (int n = 0; n < 8; n += 2)
@@ -130,8 +173,10 @@ int main() {
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
   run<1, 4, 0>(sms, 4, 200);
-  run<2, 4, 0>(sms, 4, 200);
-  run<2, 4, 0>(sms, 2, 200);
-  run<1, 4, 0>(sms, 2, 200);
+  run<3, 4, 0>(sms, 4, 200);
+  run<3, 4, 3>(sms, 4, 200);
+  run<3, 8, 3>(sms, 4, 200);
+  run<3, 4, 4>(sms, 4, 200);
+  run<3, 4, 7>(sms, 4, 200);
   return 0;
 }
