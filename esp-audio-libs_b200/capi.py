@@ -115,6 +115,7 @@ def lib():
         "espb_biquad_free": (None, [vp]),
         "espb_biquad_reset": (i, [vp, vp]),
         "espb_biquad_apply_buffer": (i, [vp, vp, C.POINTER(_Layout), i, i, vp]),
+        "espb_biquad_apply_samples": (i, [vp, vp, vp]),
         "espb_biquad_set_time_blocks": (i, [vp, i, i]),
         "espb_resampler_set_biquad_time_blocks": (i, [vp, i, i]),
         "espb_biquad_get_state": (i, [vp, vp]),
@@ -542,6 +543,15 @@ class BiquadBatch:
         lay = _Layout(*layout)
         _check(lib().espb_biquad_apply_buffer(self.h, d_buf, C.byref(lay), channels, n_samples, stream),
                "biquad_apply_buffer")
+
+    def apply_samples(self, x):
+        """One sample per series (biquad_apply_sample for the whole bank); returns the filtered samples."""
+        x = np.ascontiguousarray(x, np.float32)
+        d = DeviceBuffer.from_numpy(x)
+        _check(lib().espb_biquad_apply_samples(self.h, d.ptr, None), "biquad_apply_samples")
+        y = d.download(np.float32, x.size)
+        d.free()
+        return y
 
     def apply_interleaved(self, x, channels):
         """x: (num_streams, n*channels) float32, filtered in place on the device; returns the result."""

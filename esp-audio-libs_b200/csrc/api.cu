@@ -1224,6 +1224,13 @@ int espb_biquad_apply_buffer(EspbBiquadBatch *f, float *buf, const EspbLayout *l
   return ESPB_OK;
 }
 
+// biquad_apply_sample (art_biquad.cpp:55-69) for every series at once: samples[q] is filtered in place through
+// series q's sections, the delays advance by one sample.
+int espb_biquad_apply_samples(EspbBiquadBatch *f, float *samples, void *stream) {
+  const EspbLayout one_per_series = {1, 1, 1};
+  return espb_biquad_apply_buffer(f, samples, &one_per_series, 1, 1, stream);
+}
+
 int espb_biquad_set_time_blocks(EspbBiquadBatch *f, int block_rows, int warmup_rows) {
   if (!f || block_rows < 0 || warmup_rows < 0 || block_rows % 32 || warmup_rows % 32)
     return fail(ESPB_ERR_ARG, "biquad_set_time_blocks: rows must be non-negative multiples of 32");

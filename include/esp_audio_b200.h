@@ -177,6 +177,9 @@ int espb_biquad_reset(EspbBiquadBatch *f, void *stream);
  * (stream q / channels, channel q % channels) of the layout. */
 int espb_biquad_apply_buffer(EspbBiquadBatch *f, float *buf, const EspbLayout *layout, int channels, int num_samples,
                              void *stream);
+/* biquad_apply_sample (art_biquad.cpp:55-69), batched: one new sample per series (samples[q], device memory, filtered
+ * in place); every series' delays advance by one step.  A latency-bound call — use apply_buffer for throughput. */
+int espb_biquad_apply_samples(EspbBiquadBatch *f, float *samples, void *stream);
 /* Long single streams: filter time blocks of `block_rows` frames in parallel, each after re-running the
  * recurrence over the `warmup_rows` frames before it from a zero state (multiples of 32; 0/0 = off, the
  * default: one exact sequential run per series).  The two trajectories merge bit-exactly once they round to

@@ -70,6 +70,10 @@ inline int biquad_apply_buffer(Biquad *f, float *buffer, int64_t streamStride, i
   EspbLayout l = {streamStride, 1, channels};
   return espb_biquad_apply_buffer(f, buffer, &l, channels, num_samples, stream);
 }
+// include/art_biquad.h:36 — one new sample per series of the bank (device memory, in place)
+inline int biquad_apply_sample(Biquad *f, float *samples, void *stream = nullptr) {
+  return espb_biquad_apply_samples(f, samples, stream);
+}
 inline void biquad_free(Biquad *f) { espb_biquad_free(f); }
 
 }  // namespace art_resampler

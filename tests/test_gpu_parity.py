@@ -595,3 +595,18 @@ def test_resampler_float_rows_of_any_alignment(oracle, ch, pad, skew):
     b.free()
     d_in.free()
     d_out.free()
+
+
+def test_biquad_apply_samples_matches_sample_by_sample_reference(oracle):
+    """biquad_apply_sample (art_biquad.cpp:55-69) for a bank of series, one sample per call, bit-exact, and
+    interchangeable with apply_buffer (same state)."""
+    n_series, steps = 300, 40
+    c = espb.biquad_lowpass(0.2274)
+    bank = espb.BiquadBatch(n_series, 2, c)
+    x = np.stack([noise(steps, 1, stream=900 + q, amp=0.9) for q in range(n_series)])  # (series, steps)
+    got = np.stack([bank.apply_samples(x[:, t]) for t in range(steps)], axis=1)
+    for q in (0, 1, 127, 128, 299):
+        s1, s2 = oracle.biquad(c), oracle.biquad(c)  # the wrapper's cascade: two sections, sample by sample
+        want = np.array([s2.apply_sample(s1.apply_sample(v)) for v in x[q]], np.float32)
+        assert bits_equal(got[q], want), q
+    bank.free()
