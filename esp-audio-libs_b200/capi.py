@@ -130,6 +130,8 @@ def lib():
         "espb_resampler_policy": (i, [vp, C.POINTER(_Coeffs), C.POINTER(f), C.POINTER(f), C.POINTER(i)]),
         "espb_resampler_resample": (_WResults, [vp, vp, i64, vp, i64, sz, sz, f, vp, vp]),
         "espb_resampler_resample_host": (_WResults, [vp, vp, i64, vp, i64, sz, sz, f, vp]),
+        "espb_resampler_resample_async": (_WResults, [vp, vp, i64, vp, i64, sz, sz, f, vp]),
+        "espb_resampler_clipped_dev": (vp, [vp]),
         "espb_plan_filter_bank": (i, [i, i, f, i, vp, C.POINTER(i)]),
         "espb_plan_schedule": (i, [i, i, i, f, i, i, i, f, C.POINTER(C.c_uint), C.POINTER(C.c_uint), C.POINTER(f),
                                    C.POINTER(i), vp, vp, vp, vp]),
@@ -732,6 +734,18 @@ class Resampler:
         if _err():
             raise EspbError(f"espb_resampler_resample: {_err()}")
         return self._results(r, per)
+
+    def resample_dev_async(self, d_in, in_stride_bytes, d_out, out_stride_bytes, in_frames, out_free, gain_db=0.0,
+                           stream=None):
+        """Enqueue only; clip counts stay on the device (clipped_dev())."""
+        r = lib().espb_resampler_resample_async(self.h, d_in, in_stride_bytes, d_out, out_stride_bytes, in_frames,
+                                                out_free, gain_db, stream)
+        if _err():
+            raise EspbError(f"espb_resampler_resample_async: {_err()}")
+        return self._results(r, None)
+
+    def clipped_dev(self):
+        return lib().espb_resampler_clipped_dev(self.h)
 
     def resample_host_ptr(self, h_in, in_stride_bytes, h_out, out_stride_bytes, in_frames, out_free, gain_db=0.0):
         per = np.zeros(self.num_streams, np.uint32)

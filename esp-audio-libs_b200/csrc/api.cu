@@ -1736,6 +1736,31 @@ EspbResamplerResults espb_resampler_resample(EspbResampler *r, const uint8_t *in
   return wrapper_finish(r, wc, clipped_per_stream_host);
 }
 
+// The same call without the synchronisation: everything is enqueued on `stream` and the frame counts (known from the
+// schedule) are returned at once, so the host can plan the next call while the device works on this one.  The clip
+// counts of the call stay on the device (espb_resampler_clipped_dev) until the next call on this handle.
+EspbResamplerResults espb_resampler_resample_async(EspbResampler *r, const uint8_t *in, int64_t in_stride_bytes,
+                                                   uint8_t *out, int64_t out_stride_bytes,
+                                                   size_t input_frames_available, size_t output_frames_free,
+                                                   float gain_db, void *stream) {
+  EspbResamplerResults none{};
+  if (!r) {
+    fail(ESPB_ERR_ARG, "resample_async: NULL");
+    return none;
+  }
+  cudaStream_t s = as_stream(stream);
+  WrapperCall wc;
+  if (wrapper_plan(r, input_frames_available, output_frames_free, s, &wc) != ESPB_OK)
+    return none;
+  if (wrapper_run_range(r, 0, r->num_streams, in, in_stride_bytes, out, out_stride_bytes, wc, output_frames_free,
+                        gain_db, s, false) != ESPB_OK)
+    return none;
+  memset(r->clipped_host, 0, r->num_streams * sizeof(uint32_t));
+  return wrapper_finish(r, wc, nullptr);  // clipped_samples = 0: not known yet
+}
+
+const uint32_t *espb_resampler_clipped_dev(EspbResampler *r) { return r ? r->clipped.as<uint32_t>() : nullptr; }
+
 EspbResamplerResults espb_resampler_resample_host(EspbResampler *r, const uint8_t *in, int64_t in_stride_bytes,
                                                   uint8_t *out, int64_t out_stride_bytes,
                                                   size_t input_frames_available, size_t output_frames_free,

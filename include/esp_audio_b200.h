@@ -250,6 +250,16 @@ EspbResamplerResults espb_resampler_resample(EspbResampler *r, const uint8_t *in
                                              uint8_t *out, int64_t out_stride_bytes, size_t input_frames_available,
                                              size_t output_frames_free, float gain_db,
                                              uint32_t *clipped_per_stream_host, void *stream);
+/* Same call without the synchronisation (device buffers): all work is enqueued on `stream` and the frame counts —
+ * known from the signal-independent schedule — are returned immediately, so a caller can prepare the next call while
+ * the device runs this one.  clipped_samples is 0 in the result; the per-stream clip counts of the call are in device
+ * memory (espb_resampler_clipped_dev, num_streams uint32) once `stream` has reached this point, until the next call
+ * on the handle overwrites them. */
+EspbResamplerResults espb_resampler_resample_async(EspbResampler *r, const uint8_t *in, int64_t in_stride_bytes,
+                                                   uint8_t *out, int64_t out_stride_bytes,
+                                                   size_t input_frames_available, size_t output_frames_free,
+                                                   float gain_db, void *stream);
+const uint32_t *espb_resampler_clipped_dev(EspbResampler *r);
 /* Same call with HOST buffers: stages through pinned memory, copies host->device,
  * processes, copies device->host; stream slabs are pipelined over internal CUDA streams. */
 EspbResamplerResults espb_resampler_resample_host(EspbResampler *r, const uint8_t *in, int64_t in_stride_bytes,

@@ -610,3 +610,33 @@ def test_biquad_apply_samples_matches_sample_by_sample_reference(oracle):
         want = np.array([s2.apply_sample(s1.apply_sample(v)) for v in x[q]], np.float32)
         assert bits_equal(got[q], want), q
     bank.free()
+
+
+def test_wrapper_async_calls_match_synchronous_ones(oracle):
+    """espb_resampler_resample_async: a stream of calls enqueued without synchronising gives the same bytes, frame
+    counts and (device-side) clip counts as the synchronous call."""
+    ns, ch, frames, cap = 50, 2, 1500, 1800
+    rng = np.random.default_rng(5)
+    pcm = (rng.normal(0, 0.5, (ns, frames * ch)).clip(-1.2, 1.2) * 30000).clip(-32768, 32767).astype(np.int16)
+    outs = {}
+    for kind in ("sync", "async"):
+        r = espb.Resampler(ns, frames * ch, cap * ch, 44100, 48000, 16, 16, ch, True, True, 64, 64, mode=espb.MODE_EXACT)
+        d_in = espb.DeviceBuffer.from_numpy(pcm.view(np.uint8))
+        d_out = espb.DeviceBuffer(ns * cap * ch * 2)
+        got = []
+        for call in range(3):
+            d_out.zero()
+            if kind == "sync":
+                res = r.resample_dev(d_in.ptr, frames * ch * 2, d_out.ptr, cap * ch * 2, frames, cap, 3.0)
+                clips = res["clipped_per_stream"].copy()
+            else:
+                res = r.resample_dev_async(d_in.ptr, frames * ch * 2, d_out.ptr, cap * ch * 2, frames, cap, 3.0)
+                clips = np.zeros(ns, np.uint32)
+                espb.capi._check(espb.lib().espb_memcpy_d2h(clips.ctypes.data, r.clipped_dev(), ns * 4, None), "d2h")
+                espb.capi._check(espb.lib().espb_stream_sync(None), "sync")
+            got.append((res["frames_used"], res["frames_generated"], clips, d_out.download(np.uint8)))
+        outs[kind] = got
+        r.free()
+    for a, b in zip(outs["sync"], outs["async"]):
+        assert a[0] == b[0] and a[1] == b[1] and bits_equal(a[2], b[2]) and bits_equal(a[3], b[3])
+    assert sum(int(c[2].sum()) for c in outs["sync"]) > 0  # the +3 dB gain does clip some samples
