@@ -121,6 +121,15 @@ class Resampler {
     return espb_resampler_resample(impl_, input_buffer, in_stride_bytes, output_buffer, out_stride_bytes,
                                    input_frames_available, output_frames_free, gain_db, nullptr, stream);
   }
+  /// device buffers, enqueue only: frame counts are returned at once, clipped_samples is 0 (the per-stream counts
+  /// are at clipped_dev() once the stream has reached this point)
+  ResamplerResults resample_async(const uint8_t *input_buffer, int64_t in_stride_bytes, uint8_t *output_buffer,
+                                  int64_t out_stride_bytes, size_t input_frames_available, size_t output_frames_free,
+                                  float gain_db, void *stream = nullptr) {
+    return espb_resampler_resample_async(impl_, input_buffer, in_stride_bytes, output_buffer, out_stride_bytes,
+                                         input_frames_available, output_frames_free, gain_db, stream);
+  }
+  const uint32_t *clipped_dev() { return espb_resampler_clipped_dev(impl_); }
   /// host buffers (staged, copied and pipelined internally)
   ResamplerResults resample_host(const uint8_t *input_buffer, int64_t in_stride_bytes, uint8_t *output_buffer,
                                  int64_t out_stride_bytes, size_t input_frames_available,
