@@ -1060,6 +1060,16 @@ EspbResampleResult espb_resampleProcessInterleavedHost(EspbResampleBatch *c, con
     return res;
   }
   cudaStream_t s0 = hs->pipe.s[0];
+  const int per = pick_slab_streams(c->num_streams, c->channels);
+  if (in_row) {  // the first slab's copy needs no plan: it runs while the host builds the schedule
+    const int ns0 = per <= c->num_streams ? per : c->num_streams;
+    e = copy_rows_async(hs->stage_in.as<float>(), in_row * sizeof(float), in, (size_t) in_stream_stride * sizeof(float),
+                        in_row * sizeof(float), ns0, cudaMemcpyHostToDevice, s0);
+    if (e != cudaSuccess) {
+      cuda_fail(e, "h2d");
+      return res;
+    }
+  }
   {
     const EspbLayout stage_layout = {(int64_t) in_row, 1, ch};
     if (prepare_call(c, numInputFrames, numOutputFrames, ratio, s0,
@@ -1073,7 +1083,6 @@ EspbResampleResult espb_resampleProcessInterleavedHost(EspbResampleBatch *c, con
       return res;
   }
   cudaEventRecord(hs->pipe.ready, s0);
-  const int per = pick_slab_streams(c->num_streams, c->channels);
   EspbLayout il = {(int64_t) in_row, 1, ch}, ol = {(int64_t) out_cap_row, 1, ch};
   int slab = 0;
   for (int st0 = 0; st0 < c->num_streams; st0 += per, ++slab) {
@@ -1082,7 +1091,7 @@ EspbResampleResult espb_resampleProcessInterleavedHost(EspbResampleBatch *c, con
     cudaStreamWaitEvent(s, hs->pipe.ready, 0);
     float *din = hs->stage_in.as<float>() + (size_t) st0 * in_row;
     float *dout = hs->stage_out.as<float>() + (size_t) st0 * out_cap_row;
-    if (in_row) {
+    if (in_row && slab > 0) {  // (slab 0 was copied before the planning)
       e = copy_rows_async(din, in_row * sizeof(float), in + (size_t) st0 * in_stream_stride,
                           (size_t) in_stream_stride * sizeof(float), in_row * sizeof(float), ns,
                           cudaMemcpyHostToDevice, s);
