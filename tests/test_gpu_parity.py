@@ -640,3 +640,102 @@ def test_wrapper_async_calls_match_synchronous_ones(oracle):
     for a, b in zip(outs["sync"], outs["async"]):
         assert a[0] == b[0] and a[1] == b[1] and bits_equal(a[2], b[2]) and bits_equal(a[3], b[3])
     assert sum(int(c[2].sum()) for c in outs["sync"]) > 0  # the +3 dB gain does clip some samples
+
+
+# ---------------------------------------------------------------- full-size properties (BASELINE configs[2..4])
+def _composed_oracle(oracle, raw_row, frames, ch, sb, db, taps, filters, pol, cap, gain_db=0.0):
+    """One stream through the oracle's stages with the policy the library reports (any channel count)."""
+    o = oracle.resampler(ch, taps, filters, float(pol["art_lowpass"]), pol["art_flags"])
+    o.advance(taps / 2.0)
+    xf = oracle.quantized_to_float(raw_row, frames * ch, sb, gain_db)
+    if pol["filter"] == "pre":
+        for c in range(ch):
+            for _ in range(2):
+                oracle.biquad(pol["coeffs"], 1.0).apply_buffer(xf[c:], ch, n=frames)
+    yf, used, gen = o.process_interleaved(xf, cap, pol["sample_ratio"])
+    yf = np.ascontiguousarray(yf)
+    if pol["filter"] == "post":
+        for c in range(ch):
+            for _ in range(2):
+                oracle.biquad(pol["coeffs"], 1.0).apply_buffer(yf[c:], ch, n=gen)
+    q, clipped = oracle.float_to_quantized(yf, db)
+    return q, used, gen, clipped
+
+
+@pytest.mark.parametrize("name,ns,ch,sr,dr,bits,frames", [
+    ("C3", 16384, 1, 16000, 48000, 16, 16000),   # 16 kHz -> 48 kHz mono voice, int16 in / out, post biquad
+    ("C5 shard", 8192, 2, 48000, 44100, 32, 24000),  # 65536 / 8 stereo streams 48 -> 44.1 kHz (0.5 s per call)
+])
+def test_full_size_wrapper_configs(oracle, name, ns, ch, sr, dr, bits, frames):
+    """BASELINE configs[2] and [4] at their stream counts, exact mode: streams with identical input give identical
+    bytes wherever they sit in the batch, sampled streams are bit-exact with the composed CPU pipeline (PCM bytes and
+    clip counts), nothing is written past the generated frames, and the batch clip total is the sum of the rows."""
+    nb = bits // 8
+    rng = np.random.default_rng(ns)
+    distinct = 8
+    amp = 2 ** (bits - 1) * 0.6
+    base = (rng.normal(0, 0.45, (distinct, frames * ch)) * amp).clip(-2 ** (bits - 1), 2 ** (bits - 1) - 1).astype(np.int64)
+    raw8 = np.zeros((distinct, frames * ch * nb), np.uint8)
+    for b in range(nb):
+        raw8[:, b::nb] = (base >> (8 * b)) & 0xFF
+    raw = np.tile(raw8, (ns // distinct, 1))
+    cap = int(frames * dr / sr) + 64
+    r = espb.Resampler(ns, frames * ch, cap * ch, sr, dr, bits, bits, ch, True, True, 256, 256, mode=espb.MODE_EXACT)
+    pol = r.policy()
+    out, res = r.resample(raw, frames, cap, 2.0)   # +2 dB: some samples clip
+    gen = res["frames_generated"]
+    assert res["frames_used"] == frames and gen > 0
+    row_bytes = gen * ch * nb
+    sums = out[:, :row_bytes].astype(np.uint64).sum(axis=1)
+    for s in range(distinct):
+        assert np.all(sums[s::distinct] == sums[s])
+        assert np.all(res["clipped_per_stream"][s::distinct] == res["clipped_per_stream"][s])
+    assert not out[:, row_bytes:].any()
+    assert int(res["clipped_per_stream"].astype(np.uint64).sum()) == res["clipped_samples"] > 0
+    for s in (0, 3, ns - 1):
+        q, used, g2, clipped = _composed_oracle(oracle, raw[s], frames, ch, bits, bits, 256, 256, pol, cap, 2.0)
+        assert (used, g2) == (frames, gen)
+        assert bits_equal(out[s, :row_bytes], q), (name, s)
+        assert int(res["clipped_per_stream"][s]) == clipped
+    r.free()
+
+
+def test_full_size_long_stream_config(oracle):
+    """BASELINE configs[3]: 96 -> 44.1 kHz, 8 channels, 24-bit, 1024 taps, long streams.  Ten seconds per call: the
+    time-block form of the pre-filter gives the same bytes as the sequential one (exact mode), chunked calls give the
+    same bytes as one call, and the first second is bit-exact with the composed CPU pipeline."""
+    ns, ch, sr, dr, bits, taps, frames = 4, 8, 96000, 44100, 24, 1024, 960000
+    rng = np.random.default_rng(4)
+    base = (rng.normal(0, 0.3, (ns, frames * ch)) * 2 ** 23).clip(-2 ** 23, 2 ** 23 - 1).astype(np.int64)
+    raw = np.zeros((ns, frames * ch * 3), np.uint8)
+    for b in range(3):
+        raw[:, b::3] = (base >> (8 * b)) & 0xFF
+    del base
+    cap = int(frames * dr / sr) + 64
+
+    def run(blocks, chunks):
+        r = espb.Resampler(ns, (frames // chunks) * ch, (cap // chunks + 64) * ch, sr, dr, bits, bits, ch, True, True,
+                           taps, 256, mode=espb.MODE_EXACT)
+        if blocks:
+            r.set_biquad_time_blocks(*blocks)
+        parts, per = [], frames // chunks
+        for k in range(chunks):
+            seg = np.ascontiguousarray(raw[:, k * per * ch * 3:(k + 1) * per * ch * 3])
+            out, res = r.resample(seg, per, cap // chunks + 64, 0.0)
+            assert res["frames_used"] == per
+            parts.append(out[:, : res["frames_generated"] * ch * 3])
+        pol = r.policy()
+        r.free()
+        return np.concatenate(parts, axis=1), pol
+
+    seq, pol = run(None, 1)
+    blk, _ = run((8192, 1024), 1)
+    assert seq.shape == blk.shape and bits_equal(seq, blk)
+    chunked, _ = run(None, 10)
+    assert bits_equal(seq, chunked)
+    # the first second against the CPU pipeline (one stream; 8 channels x 44100 outputs x 2048 taps on the host)
+    one = 96000
+    q, used, gen, _ = _composed_oracle(oracle, raw[1, : one * ch * 3], one, ch, bits, bits, taps, 256, pol,
+                                       int(one * dr / sr) + 64)
+    settle = gen - 600  # the one-shot CPU run has no frames after `one`, the 10 s run has: compare what both know
+    assert bits_equal(seq[1, : settle * ch * 3], q[: settle * ch * 3])
