@@ -12,6 +12,8 @@
 //   include/art_biquad.h:30-36      biquad_init / lowpass / highpass / apply
 //   include/quantization_utils.h:15-25
 //   include/resampler.h:36-80       resampler::Resampler
+//   include/dsp.h:66-93             dsps_add_s16_ansi / dsps_mulc_s16_ansi
+//   include/wav_decoder.h:54-89     wav_decoder::WAVDecoder
 #include <pthread.h>
 #include <stdint.h>
 #include <string.h>
