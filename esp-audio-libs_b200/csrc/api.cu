@@ -326,6 +326,9 @@ struct EspbResampleBatch {
   DevBuf stage_in, stage_out;
   HostPipe pipe;
   // direct input (interleaved stereo float, see espb_resample_kernel<..., DIRECT>): decided per call
+  // without SUBSAMPLE_INTERPOLATE an output is one dot product: its own kernel and half-size G rows (default geometry)
+  bool non_interp = false;
+  int g_row_floats() const { return non_interp ? kGRowFloatsNI : kGRowFloats; }
   bool direct_ok = false;    // ESPB_DIRECT=1 switches it on
   bool direct_call = false;  // this call's plan is split at input frame 0 and its input is read through TMA
   // options
@@ -375,7 +378,8 @@ int prepare_call(EspbResampleBatch *c, int n_in, int n_out, float ratio, cudaStr
     c->state_event_pending = false;
   }
   // direct input needs the default kernel geometry and a carry that lies inside this call's input
-  want_direct = want_direct && c->direct_ok && c->bpp == 4 && c->chunk_rows == 32 && n_in >= c->geo.taps;
+  want_direct = want_direct && c->direct_ok && !c->non_interp && c->bpp == 4 && c->chunk_rows == 32 &&
+                n_in >= c->geo.taps;
   ScheduleKey k;
   k.offset_bits = f2u(c->state.offset);
   k.ratio_bits = f2u(ratio);
@@ -449,7 +453,7 @@ int prepare_call(EspbResampleBatch *c, int n_in, int n_out, float ratio, cudaStr
 // Number of passes per time slab so that the expanded coefficients fit the G budget.
 int passes_per_slab(const EspbResampleBatch *c) {
   const int n_passes = c->plan.n_passes();
-  const size_t chunk_bytes = g_chunk_floats(c->bpp, c->chunk_rows) * sizeof(float);
+  const size_t chunk_bytes = g_chunk_floats(c->bpp, c->chunk_rows, c->g_row_floats()) * sizeof(float);
   const size_t total = c->plan.chunks.size() * chunk_bytes;
   if (total <= c->g_budget_bytes || n_passes <= 1)
     return n_passes;
@@ -462,11 +466,11 @@ int passes_per_slab(const EspbResampleBatch *c) {
 int ensure_g(EspbResampleBatch *c, int chunk_first, int chunk_end, cudaStream_t stream) {
   if (c->g_resident_first == chunk_first && c->g_resident_end == chunk_end)
     return ESPB_OK;
-  const size_t chunk_floats = g_chunk_floats(c->bpp, c->chunk_rows);
+  const size_t chunk_floats = g_chunk_floats(c->bpp, c->chunk_rows, c->g_row_floats());
   CU_TRY(c->d_G.reserve((size_t) (chunk_end - chunk_first) * chunk_floats * sizeof(float)), "cudaMalloc G");
   CU_TRY(launch_expand(c->bank.as<float>(), c->d_outs.as<OutEntry>(), c->d_chunks.as<ChunkEntry>(),
                        c->d_G.as<float>(), chunk_first, chunk_end - chunk_first, (int) c->sched.generated,
-                       c->geo.taps, c->bpp, c->chunk_rows, c->direct_call, stream),
+                       c->geo.taps, c->bpp, c->chunk_rows, c->direct_call, stream, c->g_row_floats()),
          "expand kernel");
   c->g_resident_first = chunk_first;
   c->g_resident_end = chunk_end;
@@ -738,7 +742,8 @@ int run_series_range(EspbResampleBatch *c, int series_first, int n_series, const
         ev_after = c->ev_pool[c->ev_used + 1];
         c->ev_used += 2;
       }
-      CU_TRY(launch_resample(p, c->bpp, c->chunk_rows, c->mode == ESPB_MODE_EXACT, stream, direct ? &din : nullptr),
+      CU_TRY(launch_resample(p, c->bpp, c->chunk_rows, c->mode == ESPB_MODE_EXACT, stream, direct ? &din : nullptr,
+                             c->non_interp),
              "resample kernel");
       if (ev_after)
         CU_TRY(cudaEventRecord(ev_after, stream), "cudaEventRecord");
@@ -853,6 +858,7 @@ EspbResampleBatch *espb_resampleInit(int num_streams, int numChannels, int numTa
     const long cr = env_long("ESPB_CHUNK_ROWS", 32);
     c->chunk_rows = (cr == 16 || ((cr == 24 || cr == 36) && c->bpp == 4)) ? (int) cr : 32;
   }
+  c->non_interp = (flags & kFlagInterpolate) == 0 && c->bpp == 4 && c->chunk_rows == 32 && env_long("ESPB_NI", 1) != 0;
   long gb = env_long("ESPB_G_MBYTES", 0);
   if (gb > 0)
     c->g_budget_bytes = (size_t) gb << 20;

@@ -55,14 +55,17 @@ struct ResampleDirectParams {
 };
 enum OutVec : int { kOutVecNone = 0, kOutVecPlanar = 1, kOutVecStereo = 2, kOutVecFrame4 = 3, kOutVecTimeMajor = 4 };
 
-size_t resample_smem_bytes(int bpp, int chunk_rows);
-size_t g_chunk_floats(int bpp, int chunk_rows);
+size_t resample_smem_bytes(int bpp, int chunk_rows, int g_row_floats = kGRowFloats);
+size_t g_chunk_floats(int bpp, int chunk_rows, int g_row_floats = kGRowFloats);
 cudaError_t launch_finalize(OutEntry *outs, int n, int n_filters, bool lowpass, bool interp, cudaStream_t stream);
 cudaError_t launch_expand(const float *bank, const OutEntry *outs, const ChunkEntry *chunks, float *G,
                           int chunk_first, int n_chunks, int n_out, int taps, int bpp, int chunk_rows,
-                          bool split_at_zero, cudaStream_t stream);
+                          bool split_at_zero, cudaStream_t stream, int g_row_floats = kGRowFloats);
 cudaError_t launch_resample(const ResampleParams &p, int bpp, int chunk_rows, bool exact, cudaStream_t stream,
-                            const DirectInput *direct = nullptr);
+                            const DirectInput *direct = nullptr, bool non_interpolating = false);
+// non-interpolating form (resample_ni_kernel.cu; BPP 4, 32-row chunks): G rows of kGRowFloatsNI floats
+cudaError_t launch_resample_ni(const ResampleParams &q, int n_groups, int n_ctas_y, bool exact, bool tm,
+                               cudaStream_t stream);
 // direct-input form (BPP 4, 32-row chunks, caller-layout output); called by launch_resample when p.direct is set
 cudaError_t launch_resample_direct(const ResampleParams &p, const DirectInput &d, int n_groups, int n_ctas_y,
                                    bool exact, cudaStream_t stream);

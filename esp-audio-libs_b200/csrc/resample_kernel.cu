@@ -89,18 +89,35 @@ constexpr int kExpandTileFloat4 = 36 * 17 > 32 * 33 ? 36 * 17 : 32 * 33;  // row
 __global__ void __launch_bounds__(kExpandThreads)
     espb_expand_kernel(const float *__restrict__ bank, const OutEntry *__restrict__ outs,
                        const ChunkEntry *__restrict__ chunks, float *__restrict__ G, int chunk_first, int n_chunks,
-                       int n_out, int taps, int bpp, int CJ, int split_at_zero) {
+                       int n_out, int taps, int bpp, int CJ, int split_at_zero, int grf) {
   __shared__ float4 tile[kExpandTileFloat4];
-  const int quads_per_row = bpp * (kGRowFloats / 4);  // float4 per row: 16 (4 warps per pass) or 32
+  // float4 per row: 16 (4 warps per pass) or 32; half of that when a row holds one coefficient per output
+  const int quads_per_row = bpp * (grf / 4);
+  const bool ni = grf == kGRowFloatsNI;
   const int pitch = quads_per_row + 1;
   const int total = CJ * quads_per_row;
   for (int cc = blockIdx.x; cc < n_chunks; cc += gridDim.x) {
     const ChunkEntry ce = chunks[chunk_first + cc];
     for (int i = threadIdx.x; i < total; i += kExpandThreads) {
       const int quad = i / CJ, jj = i - quad * CJ;  // rows fastest: a warp reads one filter row contiguously
-      const int b = quad >> 2, pair = quad & 3;     // block in pass, output pair within block
+      // block in pass; the quad holds outputs (2 pair, 2 pair + 1) x (filter 0, 1), or four outputs x one filter
+      const int b = ni ? quad >> 1 : quad >> 2, pair = ni ? (quad & 1) * 2 : quad & 3;
       const int j = ce.j_start + jj;
       float v[4];
+      if (ni) {
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+          const int o = (ce.pass * bpp + b) * NB + pair * 2 + h;
+          float c0 = 0.0f;
+          if (o < n_out) {
+            const OutEntry e = outs[o];
+            const int k = j - e.ws;
+            if (k >= 0 && k < taps && e.kind >= kKindSingle && !(split_at_zero && ce.j_start < 0 && j >= 0))
+              c0 = __ldg(bank + (size_t) e.phase * taps + k);
+          }
+          v[h] = c0;
+        }
+      } else
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         const int o = (ce.pass * bpp + b) * NB + pair * 2 + h;
@@ -121,7 +138,7 @@ __global__ void __launch_bounds__(kExpandThreads)
       tile[jj * pitch + quad] = make_float4(v[0], v[1], v[2], v[3]);
     }
     __syncthreads();
-    float4 *dst = reinterpret_cast<float4 *>(G + (size_t) cc * CJ * bpp * kGRowFloats);
+    float4 *dst = reinterpret_cast<float4 *>(G + (size_t) cc * CJ * bpp * grf);
     for (int i = threadIdx.x; i < total; i += kExpandThreads) {
       const int jj = i / quads_per_row, quad = i - jj * quads_per_row;
       dst[i] = tile[jj * pitch + quad];
@@ -601,14 +618,14 @@ __global__ void __launch_bounds__(BPP * 32, 16 / BPP) espb_resample_kernel(const
 // ---------------------------------------------------------------------------------
 int resample_stages(int bpp, int CJ) { return CJ == 24 ? 3 : (CJ == 36 ? 2 : (bpp == 8 ? 3 : 2) * (32 / CJ)); }
 
-size_t resample_smem_bytes(int bpp, int CJ) {
+size_t resample_smem_bytes(int bpp, int CJ, int grf) {
   const int stages = resample_stages(bpp, CJ);
-  return (size_t) stages * (CJ * bpp * kGRowFloats + CJ * SGN) * sizeof(float) + stages * sizeof(uint64_t) +
+  return (size_t) stages * (CJ * bpp * grf + CJ * SGN) * sizeof(float) + stages * sizeof(uint64_t) +
          stages * sizeof(uint64_t) + max_chunks_per_cta(bpp, CJ) * (sizeof(int32_t) + bpp * sizeof(uint16_t)) +
          (size_t) bpp * NB * sizeof(OutEntry) + 4 * sizeof(int32_t);
 }
 
-size_t g_chunk_floats(int bpp, int CJ) { return (size_t) CJ * bpp * kGRowFloats; }
+size_t g_chunk_floats(int bpp, int CJ, int grf) { return (size_t) CJ * bpp * grf; }
 
 cudaError_t launch_finalize(OutEntry *outs, int n, int n_filters, bool lowpass, bool interp, cudaStream_t stream) {
   if (n <= 0)
@@ -620,7 +637,7 @@ cudaError_t launch_finalize(OutEntry *outs, int n, int n_filters, bool lowpass, 
 
 cudaError_t launch_expand(const float *bank, const OutEntry *outs, const ChunkEntry *chunks, float *G,
                           int chunk_first, int n_chunks, int n_out, int taps, int bpp, int chunk_rows,
-                          bool split_at_zero, cudaStream_t stream) {
+                          bool split_at_zero, cudaStream_t stream, int grf) {
   if (n_chunks <= 0)
     return cudaSuccess;
   int sms = 148, dev = 0;
@@ -628,7 +645,7 @@ cudaError_t launch_expand(const float *bank, const OutEntry *outs, const ChunkEn
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int grid = n_chunks < sms * 8 ? n_chunks : sms * 8;  // 8 resident CTAs of 256 threads per SM
   espb_expand_kernel<<<grid, kExpandThreads, 0, stream>>>(bank, outs, chunks, G, chunk_first, n_chunks, n_out, taps,
-                                                          bpp, chunk_rows, split_at_zero ? 1 : 0);
+                                                          bpp, chunk_rows, split_at_zero ? 1 : 0, grf);
   count_launch();
   return cudaGetLastError();
 }
@@ -800,7 +817,7 @@ static cudaError_t launch_resample_t(const ResampleParams &p, int n_groups, int 
 }
 
 cudaError_t launch_resample(const ResampleParams &p, int bpp, int chunk_rows, bool exact, cudaStream_t stream,
-                            const DirectInput *direct) {
+                            const DirectInput *direct, bool non_interpolating) {
   const int n_groups = (p.n_series + SGN - 1) / SGN;
   const int n_passes = p.pass_end - p.pass_first;
   if (n_groups <= 0 || n_passes <= 0)
@@ -825,6 +842,11 @@ cudaError_t launch_resample(const ResampleParams &p, int bpp, int chunk_rows, bo
                : launch_resample_t<BPP_, NST_, CJ_, true, false>(q, n_groups, n_ctas_y, stream))   \
          : (tm ? launch_resample_t<BPP_, NST_, CJ_, false, true>(q, n_groups, n_ctas_y, stream)    \
                : launch_resample_t<BPP_, NST_, CJ_, false, false>(q, n_groups, n_ctas_y, stream)))
+  if (non_interpolating) {  // one filter per output: resample_ni_kernel.cu
+    if (bpp != 4 || chunk_rows != 32 || direct)
+      return cudaErrorInvalidValue;
+    return launch_resample_ni(q, n_groups, n_ctas_y, exact, tm, stream);
+  }
   if (direct) {  // input rows straight from the caller's interleaved-stereo buffer (resample_direct_kernel.cu)
     if (bpp != 4 || chunk_rows != 32 || tm)
       return cudaErrorInvalidValue;

@@ -739,3 +739,36 @@ def test_full_size_long_stream_config(oracle):
                                        int(one * dr / sr) + 64)
     settle = gen - 600  # the one-shot CPU run has no frames after `one`, the 10 s run has: compare what both know
     assert bits_equal(seq[1, : settle * ch * 3], q[: settle * ch * 3])
+
+
+@pytest.mark.parametrize("flags,lowpass", [(0, 1.0), (espb.BLACKMAN_HARRIS, 1.0), (espb.INCLUDE_LOWPASS, 0.7)])
+def test_non_interpolating_kernel(oracle, flags, lowpass, monkeypatch):
+    """Flags without SUBSAMPLE_INTERPOLATE take the dedicated one-filter kernel (art_resampler.cpp:421-430): bit-exact
+    with the oracle in exact mode, <= 1e-6 in fast mode, and identical to the route through the interpolating kernel
+    (ESPB_NI=0), over chunked calls and a partial series group."""
+    ns, ch, taps, filters = 70, 2, 128, 37
+    ratio = f32(44100) / f32(48000)
+    total = 3000
+    x = np.stack([noise(total, ch, stream=40 + s, amp=0.8) for s in range(ns)])
+    results = {}
+    for label, env in (("dedicated", "1"), ("via-interp", "0")):
+        monkeypatch.setenv("ESPB_NI", env)
+        for mode in (espb.MODE_EXACT, espb.MODE_FAST):
+            b = espb.ResampleBatch(ns, ch, taps, filters, lowpass, flags, mode=mode)
+            b.advance(taps / 2)
+            outs, pos = [], 0
+            for n_in, cap in ((1000, 2000), (7, 30), (1993, 4000)):
+                y, used, gen = b.process_interleaved(x[:, pos * ch:(pos + n_in) * ch], cap, ratio, n_in=n_in)
+                outs.append(y)
+                pos += used
+            results[(label, mode)] = np.concatenate(outs, axis=1)
+            b.free()
+    assert bits_equal(results[("dedicated", espb.MODE_EXACT)], results[("via-interp", espb.MODE_EXACT)])
+    assert bits_equal(results[("dedicated", espb.MODE_FAST)], results[("via-interp", espb.MODE_FAST)])
+    for s in (0, 63, 64, ns - 1):
+        o = oracle.resampler(ch, taps, filters, lowpass, flags)
+        o.advance(taps / 2)
+        yo = np.concatenate([o.process_interleaved(x[s, a * ch:(a + n) * ch], cap, ratio, n_in=n)[0]
+                             for a, n, cap in ((0, 1000, 2000), (1000, 7, 30), (1007, 1993, 4000))])
+        assert bits_equal(results[("dedicated", espb.MODE_EXACT)][s], yo), s
+        assert np.max(np.abs(results[("dedicated", espb.MODE_FAST)][s].astype(np.float64) - yo)) <= TOL
