@@ -106,13 +106,23 @@ __global__ void __launch_bounds__(BPP * 32, 16 / BPP) espb_resample_ni_kernel(co
       issue_chunk(c);
 
   // accumulators [series e][output n]: one dot product per output (art_resampler.cpp:421-430)
-  float acc[4][NB];
+  // (fast mode: two neighbouring outputs share one packed FFMA2 — their coefficients are adjacent in G)
+  float acc[EXACT ? 4 : 1][EXACT ? NB : 1];
+  float2 accp[EXACT ? 1 : 4][EXACT ? 1 : NB / 2];
   auto clear_acc = [&]() {
+    if constexpr (EXACT) {
 #pragma unroll
-    for (int e = 0; e < 4; ++e)
+      for (int e = 0; e < 4; ++e)
 #pragma unroll
-      for (int n = 0; n < NB; ++n)
-        acc[e][n] = 0.0f;
+        for (int n = 0; n < NB; ++n)
+          acc[e][n] = 0.0f;
+    } else {
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+#pragma unroll
+        for (int m = 0; m < NB / 2; ++m)
+          accp[e][m] = make_float2(0.0f, 0.0f);
+    }
   };
   clear_acc();
 
@@ -141,12 +151,22 @@ __global__ void __launch_bounds__(BPP * 32, 16 / BPP) espb_resample_ni_kernel(co
           const float4 *gp = reinterpret_cast<const float4 *>(gb + jj * BPP * GRF);
           const float4 g0 = gp[0], g1 = gp[1];
           const float x4[4] = {xv.x, xv.y, xv.z, xv.w};
-          const float g8[NB] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+          if constexpr (EXACT) {
+            const float g8[NB] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
 #pragma unroll
-          for (int n = 0; n < NB; ++n)
+            for (int n = 0; n < NB; ++n)
 #pragma unroll
-            for (int e = 0; e < 4; ++e)
-              acc[e][n] = mac<EXACT>(g8[n], x4[e], acc[e][n]);
+              for (int e = 0; e < 4; ++e)
+                acc[e][n] = mac<true>(g8[n], x4[e], acc[e][n]);
+          } else {
+            const float2 gg[NB / 2] = {make_float2(g0.x, g0.y), make_float2(g0.z, g0.w), make_float2(g1.x, g1.y),
+                                       make_float2(g1.z, g1.w)};  // (output 2m, output 2m + 1)
+#pragma unroll
+            for (int m = 0; m < NB / 2; ++m)
+#pragma unroll
+              for (int e = 0; e < 4; ++e)
+                accp[e][m] = fma2(gg[m], x4[e], accp[e][m]);
+          }
         }
       }
     }
@@ -177,7 +197,8 @@ __global__ void __launch_bounds__(BPP * 32, 16 / BPP) espb_resample_ni_kernel(co
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           if (en.kind >= kKindSingle) {  // (no blend without SUBSAMPLE_INTERPOLATE)
-            v[e][n] = acc[e][n];
+            v[e][n] = EXACT ? acc[EXACT ? e : 0][EXACT ? n : 0] : ((n & 1) ? accp[EXACT ? 0 : e][EXACT ? 0 : n / 2].y
+                                                                           : accp[EXACT ? 0 : e][EXACT ? 0 : n / 2].x);
           } else {  // pass-through: *source (art_resampler.cpp:426,440) = tap numTaps/2-1 of the window
             v[e][n] = p.xt[((int64_t) group * p.xt_rows + (en.ws + T / 2 - 1 + T)) * SGN + lane * 4 + e];
           }
