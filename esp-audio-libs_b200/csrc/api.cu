@@ -295,6 +295,7 @@ int pick_slab_streams(int num_streams, int channels) {
 // ART resampler batch
 // ------------------------------------------------------------------------------------
 struct EspbResampleBatch {
+  int device = -1;  // the CUDA device that was current at creation: all of the context's memory lives there
   int num_streams = 0, channels = 0;
   ArtGeometry geo{};
   float lowpass = 1.0f;
@@ -373,6 +374,11 @@ void unpin_host_range(void *p) {
 // Build (or reuse) the schedule + pass plan for this call and upload the tables.
 int prepare_call(EspbResampleBatch *c, int n_in, int n_out, float ratio, cudaStream_t stream,
                  bool want_direct = false) {
+  {
+    int dev = -1;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev != c->device)
+      return fail(ESPB_ERR_STATE, "this context was created on another CUDA device (espb_set_device before the call)");
+  }
   if (c->state_event_pending) {  // order this call after an asynchronous reset issued on another stream
     CU_TRY(cudaStreamWaitEvent(stream, c->state_event, 0), "cudaStreamWaitEvent");
     c->state_event_pending = false;
@@ -843,6 +849,7 @@ EspbResampleBatch *espb_resampleInit(int num_streams, int numChannels, int numTa
   c->sched.outs.on_release = c->plan.chunks.on_release = c->plan.pass_chunk_begin.on_release = unpin_host_range;
   c->spare_outs.on_acquire = c->spare_chunks.on_acquire = c->spare_pcb.on_acquire = pin_host_range;
   c->spare_outs.on_release = c->spare_chunks.on_release = c->spare_pcb.on_release = unpin_host_range;
+  cudaGetDevice(&c->device);
   c->num_streams = num_streams;
   c->channels = numChannels;
   c->geo = ArtGeometry{numTaps, numFilters, flags};
