@@ -118,6 +118,8 @@ def lib():
         "espb_biquad_apply_samples": (i, [vp, vp, vp]),
         "espb_biquad_set_time_blocks": (i, [vp, i, i]),
         "espb_resampler_set_biquad_time_blocks": (i, [vp, i, i]),
+        "espb_biquad_block_stats": (i, [vp, C.POINTER(u64), C.POINTER(i)]),
+        "espb_resampler_biquad_block_stats": (i, [vp, C.POINTER(u64), C.POINTER(i)]),
         "espb_biquad_get_state": (i, [vp, vp]),
         "espb_quantized_to_float": (i, [vp, vp, u64, C.c_uint8, f, vp]),
         "espb_float_to_quantized": (i, [vp, vp, u64, C.c_uint8, vp, vp]),
@@ -541,6 +543,12 @@ class BiquadBatch:
     def set_time_blocks(self, block_rows, warmup_rows):
         _check(lib().espb_biquad_set_time_blocks(self.h, block_rows, warmup_rows), "biquad_set_time_blocks")
 
+    def block_stats(self):
+        """(blocks repaired so far, current warm-up rows) of the time-block mode."""
+        n, w = C.c_uint64(0), C.c_int(0)
+        _check(lib().espb_biquad_block_stats(self.h, C.byref(n), C.byref(w)), "biquad_block_stats")
+        return int(n.value), int(w.value)
+
     def apply_dev(self, d_buf, layout, channels, n_samples, stream=None):
         lay = _Layout(*layout)
         _check(lib().espb_biquad_apply_buffer(self.h, d_buf, C.byref(lay), channels, n_samples, stream),
@@ -711,6 +719,11 @@ class Resampler:
     def set_biquad_time_blocks(self, block_rows, warmup_rows):
         _check(lib().espb_resampler_set_biquad_time_blocks(self.h, block_rows, warmup_rows),
                "resampler_set_biquad_time_blocks")
+
+    def biquad_block_stats(self):
+        n, w = C.c_uint64(0), C.c_int(0)
+        _check(lib().espb_resampler_biquad_block_stats(self.h, C.byref(n), C.byref(w)), "resampler_biquad_block_stats")
+        return int(n.value), int(w.value)
 
     def policy(self):
         c, ratio, lp, flags = _Coeffs(), C.c_float(0), C.c_float(0), C.c_int(0)

@@ -331,6 +331,13 @@ struct EspbResampleBatch {
   bool non_interp = false;
   int g_row_floats() const { return non_interp ? kGRowFloatsNI : kGRowFloats; }
   bool direct_ok = false;    // ESPB_DIRECT=1 switches it on
+  // few-series form (resample_fs_kernel.cu): lanes own outputs; chosen per context when n_series <= kFsMaxSeries
+  int fs_policy = -1;        // ESPB_FS: 0 never, 1 / unset whenever the geometry allows it
+  DevBuf bank_tr;            // slice-major copy of the bank
+  int fs_kt = 0;
+  size_t fs_slice = 0;       // floats per slice
+  bool fs_call = false;      // this call runs through the few-series kernel (no pass plan, no G)
+  int fs_x_rows = 0;         // rows of the widest input tile of a CTA of this call
   bool direct_call = false;  // this call's plan is split at input frame 0 and its input is read through TMA
   // options
   bool plan_cache = true;   // reuse schedule / tables / G when a call repeats (state, n_in, n_out, ratio)
@@ -415,6 +422,23 @@ int prepare_call(EspbResampleBatch *c, int n_in, int n_out, float ratio, cudaStr
     c->tables_upload_pending = false;
   }
   build_schedule(c->geo, c->state, n_in, n_out, ratio, c->sched, /*finalize=*/false);  // pass 2 runs on the device
+  c->fs_call = false;
+  if (c->bank_tr.p && c->fs_policy != 0 && c->sched.generated > 0) {
+    // few-series form: the widest input tile (rows first window .. last window + taps of one CTA's outputs) must fit
+    const FsGeometry fg = fs_geometry(c->n_series());
+    const int n = (int) c->sched.generated, m = fg.outputs_per_cta;
+    int span = 0;
+    for (int first = 0; first < n; first += m) {
+      const int last = (first + m < n ? first + m : n) - 1;
+      const OutEntry &a = c->sched.outs[first], &b = c->sched.outs[last];  // raw entries: base + floor(offset)
+      const int d = (b.ws + (int32_t) b.w) - (a.ws + (int32_t) a.w);
+      span = d > span ? d : span;
+    }
+    c->fs_x_rows = span + c->geo.taps;
+    c->fs_call = fs_smem_bytes(fg, c->fs_slice, c->fs_x_rows) <= (size_t) 200 * 1024;
+  }
+  if (c->fs_call)
+    want_direct = false;
   c->direct_call = want_direct && (int) c->sched.used >= c->geo.taps;
   k.split = c->direct_call ? 1 : 0;
   {
@@ -422,14 +446,20 @@ int prepare_call(EspbResampleBatch *c, int n_in, int n_out, float ratio, cudaStr
     if (rc != ESPB_OK)
       return rc;
   }
-  build_pass_plan(c->sched, c->geo.taps, c->bpp, c->chunk_rows, c->plan, c->direct_call);
+  if (c->fs_call) {  // no passes, no chunks, no expanded coefficients
+    c->plan.chunks.clear();
+    c->plan.pass_chunk_begin.clear();
+    c->plan.pass_chunk_begin.push_back(0);
+  } else {
+    build_pass_plan(c->sched, c->geo.taps, c->bpp, c->chunk_rows, c->plan, c->direct_call);
+  }
   c->key = k;
   if (c->sched.generated == 0) {
     c->plan_on_device = true;
     return ESPB_OK;
   }
   CU_TRY(c->d_outs.reserve(c->sched.outs.size() * sizeof(OutEntry)), "cudaMalloc schedule");
-  CU_TRY(c->d_chunks.reserve(c->plan.chunks.size() * sizeof(ChunkEntry)), "cudaMalloc chunks");
+  CU_TRY(c->d_chunks.reserve((c->plan.chunks.size() + 1) * sizeof(ChunkEntry)), "cudaMalloc chunks");
   CU_TRY(c->d_pcb.reserve(c->plan.pass_chunk_begin.size() * sizeof(int32_t)), "cudaMalloc passes");
   CU_TRY(cudaMemcpyAsync(c->d_outs.p, c->sched.outs.data(), c->sched.outs.size() * sizeof(OutEntry),
                          cudaMemcpyHostToDevice, stream),
@@ -437,12 +467,14 @@ int prepare_call(EspbResampleBatch *c, int n_in, int n_out, float ratio, cudaStr
   CU_TRY(launch_finalize(c->d_outs.as<OutEntry>(), (int) c->sched.outs.size(), c->geo.filters,
                          (c->geo.flags & kFlagLowpass) != 0, (c->geo.flags & kFlagInterpolate) != 0, stream),
          "finalize kernel");
-  CU_TRY(cudaMemcpyAsync(c->d_chunks.p, c->plan.chunks.data(), c->plan.chunks.size() * sizeof(ChunkEntry),
-                         cudaMemcpyHostToDevice, stream),
-         "upload chunks");
-  CU_TRY(cudaMemcpyAsync(c->d_pcb.p, c->plan.pass_chunk_begin.data(),
-                         c->plan.pass_chunk_begin.size() * sizeof(int32_t), cudaMemcpyHostToDevice, stream),
-         "upload passes");
+  if (!c->fs_call) {
+    CU_TRY(cudaMemcpyAsync(c->d_chunks.p, c->plan.chunks.data(), c->plan.chunks.size() * sizeof(ChunkEntry),
+                           cudaMemcpyHostToDevice, stream),
+           "upload chunks");
+    CU_TRY(cudaMemcpyAsync(c->d_pcb.p, c->plan.pass_chunk_begin.data(),
+                           c->plan.pass_chunk_begin.size() * sizeof(int32_t), cudaMemcpyHostToDevice, stream),
+           "upload passes");
+  }
   if (!c->tables_uploaded)
     CU_TRY(cudaEventCreateWithFlags(&c->tables_uploaded, cudaEventDisableTiming), "cudaEventCreate");
   // (pageable tables were copied to a staging area before cudaMemcpyAsync returned: nothing to wait for)
@@ -521,7 +553,11 @@ int ensure_xt(EspbResampleBatch *c, int64_t rows) {
   const size_t row_bytes = kSeriesPerRow * sizeof(float);
   const size_t bytes = (size_t) c->n_groups() * rows * row_bytes;
   DevBuf nb[2];
-  cudaError_t e = nb[0].reserve(bytes);
+  // Growth is rare and synchronous (legacy-stream memset / copy below): wait for whatever earlier calls enqueued on
+  // non-blocking streams, which may still be writing the rows that are about to be carried over.
+  cudaError_t e = c->xt_rows > 0 ? cudaDeviceSynchronize() : cudaSuccess;
+  if (e == cudaSuccess)
+    e = nb[0].reserve(bytes);
   if (e == cudaSuccess)
     e = nb[1].reserve(bytes);
   if (e == cudaSuccess)  // rows nobody has written yet must still be finite (they meet zero coefficients)
@@ -573,6 +609,8 @@ struct StageFilter {
   float *state = nullptr;                // [series][sections][4] of the first series of the range
   int sections = 0;
   int block_rows = 0, warm_rows = 0;     // time-block mode of the biquad kernel (0 = sequential)
+  float *blk_state = nullptr;            // per-block state record of the first group of the range (time-block mode)
+  unsigned int *mismatches = nullptr;    // counter of repaired blocks
 };
 
 // cuTensorMapEncodeTiled through the runtime's driver entry point (the library does not link libcuda, so it still
@@ -683,7 +721,7 @@ int run_series_range(EspbResampleBatch *c, int series_first, int n_series, const
                              kChunkRows * row_bytes, ng, stream),
            "pad rows");
     CU_TRY(launch_biquad_tm(x_raw, x_new, rows, taps, n_in, n_series, pre->sections, *pre->params, pre->state,
-                            pre->block_rows, pre->warm_rows, stream),
+                            pre->block_rows, pre->warm_rows, stream, pre->blk_state, pre->mismatches),
            "biquad kernel");
   } else {
     if (int rc = stage_input(x_new, kChunkRows))
@@ -698,7 +736,40 @@ int run_series_range(EspbResampleBatch *c, int series_first, int n_series, const
   float *y_tm = nullptr;
   if (tm_out)
     y_tm = c->yt.as<float>() + (size_t) g0 * c->yt_rows * kSeriesPerRow;
-  if (c->sched.generated > 0) {
+  if (c->sched.generated > 0 && c->fs_call) {
+    FsParams fp{};
+    fp.x = x_new;
+    fp.x_fs = kSeriesPerRow;
+    fp.x_row0 = taps;
+    fp.out = out;
+    fp.out_ss = ol.stream_stride;
+    fp.out_cs = ol.channel_stride;
+    fp.out_fs = ol.frame_stride;
+    fp.out_tm = y_tm;
+    fp.bank_tr = c->bank_tr.as<float>();
+    fp.outs = c->d_outs.as<OutEntry>();
+    fp.n_series = n_series;
+    fp.channels = c->channels;
+    fp.n_out = (int) c->sched.generated;
+    fp.taps = taps;
+    fp.kt = c->fs_kt;
+    fp.slice_floats = (int) c->fs_slice;
+    cudaEvent_t ev_after = nullptr;
+    if (c->kernel_timing) {
+      while (c->ev_pool.size() < c->ev_used + 2) {
+        cudaEvent_t ev;
+        CU_TRY(cudaEventCreate(&ev), "cudaEventCreate");
+        c->ev_pool.push_back(ev);
+      }
+      CU_TRY(cudaEventRecord(c->ev_pool[c->ev_used], stream), "cudaEventRecord");
+      ev_after = c->ev_pool[c->ev_used + 1];
+      c->ev_used += 2;
+    }
+    CU_TRY(launch_resample_fs(fp, fs_geometry(c->n_series()), c->fs_x_rows, c->mode == ESPB_MODE_EXACT, stream),
+           "few-series resample kernel");
+    if (ev_after)
+      CU_TRY(cudaEventRecord(ev_after, stream), "cudaEventRecord");
+  } else if (c->sched.generated > 0) {
     ResampleParams p{};
     p.out_tm = y_tm;
     p.out_tm_rows = c->yt_rows;
@@ -771,7 +842,7 @@ int run_series_range(EspbResampleBatch *c, int series_first, int n_series, const
         blocks = post->block_rows;
       }
       CU_TRY(launch_biquad_tm(y_tm, y_f, c->yt_rows, 0, gen, n_series, post->sections, *post->params, post->state,
-                              blocks, post->warm_rows, stream),
+                              blocks, post->warm_rows, stream, post->blk_state, post->mismatches),
              "biquad kernel");
     }
     if (pcm_out) {  // resampler.cpp:152-153: float_to_quantized, fused with the way back to the caller's layout
@@ -879,6 +950,21 @@ EspbResampleBatch *espb_resampleInit(int num_streams, int numChannels, int numTa
     espb_resampleFree(c);
     return nullptr;
   }
+  c->fs_policy = (int) env_long("ESPB_FS", -1);
+  if (e == cudaSuccess && c->n_series() <= kFsMaxSeries && c->fs_policy != 0) {  // few-series form: slice-major bank
+    c->fs_kt = fs_slice_taps(numTaps, numFilters);
+    c->fs_slice = fs_slice_floats(numFilters, c->fs_kt);
+    std::vector<float> tr(c->fs_slice * (numTaps / c->fs_kt));
+    fs_build_bank_slices(c->bank_host.data(), numTaps, numFilters, c->fs_kt, tr.data());
+    e = c->bank_tr.reserve(tr.size() * sizeof(float));
+    if (e == cudaSuccess)
+      e = cudaMemcpy(c->bank_tr.p, tr.data(), tr.size() * sizeof(float), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+      cuda_fail(e, "resampleInit: device allocation");
+      espb_resampleFree(c);
+      return nullptr;
+    }
+  }
   if (ensure_xt(c, (int64_t) numTaps + kChunkRows) != ESPB_OK) {  // silent history (art_resampler.cpp:125-133)
     espb_resampleFree(c);
     return nullptr;
@@ -890,6 +976,7 @@ void espb_resampleFree(EspbResampleBatch *c) {
   if (!c)
     return;
   c->bank.release();
+  c->bank_tr.release();
   c->xt[0].release();
   c->xt[1].release();
   c->yt.release();
@@ -1091,7 +1178,7 @@ EspbResampleResult espb_resampleProcessInterleavedHost(EspbResampleBatch *c, con
   }
   const size_t out_row = (size_t) c->sched.generated * ch;
   const bool single_slab_g = passes_per_slab(c) >= c->plan.n_passes();
-  if (c->sched.generated > 0 && single_slab_g) {
+  if (c->sched.generated > 0 && single_slab_g && !c->fs_call) {
     if (ensure_g(c, 0, (int) c->plan.chunks.size(), s0) != ESPB_OK)
       return res;
   }
@@ -1156,8 +1243,66 @@ struct EspbBiquadBatch {
   DevBuf state;
   DevBuf tm, tm2;  // time-major scratch [group][tm_rows][128] (tm2: output side of the time-block mode)
   int64_t tm_rows = 0, tm2_rows = 0;
-  int block_rows = 0, warm_rows = 0;  // 0: one sequential run per series (exact); else time blocks with warm-up
+  // Time blocks (biquad_kernel.cu): -1 = automatic (few series and a long call: blocks of kAutoBlockRows rows),
+  // 0 = one sequential run per series, > 0 = blocks of that many rows.  Exact either way: the hand-over between
+  // blocks is verified bit for bit on the device and repaired where the warm-up did not converge.
+  int block_rows = -1, warm_rows = 1024;
+  DevBuf blk_state;                      // (start, end) state of every block, for the verify kernel
+  DevBuf mismatch_dev;                   // [1] blocks repaired so far in the call being enqueued
+  unsigned int *mismatch_host = nullptr; // pinned copy of the previous call's count
+  cudaEvent_t mismatch_ready = nullptr;
+  bool mismatch_pending = false;
+  uint64_t repaired_total = 0;
+  static constexpr int kAutoBlockRows = 8192, kAutoMaxGroups = 32, kMaxWarmRows = 1 << 16;
+  int n_groups() const { return (num_series + kSeriesPerRow - 1) / kSeriesPerRow; }
+  // rows per block for a call over n_rows rows (0: sequential)
+  int blocks_for(int n_rows) const {
+    if (block_rows > 0)
+      return n_rows > block_rows ? block_rows : 0;
+    if (block_rows < 0 && n_groups() <= kAutoMaxGroups && n_rows >= 2 * kAutoBlockRows)
+      return kAutoBlockRows;
+    return 0;
+  }
 };
+
+namespace {
+
+// Before a time-block launch: size the state record, harvest the previous call's repair count (widening the warm-up
+// when the trajectories did not merge), clear the counter.  No synchronisation.
+int biquad_prepare_blocks(EspbBiquadBatch *f, int n_rows, int block_rows, cudaStream_t stream) {
+  const size_t floats = biquad_block_state_floats(f->num_series, f->num_sections, n_rows, block_rows);
+  CU_TRY(f->blk_state.reserve(floats * sizeof(float)), "biquad block states");
+  if (!f->mismatch_dev.p) {
+    CU_TRY(f->mismatch_dev.reserve(sizeof(unsigned int)), "biquad counter");
+    CU_TRY(cudaMallocHost(&f->mismatch_host, sizeof(unsigned int)), "biquad counter");
+    *f->mismatch_host = 0;
+    CU_TRY(cudaEventCreateWithFlags(&f->mismatch_ready, cudaEventDisableTiming), "cudaEventCreate");
+  }
+  if (f->mismatch_pending && cudaEventQuery(f->mismatch_ready) == cudaSuccess) {
+    f->mismatch_pending = false;
+    if (*f->mismatch_host > 0) {
+      f->repaired_total += *f->mismatch_host;
+      if (f->warm_rows < EspbBiquadBatch::kMaxWarmRows)
+        f->warm_rows *= 2;
+    }
+  }
+  cudaGetLastError();  // (cudaErrorNotReady from the query is not an error)
+  CU_TRY(cudaMemsetAsync(f->mismatch_dev.p, 0, sizeof(unsigned int), stream), "biquad counter");
+  return ESPB_OK;
+}
+
+// After the launches of a call: bring the repair count to the host without waiting for it.
+int biquad_finish_blocks(EspbBiquadBatch *f, cudaStream_t stream) {
+  if (f->mismatch_pending)  // an earlier count has not been read yet: keep it (it is added up on the device side)
+    return ESPB_OK;
+  CU_TRY(cudaMemcpyAsync(f->mismatch_host, f->mismatch_dev.p, sizeof(unsigned int), cudaMemcpyDeviceToHost, stream),
+         "biquad counter");
+  CU_TRY(cudaEventRecord(f->mismatch_ready, stream), "cudaEventRecord");
+  f->mismatch_pending = true;
+  return ESPB_OK;
+}
+
+}  // namespace
 
 extern "C" {
 
@@ -1200,6 +1345,12 @@ void espb_biquad_free(EspbBiquadBatch *f) {
   f->tm.release();
   f->tm2.release();
   f->state.release();
+  f->blk_state.release();
+  f->mismatch_dev.release();
+  if (f->mismatch_host)
+    cudaFreeHost(f->mismatch_host);
+  if (f->mismatch_ready)
+    cudaEventDestroy(f->mismatch_ready);
   delete f;
 }
 
@@ -1229,17 +1380,23 @@ int espb_biquad_apply_buffer(EspbBiquadBatch *f, float *buf, const EspbLayout *l
                           f->num_series, num_samples, f->tm.as<float>(), f->tm_rows, 0, 0, s),
          "transpose kernel");
   float *filtered = f->tm.as<float>();
-  if (f->block_rows > 0 && num_samples > f->block_rows) {
+  const int blocks = f->blocks_for(num_samples);
+  if (blocks > 0) {
     if (f->tm_rows > f->tm2_rows) {
       CU_TRY(f->tm2.reserve((size_t) n_groups * f->tm_rows * kSeriesPerRow * sizeof(float)), "biquad scratch");
       f->tm2_rows = f->tm_rows;
     }
     filtered = f->tm2.as<float>();
+    if (int rc = biquad_prepare_blocks(f, num_samples, blocks, s))
+      return rc;
   }
   CU_TRY(launch_biquad_tm(f->tm.as<float>(), filtered, f->tm_rows, 0, num_samples, f->num_series, f->num_sections,
-                          f->params, f->state.as<float>(), filtered == f->tm.as<float>() ? 0 : f->block_rows,
-                          f->warm_rows, s),
+                          f->params, f->state.as<float>(), blocks, f->warm_rows, s, f->blk_state.as<float>(),
+                          f->mismatch_dev.as<unsigned int>()),
          "biquad kernel");
+  if (blocks > 0)
+    if (int rc = biquad_finish_blocks(f, s))
+      return rc;
   CU_TRY(launch_untranspose(filtered, f->tm_rows, 0, num_samples, buf, layout->stream_stride,
                             layout->channel_stride, layout->frame_stride, channels, f->num_series, s),
          "untranspose kernel");
@@ -1254,10 +1411,30 @@ int espb_biquad_apply_samples(EspbBiquadBatch *f, float *samples, void *stream) 
 }
 
 int espb_biquad_set_time_blocks(EspbBiquadBatch *f, int block_rows, int warmup_rows) {
-  if (!f || block_rows < 0 || warmup_rows < 0 || block_rows % 32 || warmup_rows % 32)
-    return fail(ESPB_ERR_ARG, "biquad_set_time_blocks: rows must be non-negative multiples of 32");
+  if (!f || block_rows < -1 || warmup_rows < 0 || (block_rows > 0 && block_rows % 32) || warmup_rows % 32)
+    return fail(ESPB_ERR_ARG, "biquad_set_time_blocks: rows must be non-negative multiples of 32 (-1: automatic)");
   f->block_rows = block_rows;
-  f->warm_rows = warmup_rows;
+  if (warmup_rows > 0 || block_rows > 0)
+    f->warm_rows = warmup_rows;
+  return ESPB_OK;
+}
+
+// Diagnostics of the time-block mode: blocks whose hand-over had to be repaired so far (0 when every warm-up merged)
+// and the current warm-up length.  Synchronises with the last call.
+int espb_biquad_block_stats(EspbBiquadBatch *f, uint64_t *repaired_blocks, int *warmup_rows) {
+  if (!f)
+    return fail(ESPB_ERR_ARG, "biquad_block_stats: NULL");
+  if (f->mismatch_pending) {
+    CU_TRY(cudaEventSynchronize(f->mismatch_ready), "cudaEventSynchronize");
+    f->mismatch_pending = false;
+    f->repaired_total += *f->mismatch_host;
+    if (*f->mismatch_host > 0 && f->warm_rows < EspbBiquadBatch::kMaxWarmRows)
+      f->warm_rows *= 2;
+  }
+  if (repaired_blocks)
+    *repaired_blocks = f->repaired_total;
+  if (warmup_rows)
+    *warmup_rows = f->warm_rows;
   return ESPB_OK;
 }
 
@@ -1578,8 +1755,15 @@ int wrapper_run_range(EspbResampler *r, int s0, int ns, const uint8_t *d_in, int
     flt.params = &lp->params;
     flt.state = lp->state.as<float>() + (size_t) s0 * ch * lp->num_sections * 4;
     flt.sections = lp->num_sections;
-    flt.block_rows = lp->block_rows;
+    const int rows = (int) (r->policy.pre ? wc.todo : wc.generated);
+    flt.block_rows = lp->blocks_for(rows);
     flt.warm_rows = lp->warm_rows;
+    if (flt.block_rows > 0) {  // (wrapper_plan sized the record; ranges start on group boundaries)
+      const size_t n_blocks = ((size_t) rows + flt.block_rows - 1) / flt.block_rows;
+      flt.blk_state = lp->blk_state.as<float>() +
+                      (size_t) (s0 * ch / kSeriesPerRow) * n_blocks * lp->num_sections * 2 * kSeriesPerRow * 4;
+      flt.mismatches = lp->mismatch_dev.as<unsigned int>();
+    }
   }
   (void) out_free;
   return run_series_range(r->art, s0 * ch, ns * ch, fin, il, fout, ol, (int) wc.todo, stream, g_preexpanded,
@@ -1611,9 +1795,17 @@ int wrapper_plan(EspbResampler *r, size_t avail, size_t out_free, cudaStream_t s
   if (wc->generated * ch > r->out_samples)
     return fail(ESPB_ERR_ARG, "resample: output exceeds the float buffer size given at construction");
   // the resampler writes time-major scratch; the post-filter and the PCM packing read it
-  rc = ensure_yt(r->art, (int64_t) wc->generated, r->policy.post && r->lowpass && r->lowpass->block_rows > 0);
+  const int post_blocks = (r->policy.post && r->lowpass) ? r->lowpass->blocks_for((int) wc->generated) : 0;
+  rc = ensure_yt(r->art, (int64_t) wc->generated, post_blocks > 0);
   if (rc != ESPB_OK)
     return rc;
+  if (r->lowpass) {
+    const int rows = (int) (r->policy.pre ? wc->todo : wc->generated);
+    const int blocks = r->lowpass->blocks_for(rows);
+    if (blocks > 0)
+      if ((rc = biquad_prepare_blocks(r->lowpass, rows, blocks, stream)) != ESPB_OK)
+        return rc;
+  }
   return ESPB_OK;
 }
 
@@ -1747,6 +1939,8 @@ EspbResamplerResults espb_resampler_resample(EspbResampler *r, const uint8_t *in
   if (wrapper_run_range(r, 0, r->num_streams, in, in_stride_bytes, out, out_stride_bytes, wc, output_frames_free,
                         gain_db, s, false) != ESPB_OK)
     return none;
+  if (r->lowpass && r->lowpass->mismatch_dev.p && biquad_finish_blocks(r->lowpass, s) != ESPB_OK)
+    return none;
   cudaError_t e = cudaMemcpyAsync(r->clipped_host, r->clipped.p, r->num_streams * sizeof(uint32_t),
                                   cudaMemcpyDeviceToHost, s);
   if (e == cudaSuccess)
@@ -1777,8 +1971,23 @@ EspbResamplerResults espb_resampler_resample_async(EspbResampler *r, const uint8
   if (wrapper_run_range(r, 0, r->num_streams, in, in_stride_bytes, out, out_stride_bytes, wc, output_frames_free,
                         gain_db, s, false) != ESPB_OK)
     return none;
+  if (r->lowpass && r->lowpass->mismatch_dev.p && biquad_finish_blocks(r->lowpass, s) != ESPB_OK)
+    return none;
   memset(r->clipped_host, 0, r->num_streams * sizeof(uint32_t));
   return wrapper_finish(r, wc, nullptr);  // clipped_samples = 0: not known yet
+}
+
+int espb_resampler_biquad_block_stats(EspbResampler *r, uint64_t *repaired_blocks, int *warmup_rows) {
+  if (!r)
+    return fail(ESPB_ERR_ARG, "resampler_biquad_block_stats: NULL");
+  if (!r->lowpass) {
+    if (repaired_blocks)
+      *repaired_blocks = 0;
+    if (warmup_rows)
+      *warmup_rows = 0;
+    return ESPB_OK;
+  }
+  return espb_biquad_block_stats(r->lowpass, repaired_blocks, warmup_rows);
 }
 
 const uint32_t *espb_resampler_clipped_dev(EspbResampler *r) { return r ? r->clipped.as<uint32_t>() : nullptr; }
@@ -1813,7 +2022,7 @@ EspbResamplerResults espb_resampler_resample_host(EspbResampler *r, const uint8_
   bool single_slab_g = true;
   if (r->policy.resampling && wc.generated > 0) {
     single_slab_g = passes_per_slab(r->art) >= r->art->plan.n_passes();
-    if (single_slab_g && ensure_g(r->art, 0, (int) r->art->plan.chunks.size(), s0) != ESPB_OK)
+    if (single_slab_g && !r->art->fs_call && ensure_g(r->art, 0, (int) r->art->plan.chunks.size(), s0) != ESPB_OK)
       return none;
   }
   cudaEventRecord(r->pipe.ready, s0);
@@ -1859,6 +2068,8 @@ EspbResamplerResults espb_resampler_resample_host(EspbResampler *r, const uint8_
       return none;
     }
   }
+  if (r->lowpass && r->lowpass->mismatch_dev.p && biquad_finish_blocks(r->lowpass, s0) != ESPB_OK)
+    return none;
   return wrapper_finish(r, wc, clipped_per_stream_host);
 }
 

@@ -16,12 +16,20 @@
 // place by the thread that owns the column, and written back by TMA bulk stores — HBM sees only
 // full 16 KB transfers, the threads only conflict-free LDS/STS.
 //
-// Long single streams (few series, many rows) additionally offer time blocks (blockIdx.y): block k
-// filters rows [k*L, (k+1)*L) after re-running the recurrence over the W rows before it from a zero
-// state ("warm-up"), out of place.  Once the two trajectories (true state vs zero start) have rounded to
-// the same two consecutive outputs they stay bit-identical; measured on the CPU oracle this happens
-// within 64 rows for pole radius 0.49, 256 for 0.77, 4096 for 0.92, and never for 0.98 (SURVEY.md §5
-// lists 1.2e-7..1.8e-6 for the superposition form of the same idea).  Opt-in; the default is one block.
+// Long single streams (few series, many rows) run in time blocks (blockIdx.y): block k filters rows
+// [k*L, (k+1)*L) after re-running the recurrence over the W rows before it from a zero state ("warm-up"),
+// out of place.  Once the two trajectories (true state vs zero start) have rounded to the same two
+// consecutive outputs they stay bit-identical; measured on the CPU oracle this happens within 64 rows for
+// pole radius 0.49, 256 for 0.77, 4096 for 0.92, and never for 0.98.  That merge is an empirical event, so it
+// is VERIFIED, not assumed: every block records the state it reached at its first row (after the warm-up)
+// and at its end; espb_biquad_verify_kernel then walks the blocks of each series in order and compares, bit
+// for bit, block k's start state with block k-1's end state.  Equal state + equal input = equal continuation,
+// so an unbroken chain of equalities from block 0 (which starts from the true saved state) proves that the
+// output is the sequential one.  Where the states differ the series' block is filtered again from the true
+// state (sequentially, by the thread that owns the series) and the chain continues from its corrected end.
+// The result is therefore the reference's (art_biquad.cpp:73-93) by construction; a failed merge only costs
+// time.  The verify kernel also commits the final state (the block kernel never writes the saved state, so
+// no block can read a state that another block of the same launch has already replaced).
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -94,7 +102,8 @@ __device__ __forceinline__ float section_step(Section &s, float x, const BiquadP
 template <int NSEC, bool FIRST_ORDER>
 __global__ void __launch_bounds__(SGN)
     espb_biquad_tm_kernel(const float *src, float *dst, int64_t rows_cap, int row_first, int n_rows, BiquadParams c,
-                          float *__restrict__ state, int n_series, int block_rows, int warm_rows) {
+                          float *__restrict__ state, int n_series, int block_rows, int warm_rows,
+                          float4 *__restrict__ blk_state) {
   extern __shared__ __align__(128) unsigned char bq_smem[];
   float (*ring)[RB][SGN] = reinterpret_cast<float (*)[RB][SGN]>(bq_smem);  // [BSTAGES][RB][SGN]
   uint64_t *full = reinterpret_cast<uint64_t *>(bq_smem + sizeof(float) * BSTAGES * RB * SGN);
@@ -147,9 +156,16 @@ __global__ void __launch_bounds__(SGN)
   }
   __syncthreads();
 
+  // time-block mode: (start, end) state of block `blk` of this thread's series, for the verify kernel
+  float4 *rec = blk_state ? blk_state + ((size_t) (blockIdx.x * gridDim.y + blk) * NSEC * 2) * SGN + tid : nullptr;
   for (int k = 0; k < n_chunks; ++k) {
     const int st = k % BSTAGES;
     const int rows = chunk_rows(k);
+    if (rec && k == first_store_chunk) {
+#pragma unroll
+      for (int s = 0; s < NSEC; ++s)
+        rec[(s * 2) * SGN] = make_float4(sec[s].in_d1, sec[s].in_d2, sec[s].out_d1, sec[s].out_d2);
+    }
     mbar_wait(&full[st], (uint32_t) ((k / BSTAGES) & 1));
     float *col = &ring[st][0][tid];
     if (rows == RB) {
@@ -187,7 +203,11 @@ __global__ void __launch_bounds__(SGN)
   if (tid == 0)
     asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory");
 
-  if (q < n_series && last_block) {
+  if (rec) {
+#pragma unroll
+    for (int s = 0; s < NSEC; ++s)
+      rec[(s * 2 + 1) * SGN] = make_float4(sec[s].in_d1, sec[s].in_d2, sec[s].out_d1, sec[s].out_d2);
+  } else if (q < n_series && last_block) {
 #pragma unroll
     for (int k = 0; k < NSEC; ++k)
       *reinterpret_cast<float4 *>(state + ((int64_t) q * NSEC + k) * 4) =
@@ -195,10 +215,77 @@ __global__ void __launch_bounds__(SGN)
   }
 }
 
+__device__ __forceinline__ bool same_bits(const float4 &a, const float4 &b) {
+  return __float_as_uint(a.x) == __float_as_uint(b.x) && __float_as_uint(a.y) == __float_as_uint(b.y) &&
+         __float_as_uint(a.z) == __float_as_uint(b.z) && __float_as_uint(a.w) == __float_as_uint(b.w);
+}
+
+// Chain check of the time blocks (see the header): one thread per series walks its blocks in order.  A block whose
+// recorded start state is not bit-identical to the true end state of its predecessor is filtered again from that
+// state.  `mismatches` counts such blocks (diagnostics; the launcher widens the warm-up when it sees any).
+template <int NSEC, bool FIRST_ORDER>
+__global__ void __launch_bounds__(SGN)
+    espb_biquad_verify_kernel(const float *src, float *dst, int64_t rows_cap, int row_first, int n_rows, BiquadParams c,
+                              float *__restrict__ state, int n_series, int block_rows, int n_blocks,
+                              const float4 *__restrict__ blk_state, unsigned int *mismatches) {
+  const int tid = threadIdx.x;
+  const int q = blockIdx.x * SGN + tid;
+  if (q >= n_series)
+    return;
+  const float4 *rec = blk_state + ((size_t) blockIdx.x * n_blocks * NSEC * 2) * SGN + tid;
+  float4 truth[NSEC];  // the true state at the end of the previous block
+#pragma unroll
+  for (int s = 0; s < NSEC; ++s)
+    truth[s] = rec[(s * 2 + 1) * SGN];  // block 0 started from the saved state
+  unsigned int bad = 0;
+  for (int k = 1; k < n_blocks; ++k) {
+    const float4 *rk = rec + (size_t) k * NSEC * 2 * SGN;
+    bool same = true;
+#pragma unroll
+    for (int s = 0; s < NSEC; ++s)
+      same = same && same_bits(rk[(s * 2) * SGN], truth[s]);
+    if (same) {
+#pragma unroll
+      for (int s = 0; s < NSEC; ++s)
+        truth[s] = rk[(s * 2 + 1) * SGN];
+      continue;
+    }
+    ++bad;
+    Section sec[NSEC];
+#pragma unroll
+    for (int s = 0; s < NSEC; ++s) {
+      sec[s].in_d1 = truth[s].x;
+      sec[s].in_d2 = truth[s].y;
+      sec[s].out_d1 = truth[s].z;
+      sec[s].out_d2 = truth[s].w;
+    }
+    const int lo = k * block_rows, hi = lo + block_rows < n_rows ? lo + block_rows : n_rows;
+    const float *ps = src + ((int64_t) blockIdx.x * rows_cap + row_first + lo) * SGN + tid;
+    float *pd = dst + ((int64_t) blockIdx.x * rows_cap + row_first + lo) * SGN + tid;
+    for (int r = 0; r < hi - lo; ++r) {
+      float v = ps[(int64_t) r * SGN];
+#pragma unroll
+      for (int s = 0; s < NSEC; ++s)
+        v = section_step<FIRST_ORDER>(sec[s], v, c);
+      pd[(int64_t) r * SGN] = v;
+    }
+#pragma unroll
+    for (int s = 0; s < NSEC; ++s)
+      truth[s] = make_float4(sec[s].in_d1, sec[s].in_d2, sec[s].out_d1, sec[s].out_d2);
+  }
+#pragma unroll
+  for (int s = 0; s < NSEC; ++s)
+    *reinterpret_cast<float4 *>(state + ((int64_t) q * NSEC + s) * 4) = truth[s];
+  if (bad && mismatches)
+    atomicAdd(mismatches, bad);
+}
+
 template <int NSEC>
 cudaError_t launch_tm(const float *src, float *dst, int64_t rows_cap, int row_first, int n_rows, int n_series,
-                      const BiquadParams &c, float *state, int block_rows, int warm_rows, cudaStream_t stream) {
+                      const BiquadParams &c, float *state, int block_rows, int warm_rows, float *blk_state,
+                      unsigned int *mismatches, cudaStream_t stream) {
   const int n_blocks = block_rows > 0 ? (n_rows + block_rows - 1) / block_rows : 1;
+  float4 *rec = block_rows > 0 ? reinterpret_cast<float4 *>(blk_state) : nullptr;
   const dim3 grid((n_series + SGN - 1) / SGN, n_blocks);
   const size_t smem = sizeof(float) * BSTAGES * RB * SGN + BSTAGES * sizeof(uint64_t);
   static PerDeviceOnce once;
@@ -213,34 +300,55 @@ cudaError_t launch_tm(const float *src, float *dst, int64_t rows_cap, int row_fi
   }
   if (c.first_order)
     espb_biquad_tm_kernel<NSEC, true><<<grid, SGN, smem, stream>>>(src, dst, rows_cap, row_first, n_rows, c, state,
-                                                                   n_series, block_rows, warm_rows);
+                                                                   n_series, block_rows, warm_rows, rec);
   else
     espb_biquad_tm_kernel<NSEC, false><<<grid, SGN, smem, stream>>>(src, dst, rows_cap, row_first, n_rows, c, state,
-                                                                    n_series, block_rows, warm_rows);
+                                                                    n_series, block_rows, warm_rows, rec);
   count_launch();
+  if (rec) {  // prove (or repair) the block hand-overs and commit the final state
+    if (c.first_order)
+      espb_biquad_verify_kernel<NSEC, true><<<grid.x, SGN, 0, stream>>>(src, dst, rows_cap, row_first, n_rows, c, state,
+                                                                       n_series, block_rows, n_blocks, rec, mismatches);
+    else
+      espb_biquad_verify_kernel<NSEC, false><<<grid.x, SGN, 0, stream>>>(src, dst, rows_cap, row_first, n_rows, c,
+                                                                        state, n_series, block_rows, n_blocks, rec,
+                                                                        mismatches);
+    count_launch();
+  }
   return cudaGetLastError();
 }
 
 }  // namespace
 
+size_t biquad_block_state_floats(int n_series, int n_sections, int n_rows, int block_rows) {
+  if (block_rows <= 0 || block_rows >= n_rows)
+    return 0;
+  const size_t n_blocks = ((size_t) n_rows + block_rows - 1) / block_rows;
+  return (size_t) ((n_series + SGN - 1) / SGN) * n_blocks * n_sections * 2 * SGN * 4;
+}
+
 cudaError_t launch_biquad_tm(const float *src, float *dst, int64_t rows_cap, int row_first, int n_rows, int n_series,
                              int n_sections, BiquadParams c, float *state, int block_rows, int warm_rows,
-                             cudaStream_t stream) {
+                             cudaStream_t stream, float *blk_state, unsigned int *mismatches) {
   if (n_series <= 0 || n_rows <= 0)
     return cudaSuccess;
-  if (block_rows > 0 && (block_rows % RB || warm_rows % RB || src == dst))
-    return cudaErrorInvalidValue;  // time blocks: multiples of the 32-row chunk, and out of place
   if (block_rows >= n_rows)
     block_rows = 0;
+  if (block_rows > 0 && (block_rows % RB || warm_rows % RB || src == dst || !blk_state))
+    return cudaErrorInvalidValue;  // time blocks: multiples of the 32-row chunk, out of place, with a state record
   switch (n_sections) {
     case 1:
-      return launch_tm<1>(src, dst, rows_cap, row_first, n_rows, n_series, c, state, block_rows, warm_rows, stream);
+      return launch_tm<1>(src, dst, rows_cap, row_first, n_rows, n_series, c, state, block_rows, warm_rows,
+                          blk_state, mismatches, stream);
     case 2:
-      return launch_tm<2>(src, dst, rows_cap, row_first, n_rows, n_series, c, state, block_rows, warm_rows, stream);
+      return launch_tm<2>(src, dst, rows_cap, row_first, n_rows, n_series, c, state, block_rows, warm_rows,
+                          blk_state, mismatches, stream);
     case 3:
-      return launch_tm<3>(src, dst, rows_cap, row_first, n_rows, n_series, c, state, block_rows, warm_rows, stream);
+      return launch_tm<3>(src, dst, rows_cap, row_first, n_rows, n_series, c, state, block_rows, warm_rows,
+                          blk_state, mismatches, stream);
     case 4:
-      return launch_tm<4>(src, dst, rows_cap, row_first, n_rows, n_series, c, state, block_rows, warm_rows, stream);
+      return launch_tm<4>(src, dst, rows_cap, row_first, n_rows, n_series, c, state, block_rows, warm_rows,
+                          blk_state, mismatches, stream);
     default:
       return cudaErrorInvalidValue;
   }

@@ -73,6 +73,33 @@ cudaError_t launch_transpose(const float *in, int64_t in_ss, int64_t in_cs, int6
                              int n_in, float *xt, int64_t rows_cap, int row_first, int pad_rows,
                              cudaStream_t stream);
 
+// Few-series form (resample_fs_kernel.cu): lanes own outputs instead of series; no expanded coefficients, no
+// chunk tables — the finalized schedule, the time-major staging rows and a slice-major copy of the bank.
+struct FsParams {
+  const float *x;    // frame j of series q: x[(j + x_row0) * x_fs + q]
+  int64_t x_fs;
+  int x_row0;
+  float *out;
+  int64_t out_ss, out_cs, out_fs;
+  float *out_tm;     // if not NULL: time-major rows of 128 floats instead of `out`
+  const float *bank_tr;  // [taps / kt][slice_floats]
+  const OutEntry *outs;  // finalized
+  int n_series, channels, n_out, taps;
+  int kt, slice_floats;
+  int q_per_out, x_tile_floats, out_vec;  // set by the launcher
+};
+struct FsGeometry {
+  int sv, b, q;          // series per lane, outputs per lane, lanes per output
+  int outputs_per_cta;
+};
+constexpr int kFsMaxSeries = 32;
+int fs_slice_taps(int taps, int filters);
+size_t fs_slice_floats(int filters, int kt);
+void fs_build_bank_slices(const float *bank, int taps, int filters, int kt, float *dst);
+FsGeometry fs_geometry(int n_series);
+size_t fs_smem_bytes(const FsGeometry &g, size_t slice_floats, int x_rows);
+cudaError_t launch_resample_fs(const FsParams &p, const FsGeometry &g, int x_rows, bool exact, cudaStream_t stream);
+
 // quantization_utils
 cudaError_t launch_q2f(const uint8_t *in, int64_t in_row_bytes, float *out, int64_t out_row_floats, int rows,
                        uint32_t row_samples, int bits, float gain_factor, cudaStream_t stream);
@@ -101,9 +128,14 @@ struct BiquadParams {
 };
 // time-major filter of rows [row_first, row_first + n_rows) of src[group][rows_cap][128] into dst (same
 // geometry; may be src itself when block_rows == 0).  block_rows > 0: time blocks with warm_rows of warm-up.
+// Time blocks need `blk_state` (biquad_block_state_floats() floats: the state every block reached at its first row and
+// at its end, which espb_biquad_verify_kernel compares — and repairs where they differ — before committing the final
+// state) and may be given a counter of repaired blocks.
+size_t biquad_block_state_floats(int n_series, int n_sections, int n_rows, int block_rows);
 cudaError_t launch_biquad_tm(const float *src, float *dst, int64_t rows_cap, int row_first, int n_rows, int n_series,
                              int n_sections, BiquadParams c, float *state /* [series][section][4] */,
-                             int block_rows, int warm_rows, cudaStream_t stream);
+                             int block_rows, int warm_rows, cudaStream_t stream, float *blk_state = nullptr,
+                             unsigned int *mismatches = nullptr);
 // time-major -> caller layout (inverse of launch_transpose): rows [row_first, row_first + n_rows)
 cudaError_t launch_untranspose(const float *tm, int64_t rows_cap, int row_first, int n_rows, float *out,
                                int64_t out_ss, int64_t out_cs, int64_t out_fs, int channels, int n_series,

@@ -180,13 +180,18 @@ int espb_biquad_apply_buffer(EspbBiquadBatch *f, float *buf, const EspbLayout *l
 /* biquad_apply_sample (art_biquad.cpp:55-69), batched: one new sample per series (samples[q], device memory, filtered
  * in place); every series' delays advance by one step.  A latency-bound call — use apply_buffer for throughput. */
 int espb_biquad_apply_samples(EspbBiquadBatch *f, float *samples, void *stream);
-/* Long single streams: filter time blocks of `block_rows` frames in parallel, each after re-running the
- * recurrence over the `warmup_rows` frames before it from a zero state (multiples of 32; 0/0 = off, the
- * default: one exact sequential run per series).  The two trajectories merge bit-exactly once they round to
- * the same consecutive outputs — within 256 frames for the pole radii the Resampler policy produces
- * (cutoff >= 0.16: radius <= 0.77), measured; not guaranteed for radii near 1 (cutoff < 0.02), where the
- * deviation is ~1e-7..4e-6.  Use a warm-up of >= 1024 frames. */
+/* Long single streams (the north star's "block-parallel state carry"): time blocks of `block_rows` frames are
+ * filtered in parallel, each after re-running the recurrence over the `warmup_rows` frames before it from a zero
+ * state.  The hand-over between blocks is VERIFIED on the device — block k's state at its first frame must equal
+ * block k-1's end state bit for bit (equal state + equal input = equal continuation) — and a block whose warm-up
+ * did not converge is filtered again from the true state, so the output is the sequential one of
+ * art_biquad.cpp:73-93 by construction; a failed merge costs time, never bits (and doubles the warm-up of later
+ * calls).  block_rows: -1 = automatic (the default: blocks of 8192 frames when the bank has <= 4096 series and the
+ * call is >= 16384 frames long), 0 = one sequential run per series, > 0 = that many frames (multiple of 32).
+ * warmup_rows: multiple of 32 (default 1024; 0 keeps the current value in automatic mode). */
 int espb_biquad_set_time_blocks(EspbBiquadBatch *f, int block_rows, int warmup_rows);
+/* blocks repaired so far (0: every warm-up merged) and the current warm-up length; synchronises with the last call */
+int espb_biquad_block_stats(EspbBiquadBatch *f, uint64_t *repaired_blocks, int *warmup_rows);
 int espb_biquad_get_state(EspbBiquadBatch *f, float *host_dst /* num_series*num_sections*4: in_d1,in_d2,out_d1,out_d2 */);
 
 /* ---- quantization_utils: replaces include/quantization_utils.h:15-25 ------------ */
@@ -239,6 +244,7 @@ void espb_resampler_free(EspbResampler *r);
 int espb_resampler_set_mode(EspbResampler *r, int mode);
 /* time-block mode of the pre/post low-pass (see espb_biquad_set_time_blocks) */
 int espb_resampler_set_biquad_time_blocks(EspbResampler *r, int block_rows, int warmup_rows);
+int espb_resampler_biquad_block_stats(EspbResampler *r, uint64_t *repaired_blocks, int *warmup_rows);
 /* policy introspection: 0 none / 1 pre / 2 post; coefficients; ART low-pass and flags */
 int espb_resampler_policy(EspbResampler *r, EspbBiquadCoefficients *coeffs, float *sample_ratio, float *art_lowpass,
                           int *art_flags);

@@ -147,6 +147,46 @@ def test_biquad_time_blocks_merge_bit_exactly(oracle, f):
     bq.free()
 
 
+@pytest.mark.parametrize("f,warm", [(0.02, 1024), (0.005, 1024), (0.005, 32), (0.0007, 256), (0.2274, 32)])
+def test_biquad_time_blocks_are_exact_by_construction(oracle, f, warm):
+    """Low cutoffs (pole radius 0.92 .. 0.997) and warm-ups far too short for the trajectories to merge: the device
+    compares every block's start state with its predecessor's end state and re-filters the block where they differ,
+    so the output and the saved state are still the sequential ones (art_biquad.cpp:73-93) bit for bit — over two
+    calls, with the automatic default (blocks of 8192 rows) and with explicit small blocks."""
+    channels, streams, n = 2, 3, 70000
+    x = np.stack([noise(n, channels, stream=20 + s, amp=0.9) for s in range(streams)])
+    c = espb.biquad_lowpass(f)
+    ref = x.copy()
+    states = []
+    for s in range(streams):
+        for ch in range(channels):
+            st = []
+            for _ in range(2):
+                b = oracle.biquad(c, 1.0)
+                b.apply_buffer(ref[s][ch:], channels, n=n)
+                st.append(b)
+            states.append(st)
+    for blocks in (-1, 2048):
+        bq = espb.BiquadBatch(streams * channels, 2, c, 1.0)
+        bq.set_time_blocks(blocks, warm)
+        y1 = bq.apply_interleaved(x[:, : 41000 * channels], channels)
+        y2 = bq.apply_interleaved(x[:, 41000 * channels:], channels)
+        y = np.concatenate([y1, y2], axis=1)
+        assert bits_equal(y, ref), (f, warm, blocks)
+        repaired, warm_now = bq.block_stats()
+        if f <= 0.005:   # these cannot merge within the warm-up: the repair path is what made the result exact
+            assert repaired > 0 and warm_now > warm
+        # the saved state is the sequential one too: a third (short, sequential) call continues identically
+        tail = noise(500, channels, stream=99, amp=0.5).reshape(1, -1).repeat(streams, axis=0)
+        y3 = bq.apply_interleaved(tail, channels)
+        bq2 = espb.BiquadBatch(streams * channels, 2, c, 1.0)
+        bq2.set_time_blocks(0, 0)
+        bq2.apply_interleaved(x, channels)
+        assert bits_equal(y3, bq2.apply_interleaved(tail, channels))
+        bq.free()
+        bq2.free()
+
+
 def test_wrapper_with_biquad_time_blocks(oracle):
     """C4-like call (96 -> 44.1 kHz, 8 channels, 24-bit, pre-filter) with the pre-filter in time-block mode."""
     ns, ch, frames = 2, 8, 20000
@@ -255,10 +295,16 @@ def test_resampler_chunked_streaming_is_bit_identical(oracle, golden):
     ns = 4
     b = espb.ResampleBatch(ns, ch, m["taps"], m["filters"], 1.0, m["flags"], mode=espb.MODE_EXACT)
     b.advance(m["advance"])
+    o_dry = oracle.resampler(ch, m["taps"], m["filters"], 1.0, m["flags"])
+    o_dry.advance(m["advance"])
     outs, pos = [], 0
     for n_in, n_out, used, gen in plan:
         seg = np.stack([x[pos * ch:(pos + int(n_in)) * ch]] * ns)
-        assert b.required(int(n_out), f32(m["ratio"])) >= 0
+        # dry runs on a context with carried state (art_resampler.cpp:257-306) against the oracle in the same state
+        assert b.required(int(n_out), f32(m["ratio"])) == o_dry.required(int(n_out), f32(m["ratio"]))
+        assert b.expected(int(n_in), f32(m["ratio"])) == o_dry.expected(int(n_in), f32(m["ratio"]))
+        assert b.position() == o_dry.position()
+        o_dry.process_interleaved(x[pos * ch:(pos + int(n_in)) * ch], int(n_out), f32(m["ratio"]), n_in=int(n_in))
         y, u, g = b.process_interleaved(seg.reshape(ns, -1), int(n_out), f32(m["ratio"]), n_in=int(n_in))
         assert (u, g) == (used, gen)
         outs.append(y)
