@@ -221,6 +221,357 @@ def bind_to_gpu_cpus(gpu):
         return f"unpinned ({type(exc).__name__})"
 
 
+class Ranks:
+    """Barrier / max-over-ranks / gather for one process per GPU.  N > 1 goes through the library's own C entry
+    points (espb_dist_*: ncclCommInitRank + ncclAllGather over NVLink) — no torch in this file."""
+
+    def __init__(self, espb, rank, world):
+        self.espb, self.rank, self.world = espb, rank, world
+        self.nccl = espb.NcclGather(rank, world) if world > 1 else None
+
+    def barrier(self):
+        L = self.espb.lib()
+        self.espb.capi._check(L.espb_device_sync(), "sync")
+        if self.nccl:
+            self.nccl.barrier()
+            self.espb.capi._check(L.espb_device_sync(), "sync")
+
+    def max(self, v):
+        return self.nccl.max_float(v) if self.nccl else float(v)
+
+    def gather(self, words):
+        return self.nccl.allgather(words) if self.nccl else [[int(w) for w in words]]
+
+    def close(self):
+        if self.nccl:
+            self.nccl.close()
+
+
+def timed_steps(espb, ranks, stream, step, steps, warmup):
+    """W warm-up steps, then K steps between CUDA events on `stream`, bracketed by barrier + device sync on both
+    sides; returns (ms per step, max over ranks)."""
+    L = espb.lib()
+    for _ in range(warmup):
+        step()
+    ranks.barrier()
+    ev0, ev1 = L.espb_event_create(), L.espb_event_create()
+    L.espb_event_record(ev0, stream)
+    for _ in range(steps):
+        step()
+    L.espb_event_record(ev1, stream)
+    ms = espb.capi.C.c_float(0)
+    espb.capi._check(L.espb_event_elapsed_ms(ev0, ev1, espb.capi.C.byref(ms)), "elapsed")
+    ranks.barrier()
+    L.espb_event_destroy(ev0)
+    L.espb_event_destroy(ev1)
+    return ranks.max(float(ms.value)) / steps
+
+
+def timed_wall(ranks, step, steps, warmup):
+    """End-to-end legs: synchronous host-buffer calls, wall clock between barriers, max over ranks."""
+    for _ in range(warmup):
+        step()
+    ranks.barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    ranks.barrier()
+    return ranks.max((time.perf_counter() - t0) / steps)
+
+
+def pcm_rows(n_rows, n_samples, bits, distinct, seed, first_row=0):
+    """Packed little-endian PCM rows: Gaussian noise at -12 dBFS, `distinct` different rows tiled by GLOBAL row index
+    (so a sharded batch holds the same streams whatever the number of ranks)."""
+    nb = (bits + 7) // 8
+    rng = np.random.default_rng(seed)
+    base = (rng.normal(0, 0.25, size=(distinct, n_samples)).clip(-1, 0.9999) * (2 ** (8 * nb - 1))).astype(np.int64)
+    raw = np.zeros((distinct, n_samples * nb), np.uint8)
+    for b in range(nb):
+        raw[:, b::nb] = (base >> (8 * b)) & 0xFF
+    idx = (np.arange(n_rows) + first_row) % distinct
+    return raw[idx]
+
+
+def link_fraction(e2e_bytes, e2e_seconds, link):
+    """Bytes per second over the host link during the e2e step, against the duplex rate the link probe measured in
+    this run with every rank copying at the same time."""
+    if not link or not link.get("duplex_sum_gbs"):
+        return None
+    return (e2e_bytes / e2e_seconds / 1e9) / link["duplex_sum_gbs"]
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# configs[2]: 16 kHz -> 48 kHz mono voice, art_biquad post-filter, 16384 streams, int16 in / int16 out (wrapper)
+# ---------------------------------------------------------------------------------------------------------------
+def bench_c3(espb, ranks, stream, peak_tf, link, steps, want_e2e, checks):
+    L = espb.lib()
+    ns, ch, sr, dr, bits, taps, filters, frames = 16384, 1, 16000, 48000, 16, 256, 256, 16000
+    cap = frames * 3 + 64
+    raw = pcm_rows(ns, frames * ch, bits, 64, 3, first_row=ranks.rank * ns)
+    r = espb.Resampler(ns, frames * ch, cap * ch, sr, dr, bits, bits, ch, True, True, taps, filters)
+    r.set_option(espb.OPT_PLAN_CACHE, 0)
+    r.set_option(espb.OPT_KERNEL_TIMING, 1)
+    in_row, out_row = raw.shape[1], (cap * ch * 2 + 15) & ~15
+    d_in, d_out = espb.DeviceBuffer.from_numpy(raw), espb.DeviceBuffer(ns * out_row)
+    res, calls = {}, [0]
+
+    def step():  # steady-state streaming call: state carried from call to call, enqueued without synchronising
+        res["r"] = r.resample_dev_async(d_in.ptr, in_row, d_out.ptr, out_row, frames, cap, 0.0, stream)
+        calls[0] += 1
+
+    ms = timed_steps(espb, ranks, stream, step, steps, 3)
+    k_ms, k_n = r.kernel_time()
+    gen = res["r"]["frames_generated"]
+    samples_rank = gen * ch * ns
+    k_ms_call = k_ms / max(calls[0], 1)
+    tf = 4.0 * taps * samples_rank / (k_ms_call * 1e-3) / 1e12 if k_ms_call > 0 else 0.0
+    rec = {"workload": "16 kHz -> 48 kHz mono voice, art_biquad post-filter (2 sections), 16384 streams per GPU, "
+                       "int16 in / int16 out through espb_resampler_resample_async, 1 s (16000 frames) per step",
+           "scaling": "weak", "value": samples_rank * ranks.world / (ms * 1e-3) / 1e6, "unit": "Msamples/s",
+           "ms_per_step": ms, "frames_out": gen, "filter": r.policy()["filter"],
+           "roofline": {"kernel": "espb_resample_kernel (time-major in, time-major out)", "bound": "fp32_fma",
+                        "achieved": tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": tf / peak_tf if peak_tf else None,
+                        "kernel_ms": k_ms_call, "kernel_share_of_step": k_ms_call / ms if ms else None},
+           "hbm_bytes_per_step_algorithmic": ns * (frames * 2 + gen * 2),
+           "l2": "PCM in + out 2.1 GB per step >> L2"}
+    if want_e2e:
+        h_in = espb.PinnedBuffer(raw.size, np.uint8)
+        h_in.array[:] = raw.reshape(-1)
+        h_out = espb.PinnedBuffer(ns * out_row, np.uint8)
+        rr = {}
+
+        def e2e_step():
+            rr["r"] = r.resample_host_ptr(h_in.ptr, in_row, h_out.ptr, out_row, frames, cap, 0.0)
+            calls[0] += 1
+
+        sec = timed_wall(ranks, e2e_step, max(3, min(steps, 6)), 2)
+        g2 = rr["r"]["frames_generated"]
+        nbytes = ns * (frames * 2 + g2 * 2)
+        rec["e2e"] = {"value": g2 * ch * ns * ranks.world / sec / 1e6, "unit": "Msamples/s", "ms_per_step": sec * 1e3,
+                      "h2d_bytes_per_step": ns * frames * 2, "d2h_bytes_per_step": ns * g2 * 2,
+                      "api": "espb_resampler_resample_host (int16 PCM on the wire: half the bytes of the float call)",
+                      "frac_of_link": link_fraction(nbytes, sec, link)}
+        if checks is not None:  # the CPU leg re-computes one stream: same input `calls` times through the oracle
+            row = ns - 1
+            checks.append(("C3", dict(raw=raw[row].copy(), calls=calls[0], frames=frames, cap=cap, sr=sr, dr=dr,
+                                      got=h_out.array.reshape(ns, out_row)[row, : g2 * 2].copy(), gen=g2), rec))
+        h_in.free()
+        h_out.free()
+    rec["checksum"] = espb.checksum_u32(d_out.ptr, ns * out_row // 4, stream) & 0x7FFFFFFFFFFFFFFF
+    r.free()
+    d_in.free()
+    d_out.free()
+    return rec
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# configs[3]: 96 kHz -> 44.1 kHz, 24-bit, 8 channels, 1024 taps, ONE long stream per GPU (pre-filter in time blocks)
+# ---------------------------------------------------------------------------------------------------------------
+def bench_c4(espb, ranks, stream, peak_tf, link, steps, want_e2e, checks):
+    ns, ch, sr, dr, bits, taps, filters, seconds = 1, 8, 96000, 44100, 24, 1024, 256, 30
+    frames = sr * seconds
+    cap = int(frames * dr / sr) + 64
+    raw = pcm_rows(ns, frames * ch, bits, 1, 4 + ranks.rank)
+    in_row, out_row = raw.shape[1], (cap * ch * 3 + 15) & ~15
+    d_in, d_out = espb.DeviceBuffer.from_numpy(raw), espb.DeviceBuffer(ns * out_row)
+    r = espb.Resampler(ns, frames * ch, cap * ch, sr, dr, bits, bits, ch, True, True, taps, filters)
+    r.set_option(espb.OPT_PLAN_CACHE, 0)
+    first = r.resample_dev(d_in.ptr, in_row, d_out.ptr, out_row, frames, cap, 0.0, stream)  # fresh state: checked below
+    head = d_out.download(np.uint8, 44100 * ch * 3)
+    r.set_option(espb.OPT_KERNEL_TIMING, 1)
+    res, calls = {}, [0]
+
+    def step():
+        res["r"] = r.resample_dev_async(d_in.ptr, in_row, d_out.ptr, out_row, frames, cap, 0.0, stream)
+        calls[0] += 1
+
+    ms = timed_steps(espb, ranks, stream, step, steps, 3)
+    k_ms, k_n = r.kernel_time()
+    gen = res["r"]["frames_generated"]
+    samples_rank = gen * ch * ns
+    k_ms_call = k_ms / max(calls[0], 1)
+    tf = 4.0 * taps * samples_rank / (k_ms_call * 1e-3) / 1e12 if k_ms_call > 0 else 0.0
+    repaired, warm = r.biquad_block_stats()
+    rec = {"workload": f"96 kHz -> 44.1 kHz, 8 channels, 24-bit in / out, 1024 taps, art_biquad pre-filter, ONE stream "
+                       f"per GPU, {seconds} s ({frames} frames) per step (replicas only: a stream does not shard)",
+           "scaling": "replicas", "value": samples_rank * ranks.world / (ms * 1e-3) / 1e6, "unit": "Msamples/s",
+           "ms_per_step": ms, "frames_out": gen, "filter": r.policy()["filter"],
+           "realtime_factor": seconds / (ms * 1e-3),
+           "biquad": {"mode": "time blocks of 8192 frames, hand-over verified on the device (exact by construction)",
+                      "blocks_repaired": repaired, "warmup_rows": warm},
+           "roofline": {"kernel": "espb_resample_fs_kernel<SV=8,B=2> (few-series form: lanes own outputs)",
+                        "bound": "shared-memory wavefronts (FP32 FMA peak as the denominator)", "achieved": tf,
+                        "peak": peak_tf, "unit": "TFLOP/s", "frac": tf / peak_tf if peak_tf else None,
+                        "kernel_ms": k_ms_call, "kernel_share_of_step": k_ms_call / ms if ms else None},
+           "l2": "PCM in 69 MB per step, but every stage streams the time-major staging rows (2 x 1.5 GB) >> L2"}
+    if want_e2e:
+        h_in = espb.PinnedBuffer(raw.size, np.uint8)
+        h_in.array[:] = raw.reshape(-1)
+        h_out = espb.PinnedBuffer(ns * out_row, np.uint8)
+        rr = {}
+
+        def e2e_step():
+            rr["r"] = r.resample_host_ptr(h_in.ptr, in_row, h_out.ptr, out_row, frames, cap, 0.0)
+
+        sec = timed_wall(ranks, e2e_step, 3, 1)
+        g2 = rr["r"]["frames_generated"]
+        rec["e2e"] = {"value": g2 * ch * ns * ranks.world / sec / 1e6, "unit": "Msamples/s", "ms_per_step": sec * 1e3,
+                      "h2d_bytes_per_step": ns * frames * ch * 3, "d2h_bytes_per_step": ns * g2 * ch * 3,
+                      "api": "espb_resampler_resample_host (24-bit PCM on the wire)",
+                      "frac_of_link": link_fraction(ns * (frames + g2) * ch * 3, sec, link)}
+        h_in.free()
+        h_out.free()
+    if checks is not None:  # first second of the first (fresh-state) call against the composed CPU pipeline
+        checks.append(("C4", dict(raw=raw[0, : 96000 * ch * 3].copy(), head=head, pol=r.policy(), ch=ch, taps=taps,
+                                  filters=filters), rec))
+    rec["first_call_frames"] = first["frames_generated"]
+    rec["checksum"] = espb.checksum_u32(d_out.ptr, ns * out_row // 4, stream) & 0x7FFFFFFFFFFFFFFF
+    r.free()
+    d_in.free()
+    d_out.free()
+    return rec
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# configs[4]: 65536 stereo float streams 48 kHz -> 44.1 kHz, sharded by stream index over the ranks (STRONG scaling)
+# ---------------------------------------------------------------------------------------------------------------
+def bench_c5(espb, ranks, stream, peak_tf, link, steps, want_e2e, checks):
+    L = espb.lib()
+    total, ch, taps, filters, flags = 65536, 2, 256, 256, 0x1
+    ratio = f32(44100) / f32(48000)
+    lowpass = float(ratio * f32(0.96))
+    chunk, calls_per_step = 6000, 8  # 1 s per stream per step as 8 streaming calls of 0.125 s (bounded memory)
+    first, ns = espb.shard_range(total, ranks.rank, ranks.world)
+    cap = int(chunk * float(ratio)) + 64
+    in_row, out_row = chunk * ch, cap * ch
+    from signals import multitone, noise
+    base = np.stack([multitone(chunk, ch, 48000.0, stream=s, amp=0.5) if s % 2 == 0
+                     else noise(chunk, ch, stream=s, amp=0.5) for s in range(DISTINCT)])
+    idx = (np.arange(ns) + first) % DISTINCT  # by GLOBAL stream index: the same batch for every N
+    h_in = espb.PinnedBuffer(ns * in_row, f32)
+    h_in.array.reshape(ns, in_row)[:] = base[idx]
+    d_in, d_out = espb.DeviceBuffer(ns * in_row * 4), espb.DeviceBuffer(ns * out_row * 4)
+    espb.capi._check(L.espb_memcpy_h2d(d_in.ptr, h_in.ptr, ns * in_row * 4, stream), "h2d")
+    d_out.zero(stream)
+    ctx = espb.ResampleBatch(ns, ch, taps, filters, lowpass, flags)
+    ctx.set_option(espb.OPT_PLAN_CACHE, 0)
+    ctx.set_option(espb.OPT_KERNEL_TIMING, 1)
+    out = {}
+
+    def step():
+        ctx.reset(stream)
+        ctx.advance(taps / 2.0)
+        g = 0
+        for _ in range(calls_per_step):
+            u, gg = ctx.process_interleaved_dev(d_in.ptr, in_row, chunk, d_out.ptr, out_row, cap, ratio, stream)
+            g += gg
+        out["gen"], out["last"] = g, gg
+
+    ms = timed_steps(espb, ranks, stream, step, steps, 3)
+    k_ms, k_n = ctx.kernel_time()
+    gen = out["gen"]
+    samples_rank = gen * ch * ns
+    k_ms_step = k_ms / (steps + 3)
+    tf = 4.0 * taps * samples_rank / (k_ms_step * 1e-3) / 1e12 if k_ms_step > 0 else 0.0
+    # per-stream checksums are order independent, so the sum over ranks must not depend on N
+    checksum = espb.checksum_u32(d_out.ptr, ns * out_row, stream)  # wrapping 64-bit sum: adds up over shards
+    g = ranks.gather([checksum, gen, first, ns])
+    assert [x[2] for x in g] == [espb.shard_range(total, r, ranks.world)[0] for r in range(ranks.world)]
+    assert sum(x[3] for x in g) == total
+    rec = {"workload": "65536 stereo float streams 48 kHz -> 44.1 kHz, 256 taps, ART low-pass 0.96 x ratio, sharded "
+                       "by stream index over the ranks; 1 s per stream per step as 8 streaming calls of 6000 frames",
+           "scaling": "strong", "streams_total": total, "streams_per_rank": ns,
+           "value": gen * ch * total / (ms * 1e-3) / 1e6, "unit": "Msamples/s", "ms_per_step": ms,
+           "frames_out_per_step": gen,
+           "roofline": {"kernel": "espb_resample_kernel<BPP=4,STAGES=2,CHUNK_ROWS=32>", "bound": "fp32_fma",
+                        "achieved": tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": tf / peak_tf if peak_tf else None,
+                        "kernel_ms_per_step": k_ms_step, "kernel_share_of_step": k_ms_step / ms if ms else None},
+           "checksums": [x[0] for x in g], "checksum_of_checksums": espb.combine_checksums([x[0] for x in g]),
+           "gather": "ncclAllGather of {checksum, frames, first stream, streams} per rank through espb_dist_allgather_u64"
+                     if ranks.world > 1 else "single rank",
+           "l2": "input + output 12 GB per step over all ranks >> L2"}
+    if want_e2e:
+        h_out = espb.PinnedBuffer(ns * out_row, f32)
+        rr = {}
+
+        def e2e_step():
+            ctx.reset(None)
+            ctx.advance(taps / 2.0)
+            gsum = 0
+            for _ in range(calls_per_step):
+                u, gg = ctx.process_interleaved_host(h_in.ptr, in_row, chunk, h_out.ptr, out_row, cap, ratio)
+                gsum += gg
+            rr["gen"], rr["last"] = gsum, gg
+
+        sec = timed_wall(ranks, e2e_step, 2, 1)
+        nbytes = ns * (calls_per_step * in_row * 4 + rr["gen"] * ch * 4)
+        rec["e2e"] = {"value": rr["gen"] * ch * total / sec / 1e6, "unit": "Msamples/s", "ms_per_step": sec * 1e3,
+                      "h2d_bytes_per_step": ns * calls_per_step * in_row * 4, "d2h_bytes_per_step": ns * rr["gen"] * ch * 4,
+                      "api": "espb_resampleProcessInterleavedHost, 8 calls per step",
+                      "frac_of_link": link_fraction(nbytes, sec, link)}
+        if checks is not None:
+            row = ns - 1
+            checks.append(("C5", dict(x=h_in.array.reshape(ns, in_row)[row].copy(), calls=calls_per_step, cap=cap,
+                                      ratio=ratio, lowpass=lowpass, flags=flags, taps=taps, filters=filters,
+                                      got=h_out.array.reshape(ns, out_row)[row, : rr["last"] * ch].copy(),
+                                      gen=rr["last"]), rec))
+        h_out.free()
+    ctx.free()
+    h_in.free()
+    d_in.free()
+    d_out.free()
+    return rec
+
+
+def run_checks(checks, mode):
+    """CPU leg (rank 0, N = 1): one stream of every sub-record re-computed by the CPU restatement of the reference."""
+    from oracle_lib import Oracle
+    orc = Oracle()
+    tol = 0.0 if mode == "exact" else 1e-6
+    for name, c, rec in checks:
+        if name == "C3":  # fast mode: PCM codes may differ by 1 LSB where the float result sits on a rounding edge
+            w = orc.wrapper(c["frames"], c["cap"], float(c["sr"]), float(c["dr"]), 16, 16, 1)
+            for _ in range(c["calls"]):
+                yo, ro = w.resample(c["raw"], c["frames"], c["cap"], 0.0)
+            assert ro["frames_generated"] == c["gen"], (name, ro["frames_generated"], c["gen"])
+            d = np.abs(c["got"].view(np.int16).astype(np.int64) - yo.view(np.int16).astype(np.int64))
+            if int(d.max()) > 1:
+                raise SystemExit(f"bench.py: {name} parity check failed (max PCM code difference {int(d.max())})")
+            rec["parity_vs_oracle"] = {"max_lsb": int(d.max()), "codes_differing": float((d > 0).mean()),
+                                       "stream_calls_replayed": c["calls"]}
+        elif name == "C4":
+            from oracle_lib import Oracle as _O  # noqa: F401
+            ch, taps, pol = c["ch"], c["taps"], c["pol"]
+            xf = orc.quantized_to_float(c["raw"], 96000 * ch, 24, 0.0)
+            if pol["filter"] == "pre":
+                for k in range(ch):
+                    for _ in range(2):
+                        orc.biquad(pol["coeffs"], 1.0).apply_buffer(xf[k:], ch, n=96000)
+            o = orc.resampler(ch, taps, c["filters"], float(pol["art_lowpass"]), pol["art_flags"])
+            o.advance(taps / 2.0)
+            yf, used, gen = o.process_interleaved(xf, 44200, pol["sample_ratio"])
+            q, _ = orc.float_to_quantized(np.ascontiguousarray(yf), 24)
+            n = (gen - 600) * ch * 3  # the one-second CPU run lacks the frames after it: compare what both know
+            a = np.frombuffer(c["head"][:n].tobytes(), np.uint8).reshape(-1, 3).astype(np.int64)
+            b = np.frombuffer(q[:n].tobytes(), np.uint8).reshape(-1, 3).astype(np.int64)
+            va = a[:, 0] | (a[:, 1] << 8) | (a[:, 2] << 16)
+            vb = b[:, 0] | (b[:, 1] << 8) | (b[:, 2] << 16)
+            d = np.abs(((va ^ 0x800000) - 0x800000) - ((vb ^ 0x800000) - 0x800000))
+            if int(d.max()) > 8:  # 1e-6 full scale = 8.4 codes at 24 bits
+                raise SystemExit(f"bench.py: {name} parity check failed (max PCM code difference {int(d.max())})")
+            rec["parity_vs_oracle"] = {"max_lsb_24bit": int(d.max()), "codes_differing": float((d > 0).mean()),
+                                       "frames_compared": gen - 600}
+        elif name == "C5":
+            o = orc.resampler(2, c["taps"], c["filters"], c["lowpass"], c["flags"])
+            o.advance(c["taps"] / 2.0)
+            for _ in range(c["calls"]):
+                yo, uo, go = o.process_interleaved(c["x"], c["cap"], c["ratio"])
+            err = float(np.max(np.abs(c["got"].astype(np.float64) - yo[: go * 2])))
+            if go != c["gen"] or err > tol:
+                raise SystemExit(f"bench.py: {name} parity check failed (generated {c['gen']} vs {go}, max-abs {err})")
+            rec["parity_vs_oracle"] = {"max_abs": err, "calls_replayed": c["calls"]}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -230,6 +581,7 @@ def main():
     ap.add_argument("--streams", type=int, default=STREAMS_PER_GPU, help="streams per GPU (default: the metric's 4096)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the C3 / C4 / C5 sub-records")
     ap.add_argument("--mode", default="fast", choices=["fast", "exact"],
                     help="arithmetic of the dot products: fast = FFMA2 chain (the metric), exact = un-fused, bit-exact")
     args = ap.parse_args()
@@ -244,19 +596,13 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    dist = None
-    if world > 1:
-        import torch
-        import torch.distributed as dist_mod
-        torch.cuda.set_device(local_rank)
-        dist_mod.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-        dist = dist_mod
     if espb.device_count() <= 0:
         raise SystemExit("bench.py: no GPU and no CPU fallback (use --impl reference for the CPU arm)")
     espb.set_device(local_rank)
     info = espb.device_info()
     L = espb.lib()
     host_affinity = bind_to_gpu_cpus(local_rank)  # before the pinned buffers are allocated and touched
+    ranks = Ranks(espb, rank, world)  # N > 1: ncclCommInitRank through the library's C entry points
 
     ns = args.streams
     cap = int(N_IN * float(RATIO)) + 64
@@ -284,47 +630,38 @@ def main():
                              mode=espb.MODE_EXACT if args.mode == "exact" else espb.MODE_FAST)
     ctx.set_option(espb.OPT_PLAN_CACHE, 0)  # every step re-plans: schedule, upload and expansion are timed
     ctx.set_option(espb.OPT_KERNEL_TIMING, 1)
+    st = {}
 
     def step():
         ctx.reset(stream)
         ctx.advance(TAPS / 2.0)  # zero delay, as resampler.cpp:94 does
-        return ctx.process_interleaved_dev(d_in.ptr, in_row, N_IN, d_out.ptr, out_row, cap, RATIO, stream)
-
-    def barrier():
-        espb.capi._check(L.espb_device_sync(), "sync")
-        if dist:
-            dist.barrier()
-        espb.capi._check(L.espb_device_sync(), "sync")
+        st["r"] = ctx.process_interleaved_dev(d_in.ptr, in_row, N_IN, d_out.ptr, out_row, cap, RATIO, stream)
 
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
     for _ in range(args.warmup):
-        used, gen = step()
-    barrier()
+        step()
+    ranks.barrier()
     ctx.kernel_time()  # drop warm-up records
 
     ev0, ev1 = L.espb_event_create(), L.espb_event_create()
     launches0 = espb.launch_count()
-    barrier()
+    ranks.barrier()
     sampler.mark()
     L.espb_event_record(ev0, stream)
     for _ in range(args.steps):
-        used, gen = step()
+        step()
     L.espb_event_record(ev1, stream)
     ms = espb.capi.C.c_float(0)
     espb.capi._check(L.espb_event_elapsed_ms(ev0, ev1, espb.capi.C.byref(ms)), "elapsed")
-    barrier()
+    ranks.barrier()
     sampler.mark()
+    used, gen = st["r"]
     launches = espb.launch_count() - launches0
     kernel_ms, kernel_launches = ctx.kernel_time()
     clocks = sampler.stop() if rank == 0 else None
-    total_ms = float(ms.value)
-    if dist:
-        import torch
-        t = torch.tensor([total_ms], device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms = float(t.item())
+    total_ms = ranks.max(float(ms.value))  # device-timed, max over ranks (gathered by ncclAllGather)
 
     samples_per_step_rank = gen * CHANNELS * ns
     samples_per_step = samples_per_step_rank * world
@@ -334,8 +671,8 @@ def main():
     # ---- correctness guard inside the bench: a sampled stream against the oracle, checksum for the gather
     checksum = espb.checksum_u32(d_out.ptr, ns * out_row, stream) & 0x7FFFFFFFFFFFFFFF
     first_stream, _ = espb.shard_range(ns * world, rank, world)
-    # NCCL: the only collective, after the timed region — per-rank checksum, frames, first stream index
-    gathered = espb.gather_words([checksum, gen, first_stream], dist, device="cuda" if dist else None)
+    # NCCL: the only collective, outside the timed region — per-rank checksum, frames, first stream index
+    gathered = ranks.gather([checksum, gen, first_stream])
     checksums = [g[0] for g in gathered]
     assert [g[2] for g in gathered] == [espb.shard_range(ns * world, r, world)[0] for r in range(world)]
 
@@ -352,11 +689,13 @@ def main():
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     traffic = None  # dram bytes per launch of the dominant kernel, from the committed ncu capture
-    try:
-        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as fh:
-            traffic = json.load(fh)
-    except Exception:
-        pass
+    for name in ("r02_traffic.json", "r01_traffic.json"):
+        try:
+            with open(os.path.join(ROOT, "profiles", name)) as fh:
+                traffic = json.load(fh)
+            break
+        except Exception:
+            pass
     roofline = {
         "kernel": "espb_resample_kernel<BPP=4,STAGES=2,CHUNK_ROWS=32,EXACT=false,TMCAP=false>", "bound": "fp32_fma", "achieved": achieved_tf,
         "peak": fma_tflops, "unit": "TFLOP/s", "frac": achieved_tf / fma_tflops if fma_tflops else None,
@@ -372,40 +711,55 @@ def main():
         "traffic_source": (traffic or {}).get("source"),
         "algorithmic_bytes_per_launch": bytes_per_launch,
         "flop_per_sample": FLOP_PER_SAMPLE, "kernel_ms": k_ms, "kernel_share_of_step": kernel_ms / total_ms,
+        "step_level_frac": (FLOP_PER_SAMPLE * samples_per_step_rank / (ms_per_step * 1e-3) / 1e12) / fma_tflops
+        if fma_tflops else None,
         "hbm": {"achieved_gbs": bytes_per_launch / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0, "peak_gbs": hbm_peak,
                 "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6.65 TB/s",
                 "bytes_per_sample": BYTES_PER_SAMPLE},
     }
 
+    # ---- the host link as plain pinned cudaMemcpyAsync sees it, every rank copying at the same time
+    link = None
+    if not args.no_e2e:
+        ranks.barrier()
+        link = espb.measure_host_link(None, 512 << 20, 64 << 20, 2)
+        ranks.barrier()
+        link["what"] = ("pinned cudaMemcpyAsync, 64 MiB slabs, H2D and D2H at once on this rank's GPU while the other "
+                        f"{world - 1} rank(s) do the same; GB/s of this rank")
+
     # ---- end to end: host buffers through the public C-ABI call, H2D + D2H inside the timed region
     e2e, e2e_last = None, None
     if not args.no_e2e:
         ctx.set_option(espb.OPT_KERNEL_TIMING, 0)
+        rr = {}
 
         def e2e_step():
             ctx.reset(None)
             ctx.advance(TAPS / 2.0)
-            return ctx.process_interleaved_host(h_in.ptr, in_row, N_IN, h_out.ptr, out_row, cap, RATIO)
+            rr["r"] = ctx.process_interleaved_host(h_in.ptr, in_row, N_IN, h_out.ptr, out_row, cap, RATIO)
 
-        for _ in range(2):
-            e2e_step()
-        barrier()
         k = max(3, min(args.steps, 10))
-        t0 = time.perf_counter()
-        for _ in range(k):
-            u2, g2 = e2e_step()  # synchronous: returns after the D2H of the results
-        barrier()
-        e2e_s = (time.perf_counter() - t0) / k
-        if dist:
-            import torch
-            t = torch.tensor([e2e_s], device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            e2e_s = float(t.item())
+        e2e_s = timed_wall(ranks, e2e_step, k, 2)  # synchronous calls: each returns after the D2H of its results
+        u2, g2 = rr["r"]
+        e2e_bytes = ns * in_row * 4 + ns * g2 * CHANNELS * 4
         e2e = {"value": g2 * CHANNELS * ns * world / e2e_s / 1e6, "unit": "Msamples/s",
                "h2d_bytes_per_step": ns * in_row * 4, "d2h_bytes_per_step": ns * g2 * CHANNELS * 4,
                "ms_per_step": e2e_s * 1e3, "steps": k,
-               "api": "espb_resampleProcessInterleavedHost (pinned host buffers, 3-stream slab pipeline)"}
+               "api": "espb_resampleProcessInterleavedHost (pinned host buffers, 3-stream slab pipeline)",
+               "link_gbs_this_rank": e2e_bytes / e2e_s / 1e9, "link_probe": link,
+               "frac_of_link": link_fraction(e2e_bytes, e2e_s, link)}
         e2e_last = (g2, ns - 1)  # checked against the CPU reference in the cpu_baseline leg below
+    ctx.free()
+    d_in.free()
+    d_out.free()
+
+    # ---- the other BASELINE configs as sub-records (their own roofline view, e2e and oracle spot-check)
+    configs, checks = {}, ([] if (rank == 0 and world == 1 and not args.no_cpu_baseline) else None)
+    if not args.no_configs and ns == STREAMS_PER_GPU:
+        sub_steps = max(3, min(args.steps, 5))
+        configs["C5"] = bench_c5(espb, ranks, stream, fma_tflops, link, sub_steps, not args.no_e2e, checks)
+        configs["C3"] = bench_c3(espb, ranks, stream, fma_tflops, link, sub_steps, not args.no_e2e, checks)
+        configs["C4"] = bench_c4(espb, ranks, stream, fma_tflops, link, sub_steps, not args.no_e2e, checks)
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -429,6 +783,8 @@ def main():
             if go != g2 or err > (0.0 if args.mode == "exact" else 1e-6):
                 raise SystemExit(f"bench.py: parity check failed (generated {g2} vs {go}, max-abs {err})")
             e2e["parity_max_abs_vs_oracle"] = err
+        if checks:
+            run_checks(checks, args.mode)
 
     if rank == 0:
         line = {
@@ -443,15 +799,17 @@ def main():
                                 "exact (tap-order FMUL+FADD per accumulator: bit-exact with the reference)"),
                        "signals": f"{DISTINCT} distinct streams (multitone + uniform noise, A=0.5) tiled",
                        "parallelism": f"streams sharded by index over {world} GPU(s), no data-path collective",
+                       "collective": ("one ncclAllGather of 3 words per rank through the library's C entry points "
+                                      "(espb_dist_allgather_u64), outside the timed region" if world > 1 else "none"),
                        "l2": "inputs+outputs 3.0 GB per step >> 126 MB L2 (no flush needed)",
                        "timed_region": "per step: reset, host schedule, table upload, coefficient expansion, "
                                        "resampler kernel, history carry (plan cache off)"},
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "host_affinity": host_affinity, "gpu_launches": int(launches),
             "clocks": clocks, "checksums": checksums, "checksum_of_checksums": espb.combine_checksums(checksums), "device": info["name"], "sm_count": info["sm_count"],
+            "nccl_version": int(L.espb_nccl_version()), "configs": configs,
         }
         print(json.dumps(line), file=out, flush=True)
-    if dist:
-        dist.destroy_process_group()
+    ranks.close()
     return 0
 
 

@@ -118,6 +118,26 @@ def lib():
         "espb_biquad_apply_samples": (i, [vp, vp, vp]),
         "espb_biquad_set_time_blocks": (i, [vp, i, i]),
         "espb_resampler_set_biquad_time_blocks": (i, [vp, i, i]),
+        "espb_last_status": (i, []),
+        "espb_nccl_version": (i, []),
+        "espb_measure_host_link": (i, [i, vp, sz, sz, i, C.POINTER(C.c_double)]),
+        "espb_multi_last_error": (C.c_char_p, []),
+        "espb_shard_range": (None, [i64, i, i, C.POINTER(i64), C.POINTER(i64)]),
+        "espb_multi_create": (vp, [i, vp]),
+        "espb_multi_free": (None, [vp]),
+        "espb_multi_size": (i, [vp]),
+        "espb_multi_device": (i, [vp, i]),
+        "espb_multi_allgather_u64": (i, [vp, vp, vp, i, vp]),
+        "espb_multi_gather_words": (i, [vp, vp, i, vp]),
+        "espb_dist_unique_id": (i, [vp]),
+        "espb_dist_init": (vp, [vp, i, i]),
+        "espb_dist_free": (None, [vp]),
+        "espb_dist_rank": (i, [vp]),
+        "espb_dist_world": (i, [vp]),
+        "espb_dist_allgather_u64": (i, [vp, vp, i, vp]),
+        "espb_dist_barrier": (i, [vp]),
+        "espb_resampler_set_option": (i, [vp, i, i]),
+        "espb_resampler_get_kernel_time": (i, [vp, C.POINTER(f), C.POINTER(i)]),
         "espb_biquad_block_stats": (i, [vp, C.POINTER(u64), C.POINTER(i)]),
         "espb_resampler_biquad_block_stats": (i, [vp, C.POINTER(u64), C.POINTER(i)]),
         "espb_biquad_get_state": (i, [vp, vp]),
@@ -255,6 +275,19 @@ def plan_policy(src_rate, dst_rate, src_bits, dst_bits, channels, use_filter, in
     return dict(filter={0: "none", 1: "pre", 2: "post"}[kind],
                 coeffs=np.array([c.a0, c.a1, c.a2, c.b1, c.b2], np.float32), sample_ratio=np.float32(ratio.value),
                 art_lowpass=np.float32(lp.value), art_flags=int(flags.value))
+
+
+def measure_host_link(devices=None, nbytes=1 << 30, slab_bytes=64 << 20, reps=3):
+    """Aggregate GB/s per direction of pinned cudaMemcpyAsync on `devices` (None: the current one), all at once."""
+    out = (C.c_double * 6)()
+    if devices is None:
+        rc = lib().espb_measure_host_link(0, None, nbytes, slab_bytes, reps, out)
+    else:
+        arr = (C.c_int * len(devices))(*devices)
+        rc = lib().espb_measure_host_link(len(devices), arr, nbytes, slab_bytes, reps, out)
+    _check(rc, "measure_host_link")
+    return dict(h2d_gbs=out[0], d2h_gbs=out[1], duplex_each_gbs=out[2], duplex_sum_gbs=out[4], duplex_seconds=out[5],
+                bytes_per_direction_per_device=nbytes, slab_bytes=slab_bytes)
 
 
 def measure_fp32_tile_pattern():
@@ -719,6 +752,14 @@ class Resampler:
     def set_biquad_time_blocks(self, block_rows, warmup_rows):
         _check(lib().espb_resampler_set_biquad_time_blocks(self.h, block_rows, warmup_rows),
                "resampler_set_biquad_time_blocks")
+
+    def set_option(self, option, value):
+        _check(lib().espb_resampler_set_option(self.h, option, value), "resampler_set_option")
+
+    def kernel_time(self):
+        ms, n = C.c_float(0), C.c_int(0)
+        _check(lib().espb_resampler_get_kernel_time(self.h, C.byref(ms), C.byref(n)), "resampler_get_kernel_time")
+        return float(ms.value), int(n.value)
 
     def biquad_block_stats(self):
         n, w = C.c_uint64(0), C.c_int(0)

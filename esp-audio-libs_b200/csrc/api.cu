@@ -23,6 +23,7 @@ using namespace espb;
 // errors, counters
 // ------------------------------------------------------------------------------------
 static thread_local std::string g_last_error;
+static thread_local int g_last_status = 0;  // ESPB_OK or the code of the calling thread's last failed call
 static std::atomic<uint64_t> g_launches{0};
 
 namespace espb {
@@ -30,6 +31,7 @@ void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 }  // namespace espb
 
 static int fail(int code, const char *what, const char *detail = nullptr) {
+  g_last_status = code;
   g_last_error = what;
   if (detail) {
     g_last_error += ": ";
@@ -56,6 +58,7 @@ static long env_long(const char *name, long dflt) {
 extern "C" {
 
 const char *espb_last_error(void) { return g_last_error.c_str(); }
+int espb_last_status(void) { return g_last_status; }
 int espb_abi_version(void) { return ESPB_ABI_VERSION; }
 uint64_t espb_launch_count(void) { return g_launches.load(); }
 
@@ -386,6 +389,8 @@ int prepare_call(EspbResampleBatch *c, int n_in, int n_out, float ratio, cudaStr
     if (cudaGetDevice(&dev) != cudaSuccess || dev != c->device)
       return fail(ESPB_ERR_STATE, "this context was created on another CUDA device (espb_set_device before the call)");
   }
+  if (!(ratio > 0.0f) || !(ratio <= 3.0e38f))  // NaN, <= 0, Inf: the reference would loop for ever or index wildly
+    return fail(ESPB_ERR_ARG, "resampleProcess: ratio must be a positive finite number");
   if (c->state_event_pending) {  // order this call after an asynchronous reset issued on another stream
     CU_TRY(cudaStreamWaitEvent(stream, c->state_event, 0), "cudaStreamWaitEvent");
     c->state_event_pending = false;
@@ -452,6 +457,14 @@ int prepare_call(EspbResampleBatch *c, int n_in, int n_out, float ratio, cudaStr
     c->plan.pass_chunk_begin.push_back(0);
   } else {
     build_pass_plan(c->sched, c->geo.taps, c->bpp, c->chunk_rows, c->plan, c->direct_call);
+    // the kernel keeps the chunk table of its passes in shared memory: one pass must fit it.  (32 outputs at a
+    // ratio below ~0.004 span more than 320 chunks of input — far outside audio use; refused, not truncated.)
+    const int limit = max_chunks_per_cta(c->bpp, c->chunk_rows);
+    for (int ps = 0; ps < c->plan.n_passes(); ++ps)
+      if (c->plan.pass_chunk_begin[ps + 1] - c->plan.pass_chunk_begin[ps] > limit) {
+        c->key = ScheduleKey{};
+        return fail(ESPB_ERR_ARG, "resampleProcess: ratio too small for the kernel's per-pass chunk table");
+      }
   }
   c->key = k;
   if (c->sched.generated == 0) {
@@ -541,7 +554,7 @@ int pick_passes_per_cta(const EspbResampleBatch *c, int n_series, int pass_first
   if (ppc * max_chunks > max_chunks_per_cta(c->bpp, c->chunk_rows))
     ppc = max_chunks_per_cta(c->bpp, c->chunk_rows) / max_chunks;
   if (ppc < 1)
-    ppc = 1;  // a single pass longer than the table cannot happen: taps <= 1024 gives <= 40 chunks per pass
+    ppc = 1;  // (prepare_call has refused calls in which a single pass is longer than the table)
   return (int) ppc;
 }
 
@@ -1102,7 +1115,7 @@ EspbResampleResult espb_resampleProcessLayout(EspbResampleBatch *c, const float 
   res.input_used = c->sched.used;
   res.output_generated = c->sched.generated;
   finish_call(c);
-  g_last_error.clear();
+  g_last_error.clear(), g_last_status = ESPB_OK;
   return res;
 }
 
@@ -1221,7 +1234,7 @@ EspbResampleResult espb_resampleProcessInterleavedHost(EspbResampleBatch *c, con
   res.input_used = c->sched.used;
   res.output_generated = c->sched.generated;
   finish_call(c);
-  g_last_error.clear();
+  g_last_error.clear(), g_last_status = ESPB_OK;
   return res;
 }
 
@@ -1822,7 +1835,7 @@ EspbResamplerResults wrapper_finish(EspbResampler *r, const WrapperCall &wc, uin
   res.clipped_samples = total;
   if (r->policy.resampling)
     finish_call(r->art);
-  g_last_error.clear();
+  g_last_error.clear(), g_last_status = ESPB_OK;
   return res;
 }
 
@@ -1902,6 +1915,24 @@ int espb_resampler_set_mode(EspbResampler *r, int mode) {
   if (!r)
     return fail(ESPB_ERR_ARG, "resampler_set_mode: NULL");
   return r->art ? espb_resampleSetMode(r->art, mode) : ESPB_OK;
+}
+
+int espb_resampler_set_option(EspbResampler *r, int option, int value) {
+  if (!r)
+    return fail(ESPB_ERR_ARG, "resampler_set_option: NULL");
+  return r->art ? espb_resampleSetOption(r->art, option, value) : ESPB_OK;
+}
+
+int espb_resampler_get_kernel_time(EspbResampler *r, float *total_ms, int *launches) {
+  if (!r || !total_ms)
+    return fail(ESPB_ERR_ARG, "resampler_get_kernel_time: NULL");
+  if (!r->art) {
+    *total_ms = 0.0f;
+    if (launches)
+      *launches = 0;
+    return ESPB_OK;
+  }
+  return espb_resampleGetKernelTime(r->art, total_ms, launches);
 }
 
 int espb_resampler_set_biquad_time_blocks(EspbResampler *r, int block_rows, int warmup_rows) {

@@ -118,9 +118,8 @@ int espb_resampleGroupsProcessInterleaved(EspbResampleGroups *g, const float *in
     results[k] = espb_resampleProcessInterleaved(g->ctx[k], in + first * in_stream_stride, in_stream_stride,
                                                  numInputFrames[k], out + first * out_stream_stride, out_stream_stride,
                                                  numOutputFrames[k], ratios[k], s);
-    const char *err = espb_last_error();
-    if (err && err[0] && results[k].input_used == 0 && results[k].output_generated == 0)
-      rc = ESPB_ERR_CUDA;  // the call reported a failure (a legitimately empty call leaves no message)
+    if (espb_last_status() != ESPB_OK)
+      rc = espb_last_status();
     if (cudaEventRecord(g->joined[k], s) != cudaSuccess || cudaStreamWaitEvent(caller, g->joined[k], 0) != cudaSuccess)
       return ESPB_ERR_CUDA;
   }

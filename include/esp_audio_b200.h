@@ -52,6 +52,10 @@ extern "C" {
 #define ESPB_MODE_EXACT 1 /* tap-order FMUL+FADD (no contraction): bit-exact with the reference */
 
 const char *espb_last_error(void); /* thread-local message of the last failing call */
+/* Status of the calling thread's last processing call: ESPB_OK, or the ESPB_ERR_* code of its failure.  The
+ * processing calls keep the reference's return types ({input_used, output_generated} / ResamplerResults), in which a
+ * failed call and a legitimately empty call both read {0, 0}; this tells them apart. */
+int espb_last_status(void);
 int espb_abi_version(void);
 
 /* ---- device + buffers (the "device-buffer interface") ------------------------ */
@@ -244,6 +248,9 @@ void espb_resampler_free(EspbResampler *r);
 int espb_resampler_set_mode(EspbResampler *r, int mode);
 /* time-block mode of the pre/post low-pass (see espb_biquad_set_time_blocks) */
 int espb_resampler_set_biquad_time_blocks(EspbResampler *r, int block_rows, int warmup_rows);
+/* ESPB_OPT_* of the wrapper's ART context; CUDA-event time of its resampler-kernel launches since the last query */
+int espb_resampler_set_option(EspbResampler *r, int option, int value);
+int espb_resampler_get_kernel_time(EspbResampler *r, float *total_ms, int *launches);
 int espb_resampler_biquad_block_stats(EspbResampler *r, uint64_t *repaired_blocks, int *warmup_rows);
 /* policy introspection: 0 none / 1 pre / 2 post; coefficients; ART low-pass and flags */
 int espb_resampler_policy(EspbResampler *r, EspbBiquadCoefficients *coeffs, float *sample_ratio, float *art_lowpass,
@@ -363,6 +370,44 @@ int espb_measure_fp32_fma_peak2(double *tflops_scalar_ffma, double *tflops_packe
 /* the resampler's inner loop alone (register tile fed from shared memory, the kernel's occupancy, no TMA /
  * barriers / epilogue): the practical ceiling of that loop, reported next to the FMA-only peak */
 int espb_measure_fp32_tile_pattern(double *tflops);
+
+/* ---- multi-GPU: stream-sharded batches ------------------------------------------------
+ * Streams are independent (the reference has no globals; a context is one stream's state), so a batch is cut into
+ * contiguous stream ranges, one per GPU, with NO collective on the data path; NCCL over NVLink only gathers a few
+ * 64-bit words per shard (checksum, frame and clip counts).  NCCL is resolved at run time (libnccl.so.2). */
+int espb_nccl_version(void);                 /* 0: NCCL not available */
+const char *espb_multi_last_error(void);
+/* contiguous range [first, first + count) of shard `rank` of `world`: sizes differ by at most one stream */
+void espb_shard_range(int64_t n_streams, int rank, int world, int64_t *first, int64_t *count);
+
+/* Host-link probe: plain pinned cudaMemcpyAsync, one call per slab, on the listed devices concurrently (n_devices <= 0:
+ * the current device).  out[6] = aggregate GB/s per direction {H2D alone, D2H alone, H2D while D2H runs, D2H while
+ * H2D runs, both directions summed, seconds of the duplex run}: the ceiling of the host-buffer entry points. */
+int espb_measure_host_link(int n_devices, const int *devices, size_t bytes, size_t slab_bytes, int reps, double *out);
+
+/* one process drives all devices: ncclCommInitAll over `devices` (NULL: 0 .. n_devices-1; n_devices <= 0: all) */
+typedef struct EspbMulti EspbMulti;
+EspbMulti *espb_multi_create(int n_devices, const int *devices);
+void espb_multi_free(EspbMulti *m);
+int espb_multi_size(const EspbMulti *m);
+int espb_multi_device(const EspbMulti *m, int rank);
+/* device k contributes `words` uint64 at send_dev[k], receives world*words (rank order) at recv_dev[k]; one
+ * ncclAllGather per device in one group call, on streams[k] (NULL: internal streams).  Asynchronous. */
+int espb_multi_allgather_u64(EspbMulti *m, const void *const *send_dev, void *const *recv_dev, int words,
+                             void *const *streams);
+/* host convenience (synchronous): words_per_rank[k*words + i] -> gathered[world*words] as device 0 received them */
+int espb_multi_gather_words(EspbMulti *m, const uint64_t *words_per_rank, int words, uint64_t *gathered);
+
+/* one process per GPU: rank 0 makes the 128-byte id, the launcher's rendezvous hands it to every rank, every rank
+ * joins with its current CUDA device */
+typedef struct EspbDist EspbDist;
+int espb_dist_unique_id(void *id128);
+EspbDist *espb_dist_init(const void *id128, int rank, int world);
+void espb_dist_free(EspbDist *d);
+int espb_dist_rank(const EspbDist *d);
+int espb_dist_world(const EspbDist *d);
+int espb_dist_allgather_u64(EspbDist *d, const uint64_t *mine, int words, uint64_t *gathered /* world*words */);
+int espb_dist_barrier(EspbDist *d);
 
 #ifdef __cplusplus
 }
