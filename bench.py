@@ -237,7 +237,13 @@ class Ranks:
             self.espb.capi._check(L.espb_device_sync(), "sync")
 
     def max(self, v):
-        return self.nccl.max_float(v) if self.nccl else float(v)
+        return max(self.all_floats(v))
+
+    def all_floats(self, v):
+        """The value of every rank, in rank order (gathered as bit patterns by ncclAllGather)."""
+        import struct
+        bits = struct.unpack("<Q", struct.pack("<d", float(v)))[0]
+        return [struct.unpack("<d", struct.pack("<Q", g[0]))[0] for g in self.gather([bits])]
 
     def gather(self, words):
         return self.nccl.allgather(words) if self.nccl else [[int(w) for w in words]]
@@ -264,7 +270,9 @@ def timed_steps(espb, ranks, stream, step, steps, warmup):
     ranks.barrier()
     L.espb_event_destroy(ev0)
     L.espb_event_destroy(ev1)
-    return ranks.max(float(ms.value)) / steps
+    per_rank = [t / steps for t in ranks.all_floats(float(ms.value))]
+    timed_steps.per_rank = per_rank
+    return max(per_rank)
 
 
 def timed_wall(ranks, step, steps, warmup):
@@ -292,12 +300,15 @@ def pcm_rows(n_rows, n_samples, bits, distinct, seed, first_row=0):
     return raw[idx]
 
 
-def link_fraction(e2e_bytes, e2e_seconds, link):
-    """Bytes per second over the host link during the e2e step, against the duplex rate the link probe measured in
-    this run with every rank copying at the same time."""
+def link_fraction(h2d_bytes, d2h_bytes, e2e_seconds, link):
+    """Time the host link alone needs for the step's bytes — the slowest of (H2D bytes at the H2D-only rate, D2H bytes
+    at the D2H-only rate, all bytes at the duplex rate), rates from the link probe of this run with every rank copying
+    at the same time — as a fraction of the measured end-to-end step time (1.0 = the step is nothing but the wire)."""
     if not link or not link.get("duplex_sum_gbs"):
         return None
-    return (e2e_bytes / e2e_seconds / 1e9) / link["duplex_sum_gbs"]
+    floor_s = max(h2d_bytes / (link["h2d_gbs"] * 1e9), d2h_bytes / (link["d2h_gbs"] * 1e9),
+                  (h2d_bytes + d2h_bytes) / (link["duplex_sum_gbs"] * 1e9))
+    return floor_s / e2e_seconds
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -328,7 +339,8 @@ def bench_c3(espb, ranks, stream, peak_tf, link, steps, want_e2e, checks):
     rec = {"workload": "16 kHz -> 48 kHz mono voice, art_biquad post-filter (2 sections), 16384 streams per GPU, "
                        "int16 in / int16 out through espb_resampler_resample_async, 1 s (16000 frames) per step",
            "scaling": "weak", "value": samples_rank * ranks.world / (ms * 1e-3) / 1e6, "unit": "Msamples/s",
-           "ms_per_step": ms, "frames_out": gen, "filter": r.policy()["filter"],
+           "ms_per_step": ms, "ms_per_step_by_rank": timed_steps.per_rank, "frames_out": gen,
+           "filter": r.policy()["filter"],
            "roofline": {"kernel": "espb_resample_kernel (time-major in, time-major out)", "bound": "fp32_fma",
                         "achieved": tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": tf / peak_tf if peak_tf else None,
                         "kernel_ms": k_ms_call, "kernel_share_of_step": k_ms_call / ms if ms else None},
@@ -350,7 +362,7 @@ def bench_c3(espb, ranks, stream, peak_tf, link, steps, want_e2e, checks):
         rec["e2e"] = {"value": g2 * ch * ns * ranks.world / sec / 1e6, "unit": "Msamples/s", "ms_per_step": sec * 1e3,
                       "h2d_bytes_per_step": ns * frames * 2, "d2h_bytes_per_step": ns * g2 * 2,
                       "api": "espb_resampler_resample_host (int16 PCM on the wire: half the bytes of the float call)",
-                      "frac_of_link": link_fraction(nbytes, sec, link)}
+                      "frac_of_link": link_fraction(ns * frames * 2, ns * g2 * 2, sec, link)}
         if checks is not None:  # the CPU leg re-computes one stream: same input `calls` times through the oracle
             row = ns - 1
             checks.append(("C3", dict(raw=raw[row].copy(), calls=calls[0], frames=frames, cap=cap, sr=sr, dr=dr,
@@ -395,8 +407,8 @@ def bench_c4(espb, ranks, stream, peak_tf, link, steps, want_e2e, checks):
     rec = {"workload": f"96 kHz -> 44.1 kHz, 8 channels, 24-bit in / out, 1024 taps, art_biquad pre-filter, ONE stream "
                        f"per GPU, {seconds} s ({frames} frames) per step (replicas only: a stream does not shard)",
            "scaling": "replicas", "value": samples_rank * ranks.world / (ms * 1e-3) / 1e6, "unit": "Msamples/s",
-           "ms_per_step": ms, "frames_out": gen, "filter": r.policy()["filter"],
-           "realtime_factor": seconds / (ms * 1e-3),
+           "ms_per_step": ms, "ms_per_step_by_rank": timed_steps.per_rank, "frames_out": gen,
+           "filter": r.policy()["filter"], "realtime_factor": seconds / (ms * 1e-3),
            "biquad": {"mode": "time blocks of 8192 frames, hand-over verified on the device (exact by construction)",
                       "blocks_repaired": repaired, "warmup_rows": warm},
            "roofline": {"kernel": "espb_resample_fs_kernel<SV=8,B=2> (few-series form: lanes own outputs)",
@@ -418,7 +430,7 @@ def bench_c4(espb, ranks, stream, peak_tf, link, steps, want_e2e, checks):
         rec["e2e"] = {"value": g2 * ch * ns * ranks.world / sec / 1e6, "unit": "Msamples/s", "ms_per_step": sec * 1e3,
                       "h2d_bytes_per_step": ns * frames * ch * 3, "d2h_bytes_per_step": ns * g2 * ch * 3,
                       "api": "espb_resampler_resample_host (24-bit PCM on the wire)",
-                      "frac_of_link": link_fraction(ns * (frames + g2) * ch * 3, sec, link)}
+                      "frac_of_link": link_fraction(ns * frames * ch * 3, ns * g2 * ch * 3, sec, link)}
         h_in.free()
         h_out.free()
     if checks is not None:  # first second of the first (fresh-state) call against the composed CPU pipeline
@@ -482,7 +494,7 @@ def bench_c5(espb, ranks, stream, peak_tf, link, steps, want_e2e, checks):
                        "by stream index over the ranks; 1 s per stream per step as 8 streaming calls of 6000 frames",
            "scaling": "strong", "streams_total": total, "streams_per_rank": ns,
            "value": gen * ch * total / (ms * 1e-3) / 1e6, "unit": "Msamples/s", "ms_per_step": ms,
-           "frames_out_per_step": gen,
+           "ms_per_step_by_rank": timed_steps.per_rank, "frames_out_per_step": gen,
            "roofline": {"kernel": "espb_resample_kernel<BPP=4,STAGES=2,CHUNK_ROWS=32>", "bound": "fp32_fma",
                         "achieved": tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": tf / peak_tf if peak_tf else None,
                         "kernel_ms_per_step": k_ms_step, "kernel_share_of_step": k_ms_step / ms if ms else None},
@@ -508,7 +520,7 @@ def bench_c5(espb, ranks, stream, peak_tf, link, steps, want_e2e, checks):
         rec["e2e"] = {"value": rr["gen"] * ch * total / sec / 1e6, "unit": "Msamples/s", "ms_per_step": sec * 1e3,
                       "h2d_bytes_per_step": ns * calls_per_step * in_row * 4, "d2h_bytes_per_step": ns * rr["gen"] * ch * 4,
                       "api": "espb_resampleProcessInterleavedHost, 8 calls per step",
-                      "frac_of_link": link_fraction(nbytes, sec, link)}
+                      "frac_of_link": link_fraction(ns * calls_per_step * in_row * 4, ns * rr["gen"] * ch * 4, sec, link)}
         if checks is not None:
             row = ns - 1
             checks.append(("C5", dict(x=h_in.array.reshape(ns, in_row)[row].copy(), calls=calls_per_step, cap=cap,
@@ -722,10 +734,12 @@ def main():
     link = None
     if not args.no_e2e:
         ranks.barrier()
-        link = espb.measure_host_link(None, 512 << 20, 64 << 20, 2)
+        # (1.5 GiB per direction, the size of the step's own buffers: smaller probes partly run out of the host's
+        # last-level cache and overstate what a sustained stream gets)
+        link = espb.measure_host_link(None, 1536 << 20, 64 << 20, 2)
         ranks.barrier()
-        link["what"] = ("pinned cudaMemcpyAsync, 64 MiB slabs, H2D and D2H at once on this rank's GPU while the other "
-                        f"{world - 1} rank(s) do the same; GB/s of this rank")
+        link["what"] = ("pinned cudaMemcpyAsync, 64 MiB slabs: H2D alone, D2H alone, both at once, on this rank's GPU "
+                        f"while the other {world - 1} rank(s) do the same; GB/s of this rank")
 
     # ---- end to end: host buffers through the public C-ABI call, H2D + D2H inside the timed region
     e2e, e2e_last = None, None
@@ -747,7 +761,7 @@ def main():
                "ms_per_step": e2e_s * 1e3, "steps": k,
                "api": "espb_resampleProcessInterleavedHost (pinned host buffers, 3-stream slab pipeline)",
                "link_gbs_this_rank": e2e_bytes / e2e_s / 1e9, "link_probe": link,
-               "frac_of_link": link_fraction(e2e_bytes, e2e_s, link)}
+               "frac_of_link": link_fraction(ns * in_row * 4, ns * g2 * CHANNELS * 4, e2e_s, link)}
         e2e_last = (g2, ns - 1)  # checked against the CPU reference in the cpu_baseline leg below
     ctx.free()
     d_in.free()

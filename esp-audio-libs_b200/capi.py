@@ -157,6 +157,8 @@ def lib():
         "espb_plan_filter_bank": (i, [i, i, f, i, vp, C.POINTER(i)]),
         "espb_plan_schedule": (i, [i, i, i, f, i, i, i, f, C.POINTER(C.c_uint), C.POINTER(C.c_uint), C.POINTER(f),
                                    C.POINTER(i), vp, vp, vp, vp]),
+        "espb_plan_schedule_segments": (i, [i, i, i, f, i, i, i, f, C.POINTER(C.c_uint), C.POINTER(C.c_uint),
+                                            C.POINTER(f), C.POINTER(i), vp, vp, vp, vp]),
         "espb_plan_passes": (i, [i, i, i, f, i, i, i, f, i, i, i, vp, vp, i, vp, i]),
         "espb_plan_policy": (i, [C.POINTER(_Config), C.POINTER(_Coeffs), C.POINTER(f), C.POINTER(f), C.POINTER(i)]),
         "espb_checksum_u32": (i, [vp, u64, vp, vp]),
@@ -250,6 +252,21 @@ def plan_schedule(taps, filters, flags, offset, index, n_in, n_out, ratio, want_
     g = int(gen.value)
     return dict(used=int(used.value), generated=g, end_offset=np.float32(eo.value), end_index=int(ei.value),
                 ws=ws[:g], phase=ph[:g], w=w[:g], kind=kind[:g])
+
+
+def plan_schedule_segments(taps, filters, flags, offset, index, n_in, n_out, ratio, want_entries=True):
+    """The same dry run through the closed-form (segmented) planner of the processing path; adds `segments`."""
+    used, gen, eo, ei = C.c_uint(0), C.c_uint(0), C.c_float(0), C.c_int(0)
+    n = max(n_out, 1)
+    ws, ph, w, kind = (np.zeros(n, np.int32), np.zeros(n, np.int32), np.zeros(n, np.float32), np.zeros(n, np.int32))
+    ptrs = [a.ctypes.data if want_entries else None for a in (ws, ph, w, kind)]
+    rc = lib().espb_plan_schedule_segments(taps, filters, flags, offset, index, n_in, n_out, ratio, C.byref(used),
+                                           C.byref(gen), C.byref(eo), C.byref(ei), *ptrs)
+    if rc < 0:
+        _check(rc, "plan_schedule_segments")
+    g = int(gen.value)
+    return dict(used=int(used.value), generated=g, end_offset=np.float32(eo.value), end_index=int(ei.value),
+                ws=ws[:g], phase=ph[:g], w=w[:g], kind=kind[:g], segments=int(rc))
 
 
 def plan_passes(taps, filters, flags, offset, index, n_in, n_out, ratio, blocks_per_pass=4, chunk_rows=32,

@@ -356,6 +356,9 @@ struct EspbResampleBatch {
   // ... so two sets of table storage alternate: a rebuild waits for the upload of the call before the previous one,
   // which in a stream of calls has long finished (no host/device serialisation from call to call)
   PodBuffer<OutEntry> spare_outs;
+  PodBuffer<SchedSegment> spare_segs;
+  DevBuf d_segs;
+  bool sched_segments = true;  // closed-form schedule expanded on the device (ESPB_SCHED=seq: per-output host schedule)
   PodBuffer<ChunkEntry> spare_chunks;
   PodBuffer<int32_t> spare_pcb;
   cudaEvent_t spare_uploaded = nullptr;
@@ -368,10 +371,13 @@ namespace {
 int ensure_xt(EspbResampleBatch *c, int64_t rows);
 
 // PodBuffer hooks: best effort (a table that cannot be page-locked is simply uploaded through a staging copy)
-// Only large tables (long calls): for the few KB of a real-time chunk a pageable source is faster — the driver
-// embeds it in the command stream, measured 136 against 157 us per 10 ms call of 4096 stereo streams.
+// Not the small ones: for the few KB of a real-time chunk a pageable source is faster — the driver embeds it in the
+// command stream (measured 136 against 157 us per 10 ms call of 4096 stereo streams).  Beyond that a pageable source
+// makes cudaMemcpyAsync stage the copy synchronously behind the stream's earlier work, which ties the host to the
+// device call by call (C3: 0.77 MB of schedule per 1 s call), so everything from 64 KB on is page-locked.
+constexpr size_t kPinTablesFrom = (size_t) 64 << 10;
 void pin_host_range(void *p, size_t bytes) {
-  if (bytes < ((size_t) 2 << 20))  // (the same threshold decides in prepare_call whether an upload must be awaited)
+  if (bytes < kPinTablesFrom)  // (the same threshold decides in prepare_call whether an upload must be awaited)
     return;
   if (cudaHostRegister(p, bytes, cudaHostRegisterDefault) != cudaSuccess)
     cudaGetLastError();
@@ -413,6 +419,7 @@ int prepare_call(EspbResampleBatch *c, int n_in, int n_out, float ratio, cudaStr
   c->g_resident_first = c->g_resident_end = -1;
   {  // rebuild into the storage of the call before the previous one
     c->sched.outs.swap_storage(c->spare_outs);
+    c->sched.segs.swap_storage(c->spare_segs);
     c->plan.chunks.swap_storage(c->spare_chunks);
     c->plan.pass_chunk_begin.swap_storage(c->spare_pcb);
     cudaEvent_t ev = c->tables_uploaded;
@@ -426,17 +433,23 @@ int prepare_call(EspbResampleBatch *c, int n_in, int n_out, float ratio, cudaStr
     CU_TRY(cudaEventSynchronize(c->tables_uploaded), "cudaEventSynchronize");
     c->tables_upload_pending = false;
   }
-  build_schedule(c->geo, c->state, n_in, n_out, ratio, c->sched, /*finalize=*/false);  // pass 2 runs on the device
+  if (c->sched_segments) {  // a few runs per ring cycle; the per-output entries are expanded on the device
+    build_schedule_segments(c->geo, c->state, n_in, n_out, ratio, c->sched);
+  } else {
+    c->sched.segmented = false;
+    c->sched.segs.clear();
+    build_schedule(c->geo, c->state, n_in, n_out, ratio, c->sched, /*finalize=*/false);  // pass 2 runs on the device
+  }
   c->fs_call = false;
   if (c->bank_tr.p && c->fs_policy != 0 && c->sched.generated > 0) {
     // few-series form: the widest input tile (rows first window .. last window + taps of one CTA's outputs) must fit
     const FsGeometry fg = fs_geometry(c->n_series());
     const int n = (int) c->sched.generated, m = fg.outputs_per_cta;
-    int span = 0;
+    int span = 0, cursor = 0;
     for (int first = 0; first < n; first += m) {
       const int last = (first + m < n ? first + m : n) - 1;
-      const OutEntry &a = c->sched.outs[first], &b = c->sched.outs[last];  // raw entries: base + floor(offset)
-      const int d = (b.ws + (int32_t) b.w) - (a.ws + (int32_t) a.w);
+      const int ws_first = schedule_ws(c->sched, first, &cursor);
+      const int d = schedule_ws(c->sched, last, &cursor) - ws_first;
       span = d > span ? d : span;
     }
     c->fs_x_rows = span + c->geo.taps;
@@ -471,15 +484,26 @@ int prepare_call(EspbResampleBatch *c, int n_in, int n_out, float ratio, cudaStr
     c->plan_on_device = true;
     return ESPB_OK;
   }
-  CU_TRY(c->d_outs.reserve(c->sched.outs.size() * sizeof(OutEntry)), "cudaMalloc schedule");
+  CU_TRY(c->d_outs.reserve((size_t) c->sched.generated * sizeof(OutEntry)), "cudaMalloc schedule");
   CU_TRY(c->d_chunks.reserve((c->plan.chunks.size() + 1) * sizeof(ChunkEntry)), "cudaMalloc chunks");
   CU_TRY(c->d_pcb.reserve(c->plan.pass_chunk_begin.size() * sizeof(int32_t)), "cudaMalloc passes");
-  CU_TRY(cudaMemcpyAsync(c->d_outs.p, c->sched.outs.data(), c->sched.outs.size() * sizeof(OutEntry),
-                         cudaMemcpyHostToDevice, stream),
-         "upload schedule");
-  CU_TRY(launch_finalize(c->d_outs.as<OutEntry>(), (int) c->sched.outs.size(), c->geo.filters,
-                         (c->geo.flags & kFlagLowpass) != 0, (c->geo.flags & kFlagInterpolate) != 0, stream),
-         "finalize kernel");
+  if (c->sched.segmented) {
+    CU_TRY(c->d_segs.reserve(c->sched.segs.size() * sizeof(SchedSegment)), "cudaMalloc schedule");
+    CU_TRY(cudaMemcpyAsync(c->d_segs.p, c->sched.segs.data(), c->sched.segs.size() * sizeof(SchedSegment),
+                           cudaMemcpyHostToDevice, stream),
+           "upload schedule");
+    CU_TRY(launch_expand_schedule(c->d_segs.as<SchedSegment>(), (int) c->sched.segs.size(), c->d_outs.as<OutEntry>(),
+                                  (int) c->sched.generated, c->geo.filters, (c->geo.flags & kFlagLowpass) != 0,
+                                  (c->geo.flags & kFlagInterpolate) != 0, stream),
+           "schedule kernel");
+  } else {
+    CU_TRY(cudaMemcpyAsync(c->d_outs.p, c->sched.outs.data(), c->sched.outs.size() * sizeof(OutEntry),
+                           cudaMemcpyHostToDevice, stream),
+           "upload schedule");
+    CU_TRY(launch_finalize(c->d_outs.as<OutEntry>(), (int) c->sched.outs.size(), c->geo.filters,
+                           (c->geo.flags & kFlagLowpass) != 0, (c->geo.flags & kFlagInterpolate) != 0, stream),
+           "finalize kernel");
+  }
   if (!c->fs_call) {
     CU_TRY(cudaMemcpyAsync(c->d_chunks.p, c->plan.chunks.data(), c->plan.chunks.size() * sizeof(ChunkEntry),
                            cudaMemcpyHostToDevice, stream),
@@ -491,8 +515,9 @@ int prepare_call(EspbResampleBatch *c, int n_in, int n_out, float ratio, cudaStr
   if (!c->tables_uploaded)
     CU_TRY(cudaEventCreateWithFlags(&c->tables_uploaded, cudaEventDisableTiming), "cudaEventCreate");
   // (pageable tables were copied to a staging area before cudaMemcpyAsync returned: nothing to wait for)
-  const size_t pin_from = (size_t) 2 << 20;
-  if (c->sched.outs.cap * sizeof(OutEntry) >= pin_from || c->plan.chunks.cap * sizeof(ChunkEntry) >= pin_from ||
+  const size_t pin_from = kPinTablesFrom;
+  if (c->sched.outs.cap * sizeof(OutEntry) >= pin_from || c->sched.segs.cap * sizeof(SchedSegment) >= pin_from ||
+      c->plan.chunks.cap * sizeof(ChunkEntry) >= pin_from ||
       c->plan.pass_chunk_begin.cap * sizeof(int32_t) >= pin_from) {
     CU_TRY(cudaEventRecord(c->tables_uploaded, stream), "cudaEventRecord");
     c->tables_upload_pending = true;
@@ -933,6 +958,12 @@ EspbResampleBatch *espb_resampleInit(int num_streams, int numChannels, int numTa
   c->sched.outs.on_release = c->plan.chunks.on_release = c->plan.pass_chunk_begin.on_release = unpin_host_range;
   c->spare_outs.on_acquire = c->spare_chunks.on_acquire = c->spare_pcb.on_acquire = pin_host_range;
   c->spare_outs.on_release = c->spare_chunks.on_release = c->spare_pcb.on_release = unpin_host_range;
+  c->sched.segs.on_acquire = c->spare_segs.on_acquire = pin_host_range;
+  c->sched.segs.on_release = c->spare_segs.on_release = unpin_host_range;
+  {
+    const char *sm = getenv("ESPB_SCHED");
+    c->sched_segments = !(sm && strcmp(sm, "seq") == 0);
+  }
   cudaGetDevice(&c->device);
   c->num_streams = num_streams;
   c->channels = numChannels;
@@ -995,6 +1026,7 @@ void espb_resampleFree(EspbResampleBatch *c) {
   c->yt.release();
   c->yt2.release();
   c->d_outs.release();
+  c->d_segs.release();
   c->d_chunks.release();
   c->d_pcb.release();
   c->d_G.release();
@@ -1594,6 +1626,45 @@ int espb_plan_schedule(int numTaps, int numFilters, int flags, float outputOffse
       kind[i] = s.outs[i].kind;
   }
   return ESPB_OK;
+}
+
+// The same entries through the closed-form (segmented) schedule and its host expansion: what the device path
+// computes.  Returns the number of segments (< 0 on error); outputs as in espb_plan_schedule.
+int espb_plan_schedule_segments(int numTaps, int numFilters, int flags, float outputOffset, int inputIndex,
+                                int numInputFrames, int numOutputFrames, float ratio, unsigned int *input_used,
+                                unsigned int *output_generated, float *end_outputOffset, int *end_inputIndex,
+                                int32_t *window_start, int32_t *phase, float *weight, int32_t *kind) {
+  if ((numTaps & 3) || numTaps <= 0 || numTaps > 1024 || numFilters < 2 || numFilters > 1024)
+    return fail(ESPB_ERR_ARG, "plan_schedule_segments: invalid taps/filters");
+  const ArtGeometry geo{numTaps, numFilters, flags};
+  Schedule s;
+  build_schedule_segments(geo, ArtState{outputOffset, inputIndex}, numInputFrames, numOutputFrames, ratio, s);
+  if (input_used)
+    *input_used = s.used;
+  if (output_generated)
+    *output_generated = s.generated;
+  if (end_outputOffset)
+    *end_outputOffset = s.end.offset;
+  if (end_inputIndex)
+    *end_inputIndex = s.end.index;
+  if (window_start || phase || weight || kind) {
+    std::vector<OutEntry> e(s.generated ? s.generated : 1);
+    expand_segments(geo, s, e.data());
+    int cursor = 0;
+    for (size_t i = 0; i < s.generated; ++i) {
+      if (window_start)
+        window_start[i] = e[i].ws;
+      if (phase)
+        phase[i] = e[i].phase;
+      if (weight)
+        weight[i] = e[i].w;
+      if (kind)
+        kind[i] = e[i].kind;
+      if (schedule_ws(s, (int) i, &cursor) != e[i].ws)
+        return fail(ESPB_ERR_STATE, "plan_schedule_segments: schedule_ws disagrees with the expansion");
+    }
+  }
+  return (int) s.segs.size();
 }
 
 int espb_plan_passes(int numTaps, int numFilters, int flags, float outputOffset, int inputIndex, int numInputFrames,

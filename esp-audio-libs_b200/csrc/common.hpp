@@ -40,6 +40,15 @@ struct OutEntry {
   int32_t kind;    // OutKind
 };
 
+// A run of consecutive outputs whose offsets form an exact arithmetic progression (plan.cpp:build_schedule_segments):
+// output n0 + j has offset off0 + j * inc (exact: all terms are multiples of one ulp) and window start
+// ws_base + floor(offset).  The host emits a few of these per ring cycle; the device expands them into OutEntry.
+struct SchedSegment {
+  int32_t n0, count;
+  int32_t ws_base;
+  float off0, inc;
+};
+
 // One pipeline chunk: kChunkRows consecutive input frames starting at j_start that
 // belong to pass `pass` (a pass = blocks_per_pass output blocks sharing one sweep).
 struct ChunkEntry {

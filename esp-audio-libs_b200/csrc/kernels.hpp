@@ -58,6 +58,8 @@ enum OutVec : int { kOutVecNone = 0, kOutVecPlanar = 1, kOutVecStereo = 2, kOutV
 size_t resample_smem_bytes(int bpp, int chunk_rows, int g_row_floats = kGRowFloats);
 size_t g_chunk_floats(int bpp, int chunk_rows, int g_row_floats = kGRowFloats);
 cudaError_t launch_finalize(OutEntry *outs, int n, int n_filters, bool lowpass, bool interp, cudaStream_t stream);
+cudaError_t launch_expand_schedule(const SchedSegment *segs, int n_segs, OutEntry *outs, int n, int n_filters,
+                                   bool lowpass, bool interp, cudaStream_t stream);
 cudaError_t launch_expand(const float *bank, const OutEntry *outs, const ChunkEntry *chunks, float *G,
                           int chunk_first, int n_chunks, int n_out, int taps, int bpp, int chunk_rows,
                           bool split_at_zero, cudaStream_t stream, int g_row_floats = kGRowFloats);

@@ -184,6 +184,176 @@ void finalize_entries(const ArtGeometry &g, OutEntry *out, size_t n) {
   }
 }
 
+void build_schedule_segments(const ArtGeometry &g, ArtState start, int n_in, int n_out, float ratio, Schedule &s) {
+  const int half = g.taps / 2, ring = g.taps * 16, drop = ring - g.taps, idx0 = start.index;
+  const float thr = (float) (ring - half);  // an output whose offset has reached this needs the ring rebase first
+  const float step = 1.0f / ratio;
+  s.outs.clear();
+  s.segs.clear();
+  s.segmented = true;
+  s.raw = false;
+  float off = start.offset;
+  int idx = start.index;
+  long long base = 0, in_left = n_in > 0 ? n_in : 0, out_left = n_out > 0 ? n_out : 0;
+  unsigned used = 0, gen = 0;
+  // The reference machine itself, for at most max_emit outputs from the current state (which is always "between
+  // two emissions").  false: the call has ended (output space or input exhausted).
+  auto emit_seq = [&](long long max_emit) -> bool {
+    long long emitted = 0;
+    for (;;) {
+      if (out_left <= 0)
+        return false;
+      if (emitted >= max_emit)
+        return true;
+      if (off >= (float) (idx - half)) {
+        if (in_left <= 0)
+          return false;
+        if (idx == ring) {
+          off -= (float) drop;
+          idx -= drop;
+          base += drop;
+        }
+        ++idx;
+        ++used;
+        --in_left;
+      } else {
+        s.segs.push_back(SchedSegment{(int32_t) gen, 1, (int32_t) (base - half + 1 - idx0), off, 0.0f});
+        off += step;
+        ++gen;
+        --out_left;
+        ++emitted;
+      }
+    }
+  };
+  // the closed form needs a sane step: positive, and small against the ring (ratios below ~4 / taps fall back)
+  const bool closed_form_ok = step > 0.0f && step < (float) g.taps * 0.25f && off >= 0.0f;
+  for (;;) {
+    if (out_left <= 0)
+      break;
+    if (!closed_form_ok) {
+      emit_seq(1LL << 62);
+      break;
+    }
+    // ---- one piece, tentatively (committed only if the input covers all of it)
+    float o = off;
+    int id = idx;
+    long long b = base, il = in_left;
+    unsigned consumed = 0;
+    if (o >= thr) {  // consume up to idx == ring, then the consume that rebases (art_resampler.cpp:175-181)
+      const long long c = (long long) (ring - id) + 1;
+      if (il < c) {
+        emit_seq(1LL << 62);
+        break;
+      }
+      il -= c;
+      consumed += (unsigned) c;
+      id = g.taps + 1;
+      o -= (float) drop;
+      b += drop;
+    }
+    if (!(o >= 1.0f)) {  // (sub-unit offsets only occur for tiny filters: not worth a closed form)
+      if (!emit_seq(1))
+        break;
+      continue;
+    }
+    const int ex = ilogbf(o);
+    const float top = ldexpf(1.0f, ex + 1);
+    const double u = ldexp(1.0, ex - 23);      // one ulp of this binade
+    const float lim = top < thr ? top : thr;   // offsets below it continue the progression
+    const float o1 = o + step;
+    const float o2 = o1 + step;
+    const float inc = o1 - o;
+    if (!(o1 < lim) || !(inc > 0.0f) || (o2 < lim && (o2 - o1) != inc)) {
+      // a one-output piece, or a tie whose first rounding differs from the following ones: one exact step
+      if (!emit_seq(1))
+        break;
+      continue;
+    }
+    const long long O = (long long) ((double) o / u), I = (long long) ((double) inc / u),
+                    Lm = (long long) ((double) lim / u);
+    // o2 < lim: the first two increments agree, so all do (a tie rounding can only differ on its first step), and the
+    // piece holds the offsets O + j I < Lm.  Otherwise the piece is {o, o1} and o2 (a real float sum) starts the next.
+    const long long nj = o2 < lim ? (Lm - O + I - 1) / I : 2;
+    const long long m = nj < out_left ? nj : out_left;
+    const double o_last = (double) (O + (m - 1) * I) * u;
+    long long need = (long long) o_last + half + 1 - id;  // o_last >= 0: truncation == floor
+    if (need < 0)
+      need = 0;
+    if (need > il) {
+      // the input ends inside this piece: the outputs it can still feed (offset < idx + input - half) leave as a
+      // run, the reference machine then consumes what is left and ends the call
+      const long long F1 = il + id - half;
+      long long cnt = ((long long) ((double) F1 / u) - O + I - 1) / I;
+      cnt = cnt < 0 ? 0 : (cnt > m ? m : cnt);
+      if (cnt > 0) {
+        const double o_fed = (double) (O + (cnt - 1) * I) * u;
+        long long nd = (long long) o_fed + half + 1 - id;
+        nd = nd < 0 ? 0 : nd;
+        in_left = il - nd;
+        used += consumed + (unsigned) nd;
+        idx = id + (int) nd;
+        base = b;
+        s.segs.push_back(SchedSegment{(int32_t) gen, (int32_t) cnt, (int32_t) (b - half + 1 - idx0), o, inc});
+        gen += (unsigned) cnt;
+        out_left -= cnt;
+        off = (float) o_fed + step;
+      }
+      emit_seq(1LL << 62);
+      break;
+    }
+    in_left = il - need;
+    used += consumed + (unsigned) need;
+    idx = id + (int) need;
+    base = b;
+    s.segs.push_back(SchedSegment{(int32_t) gen, (int32_t) m, (int32_t) (b - half + 1 - idx0), o, inc});
+    gen += (unsigned) m;
+    out_left -= m;
+    off = (float) o_last + step;
+  }
+  s.used = used;
+  s.generated = gen;
+  s.end = ArtState{off, idx};
+}
+
+static inline float segment_offset(const SchedSegment &sg, int j) {
+  return (float) ((double) sg.off0 + (double) j * (double) sg.inc);  // exact: every term is a multiple of one ulp
+}
+
+int32_t schedule_ws(const Schedule &s, int k, int *cursor) {
+  if (!s.segmented)
+    return s.raw ? s.outs[k].ws + (int32_t) s.outs[k].w : s.outs[k].ws;
+  int c = cursor ? *cursor : 0;
+  const int n = (int) s.segs.size();
+  if (c < 0 || c >= n || s.segs[c].n0 > k) {  // not a forward walk: binary search
+    int lo = 0, hi = n - 1;
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (s.segs[mid].n0 <= k)
+        lo = mid;
+      else
+        hi = mid - 1;
+    }
+    c = lo;
+  }
+  while (c + 1 < n && s.segs[c + 1].n0 <= k)
+    ++c;
+  if (cursor)
+    *cursor = c;
+  const SchedSegment &sg = s.segs[c];
+  return sg.ws_base + (int32_t) segment_offset(sg, k - sg.n0);
+}
+
+void expand_segments(const ArtGeometry &g, const Schedule &s, OutEntry *out) {
+  for (size_t i = 0; i < s.segs.size(); ++i) {
+    const SchedSegment &sg = s.segs[i];
+    for (int j = 0; j < sg.count; ++j) {
+      out[sg.n0 + j].ws = sg.ws_base;
+      out[sg.n0 + j].w = segment_offset(sg, j);
+    }
+  }
+  finalize_entries(g, out, s.generated);
+}
+
 unsigned required_samples(const ArtGeometry &g, ArtState st, int n_out, float ratio) {
   unsigned used, gen;
   run_machine(g, st, 0, n_out, ratio, false, true, &used, &gen, [](float, long long) {});
@@ -196,14 +366,13 @@ unsigned expected_output(const ArtGeometry &g, ArtState st, int n_in, float rati
   return gen;
 }
 
-static inline int32_t entry_ws(const Schedule &s, int k) {
-  return s.raw ? s.outs[k].ws + (int32_t) s.outs[k].w : s.outs[k].ws;  // raw: base + floor(offset)
-}
 
 void build_pass_plan(const Schedule &s, int taps, int blocks_per_pass, int chunk_rows, PassPlan &p,
                      bool split_at_zero) {
   const int opp = blocks_per_pass * kOutputsPerBlock;
-  const int n = (int) s.outs.size();
+  const int n = (int) s.generated;
+  int cursor = 0;
+  auto entry_ws = [&](const Schedule &sc, int k) { return schedule_ws(sc, k, &cursor); };
   p.outputs_per_pass = opp;
   p.chunks.clear();
   p.pass_chunk_begin.clear();

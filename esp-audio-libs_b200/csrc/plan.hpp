@@ -84,7 +84,9 @@ struct PodBuffer {
 };
 
 struct Schedule {
-  PodBuffer<OutEntry> outs;
+  PodBuffer<OutEntry> outs;       // per-output entries (sequential form; empty in the segmented form)
+  PodBuffer<SchedSegment> segs;   // segmented form: arithmetic-progression runs, expanded on the device
+  bool segmented = false;
   unsigned used = 0, generated = 0;
   ArtState end{};
   bool raw = false;  // entries still hold (window-start base, offset): finalize_entries() not applied yet
@@ -94,6 +96,18 @@ struct Schedule {
 // :213-240) that records, per output, the window start / phase / weight / kind.
 void build_schedule(const ArtGeometry &g, ArtState start, int n_in, int n_out, float ratio, Schedule &s,
                     bool finalize = true);
+// The same schedule in closed form.  The offset is a sequential FP32 accumulator (art_resampler.cpp:195,236), but
+// inside one binade every addition of the same step rounds the same way, so the offsets of consecutive outputs are an
+// exact arithmetic progression until the offset crosses a power of two or the ring is rebased (:175-181).  The host
+// walks those pieces (a handful per ring cycle of 15 x taps input frames: O(frames / taps) work instead of
+// O(frames)), using real float additions at every piece boundary and the sequential machine wherever the closed form
+// does not apply (tie roundings, the end of the input); the per-output entries are expanded on the device
+// (espb_expand_schedule_kernel).  Bit-identical to build_schedule by construction and by test (test_host_plan.py).
+void build_schedule_segments(const ArtGeometry &g, ArtState start, int n_in, int n_out, float ratio, Schedule &s);
+// window start of output k of either form (segment lookup through *cursor, which callers walk monotonically)
+int32_t schedule_ws(const Schedule &s, int k, int *cursor);
+// host expansion of the segmented form into finalized entries (host API, tests)
+void expand_segments(const ArtGeometry &g, const Schedule &s, OutEntry *out);
 // Second pass of the schedule (host version; espb_finalize_kernel is the device twin).
 void finalize_entries(const ArtGeometry &g, OutEntry *entries, size_t n);
 

@@ -78,6 +78,49 @@ __global__ void __launch_bounds__(256)
   outs[k] = e;
 }
 
+// Segmented schedule -> finalized entries: every output finds its arithmetic-progression run (plan.cpp:
+// build_schedule_segments) by binary search, rebuilds its offset exactly (all terms are multiples of one ulp of the
+// run's binade, so the double-precision product and sum are exact and the conversion back does not round) and
+// finishes it like espb_finalize_kernel.  The host uploads a few hundred bytes per ring cycle instead of 16 bytes
+// per output.
+__global__ void __launch_bounds__(256)
+    espb_expand_schedule_kernel(const SchedSegment *__restrict__ segs, int n_segs, OutEntry *__restrict__ outs, int n,
+                                float n_filters, int lowpass, int interp) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n)
+    return;
+  int lo = 0, hi = n_segs - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (__ldg(&segs[mid].n0) <= k)
+      lo = mid;
+    else
+      hi = mid - 1;
+  }
+  const SchedSegment sg = segs[lo];
+  const float off = (float) ((double) sg.off0 + (double) (k - sg.n0) * (double) sg.inc);
+  const float fl = (float) (int) off;
+  float frac = __fsub_rn(off, fl);
+  OutEntry e;
+  e.ws = sg.ws_base + (int32_t) fl;
+  e.phase = 0;
+  e.w = 0.0f;
+  if (frac == 0.0f && !lowpass) {
+    e.kind = kKindPass;
+  } else if (!interp) {
+    e.kind = kKindSingle;
+    e.phase = (int) __fadd_rn(__fmul_rn(frac, n_filters), 0.5f);
+  } else {
+    frac = __fmul_rn(frac, n_filters);
+    const int i = (int) frac;
+    frac = __fsub_rn(frac, (float) i);
+    e.phase = i;
+    e.w = frac;
+    e.kind = (frac == 0.0f && !lowpass) ? kKindSingle : kKindBlend;
+  }
+  outs[k] = e;
+}
+
 // ---------------------------------------------------------------------------------
 // G expansion.  CTAs stride over the chunks; within a chunk a warp takes 32 consecutive rows of one float4
 // (two outputs x two filters), so its reads of a filter row are one coalesced 128-byte line and the two schedule
@@ -631,6 +674,16 @@ cudaError_t launch_finalize(OutEntry *outs, int n, int n_filters, bool lowpass, 
   if (n <= 0)
     return cudaSuccess;
   espb_finalize_kernel<<<(n + 255) / 256, 256, 0, stream>>>(outs, n, (float) n_filters, lowpass, interp);
+  count_launch();
+  return cudaGetLastError();
+}
+
+cudaError_t launch_expand_schedule(const SchedSegment *segs, int n_segs, OutEntry *outs, int n, int n_filters,
+                                   bool lowpass, bool interp, cudaStream_t stream) {
+  if (n <= 0 || n_segs <= 0)
+    return cudaSuccess;
+  espb_expand_schedule_kernel<<<(n + 255) / 256, 256, 0, stream>>>(segs, n_segs, outs, n, (float) n_filters, lowpass,
+                                                                   interp);
   count_launch();
   return cudaGetLastError();
 }

@@ -296,6 +296,13 @@ int espb_plan_schedule(int numTaps, int numFilters, int flags, float outputOffse
                        int numInputFrames, int numOutputFrames, float ratio, unsigned int *input_used,
                        unsigned int *output_generated, float *end_outputOffset, int *end_inputIndex,
                        int32_t *window_start, int32_t *phase, float *weight, int32_t *kind);
+/* The schedule of the same call through the closed-form ("segmented") planner the processing path uses — offsets
+ * as exact arithmetic progressions per binade and ring cycle, expanded per output — for checking it against
+ * espb_plan_schedule (the reference's sequential state machine).  Returns the number of segments, < 0 on error. */
+int espb_plan_schedule_segments(int numTaps, int numFilters, int flags, float outputOffset, int inputIndex,
+                                int numInputFrames, int numOutputFrames, float ratio, unsigned int *input_used,
+                                unsigned int *output_generated, float *end_outputOffset, int *end_inputIndex,
+                                int32_t *window_start, int32_t *phase, float *weight, int32_t *kind);
 /* The kernel-side work list of a call: passes of `blocks_per_pass` x 8 outputs, each swept in chunks of `chunk_rows`
  * input rows starting at chunk_start[] (relative to the call's first input frame; negative = carried frames);
  * pass p owns chunks [pass_chunk_begin[p], pass_chunk_begin[p+1]).  split_at_zero: the form the direct-input kernel

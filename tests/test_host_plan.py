@@ -233,3 +233,53 @@ def test_pass_plan_covers_every_window(taps, ratio, n_in, split):
                 assert nxt == j + rows or (split and j < 0 <= j + rows and nxt == 0) or (split and j < 0 and nxt == 0)
             covered[max(j, lo) - lo: max(min(end, hi), lo) - lo] = True
         assert covered.all(), (p, lo, hi, starts)
+
+
+def test_closed_form_schedule_is_the_sequential_machine():
+    """The processing path plans with a closed form (plan.cpp:build_schedule_segments: the FP32 offset accumulator of
+    art_resampler.cpp:195,236 advances by an exact constant inside one binade, so runs of outputs are arithmetic
+    progressions) and expands it per output on the device.  Its host expansion must equal the reference's
+    sequential state machine bit for bit — entries, counts and final state — for the BASELINE shapes and for random
+    geometries, ratios (rational, near-unity, tie-prone steps, strong down-sampling) and chained calls."""
+    rng = np.random.default_rng(5)
+
+    def same(taps, filters, flags, off, idx, n_in, n_out, ratio):
+        a = espb.plan_schedule(taps, filters, flags, off, idx, n_in, n_out, ratio)
+        b = espb.plan_schedule_segments(taps, filters, flags, off, idx, n_in, n_out, ratio)
+        assert (a["used"], a["generated"], a["end_index"]) == (b["used"], b["generated"], b["end_index"])
+        assert a["end_offset"].tobytes() == b["end_offset"].tobytes()
+        for k in ("ws", "phase", "w", "kind"):
+            assert a[k].tobytes() == b[k].tobytes(), (k, taps, filters, flags, off, idx, n_in, n_out, float(ratio))
+        return a, b
+
+    a, b = same(256, 256, 3, 256.0, 256, 441000, 480016, f32(48000) / f32(44100))       # C1: 479880 outputs
+    assert a["generated"] == 479880 and b["segments"] < 1000                             # ... in < 1000 runs
+    same(1024, 256, 5, 1024.0, 1024, 960000, 441100, f32(44100) / f32(96000))            # C4 unit
+    same(256, 256, 1, 256.0, 256, 480000, 441000, f32(44100) / f32(48000))               # C5 unit
+    same(256, 256, 3, 256.0, 256, 160000, 480100, f32(3.0))                              # C3 unit
+    for _ in range(150):
+        taps = int(rng.choice([4, 8, 16, 32, 64, 128, 256, 512, 1024, 12, 20, 36, 100, 260]))
+        filters, flags = int(rng.integers(2, 1025)), int(rng.integers(0, 8))
+        kind = rng.integers(0, 6)
+        if kind == 0:
+            ratio = f32(rng.uniform(0.3, 3.0))
+        elif kind == 1:
+            ratio = f32(rng.choice([0.5, 2.0, 1.0, 4.0, 0.25, 1.5, 3.0, 8.0, 0.125]))
+        elif kind == 2:
+            ratio = f32(rng.integers(1, 200)) / f32(rng.integers(1, 200))
+        elif kind == 3:
+            ratio = f32(1.0) + f32(rng.uniform(-1e-3, 1e-3))
+        elif kind == 4:
+            ratio = f32(1.0) / (f32(0.5) + f32(2.0 ** -int(rng.integers(10, 24))))  # steps that round on ties
+        else:
+            ratio = f32(rng.uniform(0.02, 0.3))
+        off, idx = f32(taps / 2), taps
+        if rng.random() < 0.7:
+            off = f32(off + f32(taps / 2))
+        if rng.random() < 0.3:
+            off = f32(off + f32(rng.uniform(0, 3)))
+        for _call in range(int(rng.integers(1, 5))):
+            n_in = int(rng.choice([0, 1, 7, 441, 1000, 5000, 20000, 70000]))
+            n_out = int(rng.choice([0, 1, 5, 480, 1200, 6000, 30000, 200000]))
+            a, _ = same(taps, filters, flags, float(off), idx, n_in, n_out, ratio)
+            off, idx = a["end_offset"], a["end_index"]
