@@ -107,6 +107,7 @@ def lib():
         "espb_resampleCopyFilters": (i, [vp, vp]),
         "espb_resampleProcessInterleaved": (_Result, [vp, vp, i64, i, vp, i64, i, f, vp]),
         "espb_resampleProcess": (_Result, [vp, vp, i64, i64, i, vp, i64, i64, i, f, vp]),
+        "espb_resampleProcessPlanes": (_Result, [vp, vp, i, vp, i, f, vp]),
         "espb_resampleProcessLayout": (_Result, [vp, vp, C.POINTER(_Layout), i, vp, C.POINTER(_Layout), i, f, vp]),
         "espb_resampleProcessInterleavedHost": (_Result, [vp, vp, i64, i, vp, i64, i, f]),
         "espb_biquad_lowpass": (None, [C.POINTER(_Coeffs), C.c_double]),
@@ -119,6 +120,8 @@ def lib():
         "espb_biquad_set_time_blocks": (i, [vp, i, i]),
         "espb_resampler_set_biquad_time_blocks": (i, [vp, i, i]),
         "espb_last_status": (i, []),
+        "espb_resampleGroupsIsFused": (i, [vp]),
+        "espb_resampleGroupsReset": (i, [vp, i, vp]),
         "espb_nccl_version": (i, []),
         "espb_measure_host_link": (i, [i, vp, sz, sz, i, C.POINTER(C.c_double)]),
         "espb_multi_last_error": (C.c_char_p, []),
@@ -501,6 +504,28 @@ class ResampleBatch:
         return y, int(r.input_used), int(r.output_generated)
 
 
+    def process_planes(self, planes, n_out, ratio):
+        """planes: list of num_streams*channels 1-D float32 arrays (one separately allocated device buffer each,
+        plane q = stream q // channels, channel q % channels) -> (list of output planes, used, generated)."""
+        n = len(planes)
+        n_in = len(planes[0])
+        cap = max(n_out, 1)
+        d_in = [DeviceBuffer.from_numpy(np.ascontiguousarray(p, np.float32) if n_in else np.zeros(1, np.float32))
+                for p in planes]
+        d_out = [DeviceBuffer(cap * 4) for _ in range(n)]
+        for d in d_out:
+            d.zero()
+        pin = (C.c_void_p * n)(*[d.ptr for d in d_in])
+        pout = (C.c_void_p * n)(*[d.ptr for d in d_out])
+        r = lib().espb_resampleProcessPlanes(self.h, pin, n_in, pout, n_out, ratio, None)
+        if _err():
+            raise EspbError(f"espb_resampleProcessPlanes: {_err()}")
+        ys = [d.download(np.float32)[: r.output_generated].copy() for d in d_out]
+        for d in d_in + d_out:
+            d.free()
+        return ys, int(r.input_used), int(r.output_generated)
+
+
 class ResampleGroups:
     """Ratio groups (ASRC): one batch context per group of streams that share a clock."""
 
@@ -515,6 +540,12 @@ class ResampleGroups:
 
     def context(self, k):
         return lib().espb_resampleGroupsContext(self.h, k)
+
+    def is_fused(self):
+        return bool(lib().espb_resampleGroupsIsFused(self.h))
+
+    def reset(self, k, stream=None):
+        _check(lib().espb_resampleGroupsReset(self.h, k, stream), "resampleGroupsReset")
 
     def advance(self, k, delta):
         lib().espb_resampleAdvancePosition(self.context(k), delta)

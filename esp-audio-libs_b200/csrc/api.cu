@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "../../include/esp_audio_b200.h"
+#include "internal.hpp"
 #include "kernels.hpp"
 #include "plan.hpp"
 
@@ -247,6 +248,12 @@ namespace {
 
 struct HostPipe {
   static const int kStreams = 3;
+  // error exit of a host-buffer call: copies into the caller's buffers may still be in flight on these streams
+  void drain() {
+    for (int i = 0; i < kStreams; ++i)
+      if (s[i])
+        cudaStreamSynchronize(s[i]);
+  }
   cudaStream_t s[kStreams] = {nullptr, nullptr, nullptr};
   cudaEvent_t ready = nullptr;
   bool ok = false;
@@ -298,6 +305,7 @@ int pick_slab_streams(int num_streams, int channels) {
 // ART resampler batch
 // ------------------------------------------------------------------------------------
 struct EspbResampleBatch {
+  bool state_only = false;  // position state and geometry only (internal.hpp): the fused clock groups own the data
   int device = -1;  // the CUDA device that was current at creation: all of the context's memory lives there
   int num_streams = 0, channels = 0;
   ArtGeometry geo{};
@@ -357,6 +365,7 @@ struct EspbResampleBatch {
   // which in a stream of calls has long finished (no host/device serialisation from call to call)
   PodBuffer<OutEntry> spare_outs;
   PodBuffer<SchedSegment> spare_segs;
+  DevBuf d_ptrs;  // device copy of the plane-pointer tables of espb_resampleProcessPlanes: [2][n_series]
   DevBuf d_segs;
   bool sched_segments = true;  // closed-form schedule expanded on the device (ESPB_SCHED=seq: per-output host schedule)
   PodBuffer<ChunkEntry> spare_chunks;
@@ -395,6 +404,8 @@ int prepare_call(EspbResampleBatch *c, int n_in, int n_out, float ratio, cudaStr
     if (cudaGetDevice(&dev) != cudaSuccess || dev != c->device)
       return fail(ESPB_ERR_STATE, "this context was created on another CUDA device (espb_set_device before the call)");
   }
+  if (c->state_only)
+    return fail(ESPB_ERR_STATE, "this context belongs to a fused clock-group set: process through espb_resampleGroups*");
   if (!(ratio > 0.0f) || !(ratio <= 3.0e38f))  // NaN, <= 0, Inf: the reference would loop for ever or index wildly
     return fail(ESPB_ERR_ARG, "resampleProcess: ratio must be a positive finite number");
   if (c->state_event_pending) {  // order this call after an asynchronous reset issued on another stream
@@ -641,6 +652,12 @@ struct PcmOut {
   int64_t scratch_row = 0;
 };
 
+// Planar buffers as pointer tables (resampleProcess, include/art_resampler.h:36-37): device copies of the tables.
+struct PtrIO {
+  const float *const *in = nullptr;  // [n_series] device pointers, plane q = stream q / channels, channel q % channels
+  float *const *out = nullptr;
+};
+
 // Optional in-library neighbours of the resampler (Resampler::resample's pre / post low-pass).
 struct StageFilter {
   const BiquadParams *params = nullptr;  // NULL: no filter
@@ -698,7 +715,7 @@ int make_input_map(CUtensorMap *map, const float *in, int64_t stream_stride, int
 int run_series_range(EspbResampleBatch *c, int series_first, int n_series, const float *in, const EspbLayout &il,
                      float *out, const EspbLayout &ol, int n_in, cudaStream_t stream, bool g_preexpanded,
                      const StageFilter *pre = nullptr, const StageFilter *post = nullptr,
-                     const PcmIn *pcm_in = nullptr, const PcmOut *pcm_out = nullptr) {
+                     const PcmIn *pcm_in = nullptr, const PcmOut *pcm_out = nullptr, const PtrIO *ptrs = nullptr) {
   const int taps = c->geo.taps;
   const int g0 = series_first / kSeriesPerRow, ng = (n_series + kSeriesPerRow - 1) / kSeriesPerRow;
   const int64_t rows = c->xt_rows;
@@ -707,7 +724,7 @@ int run_series_range(EspbResampleBatch *c, int series_first, int n_series, const
   float *x_new = c->xt[1 - c->xt_cur].as<float>() + (size_t) g0 * rows * kSeriesPerRow;
   // direct input: nothing is staged — the kernel reads the carried frames where they lie and the new frames from
   // the caller's buffer; afterwards the frames [used - taps, used) become rows [0, taps) of the other buffer
-  const bool direct = c->direct_call && !pre && !post && !pcm_in && !pcm_out;
+  const bool direct = c->direct_call && !pre && !post && !pcm_in && !pcm_out && !ptrs;
   if (c->direct_call && !direct)
     return fail(ESPB_ERR_STATE, "direct-input plan with library stages around the resampler");
   if (!direct)
@@ -717,6 +734,11 @@ int run_series_range(EspbResampleBatch *c, int series_first, int n_series, const
   // caller's frames -> rows [taps, taps + n_in) of `dst` (+ `pad` zero rows): float layouts through the
   // transposing stage; packed PCM through the fused conversion, with the stage-by-stage path for the tail
   auto stage_input = [&](float *dst, int pad) -> int {
+    if (ptrs) {
+      CU_TRY(launch_transpose_ptrs(ptrs->in + series_first, n_series, n_in, dst, rows, taps, pad, stream),
+             "transpose kernel");
+      return ESPB_OK;
+    }
     if (pcm_in) {
       cudaError_t e = cudaSuccess;
       const int n_streams = n_series / c->channels;
@@ -770,7 +792,7 @@ int run_series_range(EspbResampleBatch *c, int series_first, int n_series, const
              "biquad kernel");
   }
   const bool post_on = post && post->params && c->sched.generated > 0;
-  const bool tm_out = (post_on || pcm_out) && c->sched.generated > 0;  // a library stage follows the resampler
+  const bool tm_out = (post_on || pcm_out || ptrs) && c->sched.generated > 0;  // a library stage follows the resampler
   float *y_tm = nullptr;
   if (tm_out)
     y_tm = c->yt.as<float>() + (size_t) g0 * c->yt_rows * kSeriesPerRow;
@@ -904,6 +926,9 @@ int run_series_range(EspbResampleBatch *c, int series_first, int n_series, const
                           (uint32_t) ((gen - fast) * c->channels), pcm_out->bits, pcm_out->clipped, true, stream),
                "f2q kernel");
       }
+    } else if (ptrs) {
+      CU_TRY(launch_untranspose_ptrs(y_f, c->yt_rows, 0, gen, ptrs->out + series_first, n_series, stream),
+             "untranspose kernel");
     } else {
       CU_TRY(launch_untranspose(y_f, c->yt_rows, 0, gen, out, ol.stream_stride, ol.channel_stride, ol.frame_stride,
                                 c->channels, n_series, stream),
@@ -1027,6 +1052,7 @@ void espb_resampleFree(EspbResampleBatch *c) {
   c->yt2.release();
   c->d_outs.release();
   c->d_segs.release();
+  c->d_ptrs.release();
   c->d_chunks.release();
   c->d_pcb.release();
   c->d_G.release();
@@ -1048,6 +1074,8 @@ void espb_resampleFree(EspbResampleBatch *c) {
 int espb_resampleReset(EspbResampleBatch *c, void *stream) {
   if (!c)
     return fail(ESPB_ERR_ARG, "resampleReset: NULL context");
+  if (c->state_only)
+    return fail(ESPB_ERR_STATE, "resampleReset: group of a fused clock-group set (use espb_resampleGroupsReset)");
   const size_t row_bytes = kSeriesPerRow * sizeof(float);
   CU_TRY(cudaMemset2DAsync(c->xt[c->xt_cur].as<float>() + (size_t) c->carry_row * kSeriesPerRow,
                            c->xt_rows * row_bytes, 0, c->geo.taps * row_bytes, c->n_groups(), as_stream(stream)),
@@ -1123,6 +1151,10 @@ void espb_resampleGetState(EspbResampleBatch *c, float *outputOffset, int *input
   *inputIndex = c->state.index;
 }
 int espb_resampleCopyFilters(EspbResampleBatch *c, float *host_dst) {
+  if (c->state_only) {
+    memcpy(host_dst, c->bank_host.data(), c->bank_host.size() * sizeof(float));
+    return ESPB_OK;
+  }
   // read back from the device copy: what the kernels actually use
   CU_TRY(cudaMemcpy(host_dst, c->bank.p, c->bank_host.size() * sizeof(float), cudaMemcpyDeviceToHost),
          "resampleCopyFilters");
@@ -1168,6 +1200,46 @@ EspbResampleResult espb_resampleProcess(EspbResampleBatch *c, const float *in, i
                                         float ratio, void *stream) {
   EspbLayout il = {in_stream_stride, in_channel_stride, 1}, ol = {out_stream_stride, out_channel_stride, 1};
   return espb_resampleProcessLayout(c, in, &il, numInputFrames, out, &ol, numOutputFrames, ratio, stream);
+}
+
+// resampleProcess with the reference's own argument form (include/art_resampler.h:36-37): one pointer per plane.
+// `inputs` / `outputs` are HOST arrays of num_streams * numChannels DEVICE pointers (plane q = stream q / channels,
+// channel q % channels), each plane a separately allocated buffer of numInputFrames / numOutputFrames floats.
+EspbResampleResult espb_resampleProcessPlanes(EspbResampleBatch *c, const float *const *inputs, int numInputFrames,
+                                              float *const *outputs, int numOutputFrames, float ratio, void *stream) {
+  EspbResampleResult res = {0, 0};
+  if (!c || !inputs || !outputs) {
+    fail(ESPB_ERR_ARG, "resampleProcessPlanes: NULL argument");
+    return res;
+  }
+  if (numInputFrames < 0)
+    numInputFrames = 0;
+  cudaStream_t s = as_stream(stream);
+  if (prepare_call(c, numInputFrames, numOutputFrames, ratio, s, false) != ESPB_OK)
+    return res;
+  const size_t n = (size_t) c->n_series();
+  // the tables are small (8 bytes per plane) and pageable: the driver copies them out before the call returns
+  if (c->d_ptrs.reserve(2 * n * sizeof(void *)) != cudaSuccess ||
+      cudaMemcpyAsync(c->d_ptrs.p, inputs, n * sizeof(void *), cudaMemcpyHostToDevice, s) != cudaSuccess ||
+      cudaMemcpyAsync(c->d_ptrs.as<void *>() + n, outputs, n * sizeof(void *), cudaMemcpyHostToDevice, s) !=
+          cudaSuccess) {
+    fail(ESPB_ERR_CUDA, "resampleProcessPlanes: pointer tables");
+    return res;
+  }
+  if (ensure_yt(c, (int64_t) c->sched.generated, false) != ESPB_OK)
+    return res;
+  PtrIO io;
+  io.in = reinterpret_cast<const float *const *>(c->d_ptrs.p);
+  io.out = reinterpret_cast<float *const *>(c->d_ptrs.as<void *>() + n);
+  const EspbLayout none = {0, 0, 1};
+  if (run_series_range(c, 0, c->n_series(), nullptr, none, nullptr, none, numInputFrames, s, false, nullptr, nullptr,
+                       nullptr, nullptr, &io) != ESPB_OK)
+    return res;
+  res.input_used = c->sched.used;
+  res.output_generated = c->sched.generated;
+  finish_call(c);
+  g_last_error.clear(), g_last_status = ESPB_OK;
+  return res;
 }
 
 // Host-buffer variant: rows of `in`/`out` are host memory (pinned for full PCIe speed).
@@ -1242,16 +1314,20 @@ EspbResampleResult espb_resampleProcessInterleavedHost(EspbResampleBatch *c, con
                           cudaMemcpyHostToDevice, s);
       if (e != cudaSuccess) {
         cuda_fail(e, "h2d");
+        hs->pipe.drain();
         return res;
       }
     }
-    if (run_series_range(c, st0 * ch, ns * ch, din, il, dout, ol, numInputFrames, s, single_slab_g) != ESPB_OK)
+    if (run_series_range(c, st0 * ch, ns * ch, din, il, dout, ol, numInputFrames, s, single_slab_g) != ESPB_OK) {
+      hs->pipe.drain();
       return res;
+    }
     if (out_row) {
       e = copy_rows_async(out + (size_t) st0 * out_stream_stride, (size_t) out_stream_stride * sizeof(float), dout,
                           out_cap_row * sizeof(float), out_row * sizeof(float), ns, cudaMemcpyDeviceToHost, s);
       if (e != cudaSuccess) {
         cuda_fail(e, "d2h");
+        hs->pipe.drain();
         return res;
       }
     }
@@ -2140,19 +2216,23 @@ EspbResamplerResults espb_resampler_resample_host(EspbResampler *r, const uint8_
                           cudaMemcpyHostToDevice, s);
       if (e != cudaSuccess) {
         cuda_fail(e, "h2d");
+        r->pipe.drain();
         return none;
       }
     }
     // the range helper offsets rows by s0 itself: pass the bases
     if (wrapper_run_range(r, st0, ns, r->pcm_in.as<uint8_t>(), (int64_t) in_pitch, r->pcm_out.as<uint8_t>(),
-                          (int64_t) out_pitch, wc, output_frames_free, gain_db, s, single_slab_g) != ESPB_OK)
+                          (int64_t) out_pitch, wc, output_frames_free, gain_db, s, single_slab_g) != ESPB_OK) {
+      r->pipe.drain();
       return none;
+    }
     if (out_bytes) {
       e = copy_rows_async(out + (size_t) st0 * out_stride_bytes, (size_t) out_stride_bytes,
                           r->pcm_out.as<uint8_t>() + (size_t) st0 * out_pitch, out_pitch, out_bytes, ns,
                           cudaMemcpyDeviceToHost, s);
       if (e != cudaSuccess) {
         cuda_fail(e, "d2h");
+        r->pipe.drain();
         return none;
       }
     }
@@ -2160,6 +2240,7 @@ EspbResamplerResults espb_resampler_resample_host(EspbResampler *r, const uint8_
                         cudaMemcpyDeviceToHost, s);
     if (e != cudaSuccess) {
       cuda_fail(e, "d2h clip counts");
+      r->pipe.drain();
       return none;
     }
   }
@@ -2176,3 +2257,28 @@ EspbResamplerResults espb_resampler_resample_host(EspbResampler *r, const uint8_
 }
 
 }  // extern "C"
+
+// ------------------------------------------------------------------------------------
+// internal.hpp
+// ------------------------------------------------------------------------------------
+namespace espb {
+
+EspbResampleBatch *new_state_only_context(int num_streams, int channels, const ArtGeometry &geo, float lowpass) {
+  EspbResampleBatch *c = new EspbResampleBatch();
+  c->state_only = true;
+  cudaGetDevice(&c->device);
+  c->num_streams = num_streams;
+  c->channels = channels;
+  c->geo = geo;
+  c->lowpass = lowpass;
+  c->state = initial_state(geo.taps);
+  return c;
+}
+ArtState context_state(const EspbResampleBatch *c) { return c->state; }
+void set_context_state(EspbResampleBatch *c, ArtState st) { c->state = st; }
+int context_mode(const EspbResampleBatch *c) { return c->mode; }
+void set_context_mode(EspbResampleBatch *c, int mode) { c->mode = mode; }
+int api_fail(int code, const char *what, const char *detail) { return fail(code, what, detail); }
+void api_ok() { g_last_error.clear(), g_last_status = ESPB_OK; }
+
+}  // namespace espb

@@ -75,6 +75,24 @@ cudaError_t launch_transpose(const float *in, int64_t in_ss, int64_t in_cs, int6
                              int n_in, float *xt, int64_t rows_cap, int row_first, int pad_rows,
                              cudaStream_t stream);
 
+// Fused clock groups (groups.cu): one launch serves every group of a set; blockIdx.y selects the group.  Offsets are
+// in floats / entries relative to the pointers in FsParams.
+struct FsGroupDesc {
+  int64_t x_off;      // this group's staging rows inside the current staging buffer
+  int64_t x_old_off;  // ... inside the previous one (the carried frames)
+  int64_t out_off;    // first stream of the group in the caller's output
+  int64_t in_off;     // ... in the caller's input
+  int32_t n_in, n_out;
+  int32_t outs_begin;           // first entry of the group in the concatenated schedule
+  int32_t seg_begin, n_segs;    // its runs in the concatenated segment table
+  int32_t carry_row;            // row of the previous staging buffer where the carried frames start
+};
+// planar buffers given as one device pointer per (stream, channel) plane (the table itself in device memory)
+cudaError_t launch_transpose_ptrs(const float *const *planes_dev, int n_series, int n_in, float *xt, int64_t rows_cap,
+                                  int row_first, int pad_rows, cudaStream_t stream);
+cudaError_t launch_untranspose_ptrs(const float *tm, int64_t rows_cap, int row_first, int n_rows,
+                                    float *const *planes_dev, int n_series, cudaStream_t stream);
+
 // Few-series form (resample_fs_kernel.cu): lanes own outputs instead of series; no expanded coefficients, no
 // chunk tables — the finalized schedule, the time-major staging rows and a slice-major copy of the bank.
 struct FsParams {
@@ -89,6 +107,7 @@ struct FsParams {
   int n_series, channels, n_out, taps;
   int kt, slice_floats;
   int q_per_out, x_tile_floats, out_vec;  // set by the launcher
+  const FsGroupDesc *groups;              // fused clock groups: per-group offsets and counts (blockIdx.y), else NULL
 };
 struct FsGeometry {
   int sv, b, q;          // series per lane, outputs per lane, lanes per output
@@ -100,7 +119,16 @@ size_t fs_slice_floats(int filters, int kt);
 void fs_build_bank_slices(const float *bank, int taps, int filters, int kt, float *dst);
 FsGeometry fs_geometry(int n_series);
 size_t fs_smem_bytes(const FsGeometry &g, size_t slice_floats, int x_rows);
-cudaError_t launch_resample_fs(const FsParams &p, const FsGeometry &g, int x_rows, bool exact, cudaStream_t stream);
+cudaError_t launch_resample_fs(const FsParams &p, const FsGeometry &g, int x_rows, bool exact, cudaStream_t stream,
+                               int n_groups = 1);
+// fused clock groups: carried frames + new input of every group -> compact time-major staging rows [row][pitch]
+cudaError_t launch_fsg_stage(const FsGroupDesc *groups, int n_groups, const float *old_buf, float *new_buf, int pitch,
+                             int taps, const float *in, int64_t in_ss, int channels, int n_series, int max_rows,
+                             cudaStream_t stream);
+// ... and the per-output schedule entries of every group from the concatenated segment table
+cudaError_t launch_expand_schedule_groups(const FsGroupDesc *groups, int n_groups, const SchedSegment *segs,
+                                          OutEntry *outs, int max_n_out, int n_filters, bool lowpass, bool interp,
+                                          cudaStream_t stream);
 
 // quantization_utils
 cudaError_t launch_q2f(const uint8_t *in, int64_t in_row_bytes, float *out, int64_t out_row_floats, int rows,

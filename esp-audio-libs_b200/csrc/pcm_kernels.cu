@@ -363,6 +363,17 @@ cudaError_t launch_q2f(const uint8_t *in, int64_t in_row_bytes, float *out, int6
                        uint32_t row_samples, int bits, float gain_factor, cudaStream_t stream) {
   if (rows <= 0 || row_samples == 0)
     return cudaSuccess;
+  constexpr int kMaxGridY = 65535;  // rows ride on gridDim.y: larger batches go in slices
+  if (rows > kMaxGridY) {
+    for (int r0 = 0; r0 < rows; r0 += kMaxGridY) {
+      const int nr = rows - r0 < kMaxGridY ? rows - r0 : kMaxGridY;
+      cudaError_t e = launch_q2f(in + (int64_t) r0 * in_row_bytes, in_row_bytes, out + (int64_t) r0 * out_row_floats,
+                                 out_row_floats, nr, row_samples, bits, gain_factor, stream);
+      if (e != cudaSuccess)
+        return e;
+    }
+    return cudaSuccess;
+  }
   const int nbytes = (bits + 7) / 8;
   int vec_ok = ((uintptr_t) in % 4 == 0) && (in_row_bytes % 4 == 0 || rows == 1) &&
                ((uintptr_t) out % 16 == 0) && (out_row_floats % 4 == 0 || rows == 1);
@@ -397,6 +408,17 @@ cudaError_t launch_f2q(const float *in, int64_t in_row_floats, uint8_t *out, int
                        uint32_t row_samples, int bits, uint32_t *clipped, bool clipped_per_row, cudaStream_t stream) {
   if (rows <= 0 || row_samples == 0)
     return cudaSuccess;
+  if (rows > 65535) {  // rows ride on gridDim.y: larger batches go in slices
+    for (int r0 = 0; r0 < rows; r0 += 65535) {
+      const int nr = rows - r0 < 65535 ? rows - r0 : 65535;
+      cudaError_t e = launch_f2q(in + (int64_t) r0 * in_row_floats, in_row_floats, out + (int64_t) r0 * out_row_bytes,
+                                 out_row_bytes, nr, row_samples, bits,
+                                 (clipped && clipped_per_row) ? clipped + r0 : clipped, clipped_per_row, stream);
+      if (e != cudaSuccess)
+        return e;
+    }
+    return cudaSuccess;
+  }
   const int nbytes = (bits + 7) / 8;
   const F2QConst c = make_f2q_const(bits);
   int vec_ok = ((uintptr_t) out % 4 == 0) && (out_row_bytes % 4 == 0 || rows == 1) &&

@@ -26,26 +26,26 @@ __device__ __forceinline__ uint32_t mulc2(uint32_t a, int32_t c) {
 }
 
 __global__ void __launch_bounds__(256)
-    espb_add_s16_vec_kernel(const uint4 *__restrict__ a, const uint4 *__restrict__ b, uint4 *__restrict__ out,
+    espb_add_s16_vec_kernel(const uint4 *a, const uint4 *b, uint4 *out,
                             uint64_t n_vec, int shift) {
   const uint64_t stride = (uint64_t) gridDim.x * blockDim.x;
   for (uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += stride) {
-    const uint4 x = __ldg(a + i), y = __ldg(b + i);
+    const uint4 x = a[i], y = b[i];  // plain loads: the buffers may alias (in-place mixing, as in the reference)
     out[i] = make_uint4(add2(x.x, y.x, shift), add2(x.y, y.y, shift), add2(x.z, y.z, shift), add2(x.w, y.w, shift));
   }
 }
 
 __global__ void __launch_bounds__(256)
-    espb_mulc_s16_vec_kernel(const uint4 *__restrict__ a, uint4 *__restrict__ out, uint64_t n_vec, int c) {
+    espb_mulc_s16_vec_kernel(const uint4 *a, uint4 *out, uint64_t n_vec, int c) {
   const uint64_t stride = (uint64_t) gridDim.x * blockDim.x;
   for (uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += stride) {
-    const uint4 x = __ldg(a + i);
+    const uint4 x = a[i];
     out[i] = make_uint4(mulc2(x.x, c), mulc2(x.y, c), mulc2(x.z, c), mulc2(x.w, c));
   }
 }
 
 __global__ void __launch_bounds__(256)
-    espb_add_s16_strided_kernel(const int16_t *__restrict__ a, const int16_t *__restrict__ b, int16_t *__restrict__ out,
+    espb_add_s16_strided_kernel(const int16_t *a, const int16_t *b, int16_t *out,
                                 uint64_t first, uint64_t n, int64_t s1, int64_t s2, int64_t so, int shift) {
   const uint64_t stride = (uint64_t) gridDim.x * blockDim.x;
   for (uint64_t i = first + (uint64_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(256)
 }
 
 __global__ void __launch_bounds__(256)
-    espb_mulc_s16_strided_kernel(const int16_t *__restrict__ a, int16_t *__restrict__ out, uint64_t first, uint64_t n,
+    espb_mulc_s16_strided_kernel(const int16_t *a, int16_t *out, uint64_t first, uint64_t n,
                                  int64_t si, int64_t so, int c) {
   const uint64_t stride = (uint64_t) gridDim.x * blockDim.x;
   for (uint64_t i = first + (uint64_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)

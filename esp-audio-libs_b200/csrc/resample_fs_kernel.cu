@@ -70,7 +70,18 @@ struct XVec<8> {
 };
 
 template <int SV, int B, bool EXACT>
-__global__ void __launch_bounds__(FS_THREADS) espb_resample_fs_kernel(const FsParams p) {
+__global__ void __launch_bounds__(FS_THREADS) espb_resample_fs_kernel(const FsParams pp) {
+  FsParams p = pp;
+  if (pp.groups) {  // fused clock groups: this CTA works on group blockIdx.y (its own schedule, rows and output)
+    const FsGroupDesc gd = pp.groups[blockIdx.y];
+    p.x = pp.x + gd.x_off;
+    p.outs = pp.outs + gd.outs_begin;
+    p.n_out = gd.n_out;
+    p.out = pp.out + gd.out_off;
+    const int per_cta = (FS_THREADS / pp.q_per_out) * B;
+    if ((int) blockIdx.x * per_cta >= gd.n_out)
+      return;
+  }
   extern __shared__ __align__(128) unsigned char fs_smem[];
   float *slices = reinterpret_cast<float *>(fs_smem);                            // [FS_STAGES][slice_floats]
   float *xtile = slices + (size_t) FS_STAGES * p.slice_floats;                   // [x_rows][Q * SV]
@@ -254,7 +265,7 @@ __global__ void __launch_bounds__(FS_THREADS) espb_resample_fs_kernel(const FsPa
 }
 
 template <int SV, int B, bool EXACT>
-cudaError_t launch_fs_t(const FsParams &p, size_t smem, int grid, cudaStream_t stream) {
+cudaError_t launch_fs_t(const FsParams &p, size_t smem, dim3 grid, cudaStream_t stream) {
   static PerDeviceOnce once;
   static size_t smem_set[64] = {};
   int dev = 0;
@@ -284,6 +295,104 @@ cudaError_t launch_fs_t(const FsParams &p, size_t smem, int grid, cudaStream_t s
 }
 
 }  // namespace
+
+// ---------------------------------------------------------------------------------
+// Fused clock groups: staging and schedule expansion for all groups of a set in one launch each.
+// ---------------------------------------------------------------------------------
+// Row r < taps of a group's new staging rows = row carry_row + r of its previous ones (the frames the reference keeps
+// at the front of its ring, art_resampler.cpp:216-222); row taps + j = input frame j of the group's streams
+// (interleaved caller layout), series beyond n_series are zero.
+__global__ void __launch_bounds__(256)
+    espb_fsg_stage_kernel(const FsGroupDesc *__restrict__ groups, const float *__restrict__ old_buf,
+                          float *__restrict__ new_buf, int pitch, int taps, const float *__restrict__ in, int64_t in_ss,
+                          int channels, int n_series, int rows_per_cta) {
+  const FsGroupDesc gd = groups[blockIdx.y];
+  const int rows = taps + gd.n_in;
+  const int r0 = blockIdx.x * rows_per_cta;
+  if (r0 >= rows)
+    return;
+  const int r1 = r0 + rows_per_cta < rows ? r0 + rows_per_cta : rows;
+  float *dst = new_buf + gd.x_off;
+  const float *old = old_buf + gd.x_old_off;
+  const float *src = in + gd.in_off;
+  for (int i = threadIdx.x; i < (r1 - r0) * pitch; i += blockDim.x) {
+    const int r = r0 + i / pitch, q = i % pitch;
+    float v = 0.0f;
+    if (r < taps) {
+      v = old[(int64_t) (gd.carry_row + r) * pitch + q];
+    } else if (q < n_series) {
+      const int st = q / channels, ch = q - st * channels;
+      v = __ldg(src + (int64_t) st * in_ss + (int64_t) (r - taps) * channels + ch);
+    }
+    dst[(int64_t) r * pitch + q] = v;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+    espb_expand_schedule_groups_kernel(const FsGroupDesc *__restrict__ groups, const SchedSegment *__restrict__ segs,
+                                       OutEntry *__restrict__ outs, float n_filters, int lowpass, int interp) {
+  const FsGroupDesc gd = groups[blockIdx.y];
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= gd.n_out)
+    return;
+  const SchedSegment *sg0 = segs + gd.seg_begin;
+  int lo = 0, hi = gd.n_segs - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (__ldg(&sg0[mid].n0) <= k)
+      lo = mid;
+    else
+      hi = mid - 1;
+  }
+  const SchedSegment sg = sg0[lo];
+  const float off = (float) ((double) sg.off0 + (double) (k - sg.n0) * (double) sg.inc);
+  const float fl = (float) (int) off;
+  float frac = __fsub_rn(off, fl);
+  OutEntry e;
+  e.ws = sg.ws_base + (int32_t) fl;
+  e.phase = 0;
+  e.w = 0.0f;
+  if (frac == 0.0f && !lowpass) {
+    e.kind = kKindPass;
+  } else if (!interp) {
+    e.kind = kKindSingle;
+    e.phase = (int) __fadd_rn(__fmul_rn(frac, n_filters), 0.5f);
+  } else {
+    frac = __fmul_rn(frac, n_filters);
+    const int i = (int) frac;
+    frac = __fsub_rn(frac, (float) i);
+    e.phase = i;
+    e.w = frac;
+    e.kind = (frac == 0.0f && !lowpass) ? kKindSingle : kKindBlend;
+  }
+  outs[gd.outs_begin + k] = e;
+}
+
+cudaError_t launch_fsg_stage(const FsGroupDesc *groups, int n_groups, const float *old_buf, float *new_buf, int pitch,
+                             int taps, const float *in, int64_t in_ss, int channels, int n_series, int max_rows,
+                             cudaStream_t stream) {
+  if (n_groups <= 0 || max_rows <= 0)
+    return cudaSuccess;
+  // about 2048 elements per CTA
+  int rows_per_cta = 2048 / pitch;
+  rows_per_cta = rows_per_cta < 1 ? 1 : rows_per_cta;
+  const dim3 grid((max_rows + rows_per_cta - 1) / rows_per_cta, n_groups);
+  espb_fsg_stage_kernel<<<grid, 256, 0, stream>>>(groups, old_buf, new_buf, pitch, taps, in, in_ss, channels, n_series,
+                                                  rows_per_cta);
+  count_launch();
+  return cudaGetLastError();
+}
+
+cudaError_t launch_expand_schedule_groups(const FsGroupDesc *groups, int n_groups, const SchedSegment *segs,
+                                          OutEntry *outs, int max_n_out, int n_filters, bool lowpass, bool interp,
+                                          cudaStream_t stream) {
+  if (n_groups <= 0 || max_n_out <= 0)
+    return cudaSuccess;
+  const dim3 grid((max_n_out + 255) / 256, n_groups);
+  espb_expand_schedule_groups_kernel<<<grid, 256, 0, stream>>>(groups, segs, outs, (float) n_filters, lowpass, interp);
+  count_launch();
+  return cudaGetLastError();
+}
 
 // Tap-range width of the slices: the widest power of two (4..64) that divides `taps` and keeps one slice of all
 // filters+2 rows (pitch kt+1) within 21 KB, so that three stages and the input tile leave room for two CTAs per SM.
@@ -326,7 +435,7 @@ size_t fs_smem_bytes(const FsGeometry &g, size_t slice_floats, int x_rows) {
 }
 
 cudaError_t launch_resample_fs(const FsParams &p_in, const FsGeometry &g, int x_rows, bool exact,
-                               cudaStream_t stream) {
+                               cudaStream_t stream, int n_groups) {
   if (p_in.n_out <= 0 || p_in.n_series <= 0)
     return cudaSuccess;
   FsParams p = p_in;
@@ -341,7 +450,8 @@ cudaError_t launch_resample_fs(const FsParams &p_in, const FsGeometry &g, int x_
                p.out_ss % 4 == 0 && p.out_fs % g.sv == 0)
                   ? 1
                   : 0;
-  const int grid = (p.n_out + g.outputs_per_cta - 1) / g.outputs_per_cta;
+  // (fused groups: n_out is the largest group's count; CTAs past a group's own count leave at once)
+  const dim3 grid((p.n_out + g.outputs_per_cta - 1) / g.outputs_per_cta, p.groups ? n_groups : 1);
 #define ESPB_FS(SV_, B_) \
   (exact ? launch_fs_t<SV_, B_, true>(p, smem, grid, stream) : launch_fs_t<SV_, B_, false>(p, smem, grid, stream))
   if (g.sv == 2 && g.b == 4)

@@ -299,6 +299,55 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// Planar input given as one pointer per (stream, channel) plane — the reference's resampleProcess signature
+// (`const float *const *inputs`, include/art_resampler.h:36-37): separately allocated channel buffers.  Same tiling
+// as the generic kernel (frames contiguous per plane: a warp reads 32 consecutive frames of one plane).
+__global__ void __launch_bounds__(256)
+    espb_transpose_ptr_kernel(const float *const *__restrict__ planes, int n_series, int n_in,
+                              float *__restrict__ xt, int64_t rows_cap, int row_first, int pad_rows) {
+  __shared__ float tile[TR_ROWS][SGN + 1];
+  const int g = blockIdx.x;
+  const int j0 = blockIdx.y * TR_ROWS;
+  const int tid = threadIdx.x;
+  const int total_rows = n_in + pad_rows;
+  for (int i = tid; i < SGN * TR_ROWS; i += 256) {
+    const int sl = i / TR_ROWS, t = i - sl * TR_ROWS;
+    const int q = g * SGN + sl, j = j0 + t;
+    float v = 0.0f;
+    if (q < n_series && j < n_in)
+      v = __ldg(planes[q] + j);
+    tile[t][sl] = v;
+  }
+  __syncthreads();
+  float4 *dst = reinterpret_cast<float4 *>(xt + ((int64_t) g * rows_cap + row_first + j0) * SGN);
+  for (int i = tid; i < TR_ROWS * (SGN / 4); i += 256) {
+    const int t = i / (SGN / 4), c4 = i - t * (SGN / 4);
+    if (j0 + t < total_rows)
+      dst[i] = make_float4(tile[t][c4 * 4], tile[t][c4 * 4 + 1], tile[t][c4 * 4 + 2], tile[t][c4 * 4 + 3]);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+    espb_untranspose_ptr_kernel(const float *__restrict__ tm, int64_t rows_cap, int row_first, int n_rows,
+                                float *const *__restrict__ planes, int n_series) {
+  __shared__ float tile[TR_ROWS][SGN + 1];
+  const int g = blockIdx.x;
+  const int j0 = blockIdx.y * TR_ROWS;
+  const int tid = threadIdx.x;
+  const float *src = tm + ((int64_t) g * rows_cap + row_first + j0) * SGN;
+  for (int i = tid; i < TR_ROWS * SGN; i += 256) {
+    const int t = i / SGN, sl = i - t * SGN;
+    tile[t][sl] = (j0 + t < n_rows) ? __ldg(src + i) : 0.0f;
+  }
+  __syncthreads();
+  for (int i = tid; i < SGN * TR_ROWS; i += 256) {
+    const int sl = i / TR_ROWS, t = i - sl * TR_ROWS;
+    const int q = g * SGN + sl, j = j0 + t;
+    if (q < n_series && j < n_rows)
+      planes[q][j] = tile[t][sl];
+  }
+}
+
 // ---------------------------------------------------------------------------------
 // Inverse stage: time-major tm[group][row][128] -> caller layout.  Same tiling as the transposing
 // stage: 128-bit loads along series, 128-bit stores along time.
@@ -760,6 +809,28 @@ cudaError_t launch_transpose(const float *in, int64_t in_ss, int64_t in_cs, int6
                                                     row_first, fast_rows, pad_rows);
     count_launch();
   }
+  return cudaGetLastError();
+}
+
+cudaError_t launch_transpose_ptrs(const float *const *planes_dev, int n_series, int n_in, float *xt, int64_t rows_cap,
+                                  int row_first, int pad_rows, cudaStream_t stream) {
+  const int n_groups = (n_series + SGN - 1) / SGN;
+  if (n_groups <= 0 || n_in + pad_rows <= 0)
+    return cudaSuccess;
+  dim3 grid(n_groups, (n_in + pad_rows + TR_ROWS - 1) / TR_ROWS);
+  espb_transpose_ptr_kernel<<<grid, 256, 0, stream>>>(planes_dev, n_series, n_in, xt, rows_cap, row_first, pad_rows);
+  count_launch();
+  return cudaGetLastError();
+}
+
+cudaError_t launch_untranspose_ptrs(const float *tm, int64_t rows_cap, int row_first, int n_rows,
+                                    float *const *planes_dev, int n_series, cudaStream_t stream) {
+  const int n_groups = (n_series + SGN - 1) / SGN;
+  if (n_groups <= 0 || n_rows <= 0)
+    return cudaSuccess;
+  dim3 grid(n_groups, (n_rows + TR_ROWS - 1) / TR_ROWS);
+  espb_untranspose_ptr_kernel<<<grid, 256, 0, stream>>>(tm, rows_cap, row_first, n_rows, planes_dev, n_series);
+  count_launch();
   return cudaGetLastError();
 }
 

@@ -20,7 +20,7 @@ __global__ void __launch_bounds__(256)
     head = n;
   const uint64_t n_vec = (n - head) / 4;
   const uint4 *v = reinterpret_cast<const uint4 *>(w + head);
-#pragma unroll 4
+#pragma unroll 8
   for (uint64_t i = tid; i < n_vec; i += stride) {
     const uint4 q = __ldg(v + i);
     acc += (unsigned long long) q.x + q.y + q.z + q.w;
@@ -32,8 +32,18 @@ __global__ void __launch_bounds__(256)
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1)
     acc += __shfl_xor_sync(0xffffffffu, acc, d);
+  // one atomic per CTA (one per warp was 19 k atomics on a single address: 60 % of the kernel's time)
+  __shared__ unsigned long long part[8];
   if ((threadIdx.x & 31) == 0)
-    atomicAdd(sum, acc);
+    part[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long t = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+      t += part[k];
+    atomicAdd(sum, t);
+  }
 }
 
 // 32 independent FFMA chains per thread, operands in registers, nothing else in the loop.

@@ -127,6 +127,12 @@ EspbResampleResult espb_resampleProcess(EspbResampleBatch *cxt, const float *in,
                                         int64_t in_channel_stride, int numInputFrames, float *out,
                                         int64_t out_stream_stride, int64_t out_channel_stride, int numOutputFrames,
                                         float ratio, void *stream);
+/* resampleProcess with the reference's own argument form (`const float *const *inputs`, `float *const *outputs`,
+ * include/art_resampler.h:36-37): one pointer per plane.  `inputs` / `outputs` are HOST arrays of
+ * num_streams * numChannels DEVICE pointers (plane q = stream q / numChannels, channel q % numChannels); the planes
+ * may be separately allocated buffers. */
+EspbResampleResult espb_resampleProcessPlanes(EspbResampleBatch *cxt, const float *const *inputs, int numInputFrames,
+                                              float *const *outputs, int numOutputFrames, float ratio, void *stream);
 /* general form */
 EspbResampleResult espb_resampleProcessLayout(EspbResampleBatch *cxt, const float *in, const EspbLayout *in_layout,
                                               int numInputFrames, float *out, const EspbLayout *out_layout,
@@ -150,6 +156,15 @@ EspbResampleGroups *espb_resampleGroupsInit(int num_groups, const int *streams_p
                                             int numFilters, float lowpassRatio, int flags);
 void espb_resampleGroupsFree(EspbResampleGroups *g);
 int espb_resampleGroupsCount(const EspbResampleGroups *g);
+/* 1 when the set runs in the fused form: every group the same number of streams and <= 32 series ("one clock per
+ * stream" and the like).  One compact staging buffer, schedule table and filter bank serve all groups, and a call is
+ * four device operations whatever the number of groups (upload, staging, schedule expansion, one resampler launch with
+ * a grid dimension over the groups).  espb_resampleGroupsContext then returns state-only contexts: the position calls
+ * (advance / position / state / required / expected) work per group, processing goes through the set.
+ * ESPB_GROUPS_FUSED=0 forces one full context per group. */
+int espb_resampleGroupsIsFused(const EspbResampleGroups *g);
+/* resampleReset (art_resampler.cpp:144-152) for one group */
+int espb_resampleGroupsReset(EspbResampleGroups *g, int group, void *stream);
 int espb_resampleGroupsFirstStream(const EspbResampleGroups *g, int group);
 /* the group's batch context, for resampleAdvancePosition / Reset / GetPosition / GetRequiredSamples / ... */
 EspbResampleBatch *espb_resampleGroupsContext(EspbResampleGroups *g, int group);

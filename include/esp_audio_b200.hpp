@@ -41,6 +41,12 @@ inline ResampleResult resampleProcess(Resample *cxt, const float *input, int64_t
   return espb_resampleProcess(cxt, input, inStreamStride, inChannelStride, numInputFrames, output, outStreamStride,
                               outChannelStride, numOutputFrames, ratio, stream);
 }
+// include/art_resampler.h:36-37 verbatim — one (device) pointer per plane, numStreams x numChannels of them
+inline ResampleResult resampleProcess(Resample *cxt, const float *const *inputs, int numInputFrames,
+                                      float *const *outputs, int numOutputFrames, float ratio,
+                                      void *stream = nullptr) {
+  return espb_resampleProcessPlanes(cxt, inputs, numInputFrames, outputs, numOutputFrames, ratio, stream);
+}
 inline ResampleResult resampleProcessInterleaved(Resample *cxt, const float *input, int64_t inStreamStride,
                                                  int numInputFrames, float *output, int64_t outStreamStride,
                                                  int numOutputFrames, float ratio, void *stream = nullptr) {

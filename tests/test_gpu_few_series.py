@@ -180,3 +180,181 @@ def test_wrapper_few_streams_bit_exact(oracle, cfg):
             assert bits_equal(out[s][:n], yo[:n]), (cfg, k, s)
             assert int(res["clipped_per_stream"][s]) == ro["clipped_samples"]
     r.free()
+
+
+@pytest.mark.parametrize("shape", [(40, 1, 2), (9, 4, 3), (5, 2, 1)])   # groups, streams per group, channels
+@pytest.mark.parametrize("mode", ["exact", "fast"])
+def test_fused_clock_groups_per_stream_ratios(oracle, shape, mode, monkeypatch):
+    """SURVEY 8f N1 as written: every stream (or small group of streams) on its own clock inside one set — the ratio is
+    per group AND per call, chunk sizes differ per group, state stays on the device (art_resampler.cpp:57-62,167,208).
+    The fused form (one staging / schedule / resampler launch for all groups) against one reference-style context per
+    stream fed the same calls: bit-exact in exact mode, <= 1e-6 in fast mode; identical to the one-context-per-group
+    form; per-group reset."""
+    n_groups, spg, ch = shape
+    taps, filters, flags = 64, 128, 3
+    ns = n_groups * spg
+    rng = np.random.default_rng(7)
+    base = [f32(rng.choice([48000 / 44100, 44100 / 48000, 2.0, 0.5, 1.0, 1.37])) for _ in range(n_groups)]
+    total = 3000
+    x = np.stack([noise(total, ch, stream=900 + s, amp=0.7) for s in range(ns)])
+    calls = []
+    for call in range(7):
+        n_in = [int(rng.integers(0, 500)) for _ in range(n_groups)]
+        n_out = [int(rng.integers(0, 900)) for _ in range(n_groups)]
+        ratios = [f32(base[k] * f32(1.0 + 3e-4 * np.sin(call + k))) for k in range(n_groups)]
+        calls.append((n_in, n_out, ratios))
+
+    def run(fused):
+        monkeypatch.setenv("ESPB_GROUPS_FUSED", "1" if fused else "0")
+        g = espb.ResampleGroups([spg] * n_groups, ch, taps, filters, 1.0, flags,
+                                mode=espb.MODE_EXACT if mode == "exact" else espb.MODE_FAST)
+        assert g.is_fused() == fused
+        for k in range(n_groups):
+            g.advance(k, taps / 2)
+        pos = [0] * n_groups
+        outs, states = [], []
+        for n_in, n_out, ratios in calls:
+            n_in = [min(n_in[k], total - pos[k]) for k in range(n_groups)]
+            row = max(max(n_in), 1) * ch
+            xin = np.zeros((ns, row), f32)
+            for s in range(ns):
+                k = s // spg
+                xin[s, : n_in[k] * ch] = x[s, pos[k] * ch:(pos[k] + n_in[k]) * ch]
+            y, res = g.process_interleaved(xin, n_in, n_out, ratios)
+            outs.append((xin, n_in, y, res))
+            for k in range(n_groups):
+                pos[k] += res[k][0]
+            states.append([g.state(k) for k in range(n_groups)])
+        # reset of one group: its next call starts from silence and the initial position again
+        g.reset(0)
+        g.advance(0, taps / 2)
+        n_in = [200] * n_groups
+        xin = np.ascontiguousarray(x[:, : 200 * ch])
+        y, res = g.process_interleaved(xin, n_in, [400] * n_groups, [base[k] for k in range(n_groups)])
+        g.free()
+        return outs, states, (y, res)
+
+    fused, st_f, reset_f = run(True)
+    plain, st_p, reset_p = run(False)
+    orc = [oracle.resampler(ch, taps, filters, 1.0, flags) for _ in range(ns)]
+    for o in orc:
+        o.advance(taps / 2)
+    worst = 0.0
+    for c, ((xin, n_in, y, res), (_, _, yp, resp)) in enumerate(zip(fused, plain)):
+        assert res == resp
+        assert bits_equal(y, yp), c                      # fused == one context per group
+        n_out, ratios = calls[c][1], calls[c][2]
+        for s in range(ns):
+            k = s // spg
+            yo, uo, go = orc[s].process_interleaved(xin[s, : n_in[k] * ch], n_out[k], ratios[k], n_in=n_in[k])
+            assert res[k] == (uo, go), (c, s)
+            got = y[s, : go * ch]
+            if mode == "exact":
+                assert bits_equal(got, yo), (c, s)
+            elif go:
+                worst = max(worst, float(np.max(np.abs(got.astype(np.float64) - yo))))
+        assert st_f[c] == st_p[c] == [orc[k * spg].state() for k in range(n_groups)]
+    assert worst <= TOL
+    # after the reset: group 0 equals a fresh context, the others continue
+    y, res = reset_f
+    assert bits_equal(y, reset_p[0]) and res == reset_p[1]
+    fresh = oracle.resampler(ch, taps, filters, 1.0, flags)
+    fresh.advance(taps / 2)
+    yo, uo, go = fresh.process_interleaved(x[0, : 200 * ch], 400, base[0], n_in=200)
+    assert res[0] == (uo, go)
+    if mode == "exact":
+        assert bits_equal(y[0, : go * ch], yo)
+
+
+@pytest.mark.parametrize("ns,ch", [(1, 2), (3, 2), (70, 2), (2, 5)])
+def test_planar_pointer_tables(oracle, ns, ch):
+    """resampleProcess with the reference's own argument form: one separately allocated buffer per (stream, channel)
+    plane (include/art_resampler.h:36-37, art_resampler.cpp:167-202).  Bit-exact with the oracle's planar call, over
+    two calls (state carried), through the few-series kernel (<= 32 series) and the standard one (140 series)."""
+    taps, filters, flags = 64, 32, 3
+    ratio = f32(48000) / f32(44100)
+    n_in = 1500
+    x = [noise(n_in, 1, stream=1200 + q, amp=0.8) for q in range(ns * ch)]
+    b = espb.ResampleBatch(ns, ch, taps, filters, 1.0, flags, mode=espb.MODE_EXACT)
+    b.advance(taps / 2)
+    os_ = [oracle.resampler(ch, taps, filters, 1.0, flags) for _ in range(ns)]
+    for o in os_:
+        o.advance(taps / 2)
+    for a, e in ((0, 700), (700, n_in)):
+        ys, used, gen = b.process_planes([p[a:e] for p in x], 1000, ratio)
+        for s in range(ns):
+            xi = np.stack([x[s * ch + c][a:e] for c in range(ch)], axis=1).reshape(-1)   # interleave for the oracle
+            yo, uo, go = os_[s].process_interleaved(xi, 1000, ratio, n_in=e - a)
+            assert (used, gen) == (uo, go)
+            for c in range(ch):
+                assert bits_equal(ys[s * ch + c], yo.reshape(-1, ch)[:go, c]), (s, c)
+    b.free()
+
+
+def test_cpp_shim_runs_on_the_gpu(oracle, tmp_path):
+    """include/esp_audio_b200.hpp — the reference's names over the C ABI — compiled into a small C++ program that
+    resamples one stereo stream on the device (resampleInit / AdvancePosition / ProcessInterleaved / GetPosition) and
+    filters it (biquad_init / apply_buffer); its output file must equal the oracle's bytes."""
+    import os
+    import shutil
+    import subprocess
+    if not shutil.which("g++"):
+        pytest.skip("no g++")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    n_in, cap = 4000, 4500
+    x = noise(n_in, 2, stream=77, amp=0.6)
+    x.tofile(tmp_path / "in.f32")
+    src = tmp_path / "run.cpp"
+    src.write_text(r'''
+#include <cstdio>
+#include <vector>
+#include "esp_audio_b200.hpp"
+namespace a = esp_audio_libs_b200::art_resampler;
+int main(int argc, char **argv) {
+  const int n_in = 4000, cap = 4500;
+  std::vector<float> x(n_in * 2), y(cap * 2, 0.0f);
+  FILE *f = fopen(argv[1], "rb");
+  if (!f || fread(x.data(), 4, x.size(), f) != x.size()) return 2;
+  fclose(f);
+  espb_set_device(0);
+  a::Resample *r = a::resampleInit(1, 2, 256, 256, 1.0f, a::SUBSAMPLE_INTERPOLATE_ | a::BLACKMAN_HARRIS_);
+  if (!r) return 3;
+  espb_resampleSetMode(r, ESPB_MODE_EXACT);
+  a::resampleAdvancePosition(r, 128.0f);
+  float *din = (float *) espb_malloc(x.size() * 4), *dout = (float *) espb_malloc(y.size() * 4);
+  espb_memcpy_h2d(din, x.data(), x.size() * 4, nullptr);
+  espb_memset(dout, 0, y.size() * 4, nullptr);
+  a::ResampleResult res = a::resampleProcessInterleaved(r, din, n_in * 2, n_in, dout, cap * 2, cap, 48000.0f / 44100.0f);
+  a::BiquadCoefficients c;
+  a::biquad_lowpass(&c, 0.2274);
+  a::Biquad *b = a::biquad_init(2, 2, &c, 1.0f);
+  if (!b || a::biquad_apply_buffer(b, dout, cap * 2, 2, (int) res.output_generated) != 0) return 4;
+  espb_memcpy_d2h(y.data(), dout, y.size() * 4, nullptr);
+  espb_device_sync();
+  f = fopen(argv[2], "wb");
+  fwrite(y.data(), 4, res.output_generated * 2, f);
+  fclose(f);
+  printf("%u %u %.9g\n", res.input_used, res.output_generated, a::resampleGetPosition(r));
+  a::biquad_free(b);
+  a::resampleFree(r);
+  return 0;
+}
+''')
+    exe = tmp_path / "run"
+    libdir = os.path.dirname(espb.library_path())
+    subprocess.run(["g++", "-std=c++11", "-I", os.path.join(root, "include"), str(src), "-o", str(exe), "-L", libdir,
+                    "-lesp_audio_b200", f"-Wl,-rpath,{libdir}"], check=True)
+    p = subprocess.run([str(exe), str(tmp_path / "in.f32"), str(tmp_path / "out.f32")], capture_output=True, text=True)
+    assert p.returncode == 0, p.stderr
+    used, gen, position = p.stdout.split()
+    o = oracle.resampler(2, 256, 256, 1.0, 3)
+    o.advance(128.0)
+    yo, uo, go = o.process_interleaved(x, cap, f32(48000) / f32(44100))
+    assert (int(used), int(gen)) == (uo, go) and f32(float(position)) == f32(o.position())
+    yo = np.ascontiguousarray(yo[: go * 2])
+    c = oracle.biquad_lowpass(0.2274)
+    for ch in range(2):
+        for _ in range(2):
+            oracle.biquad(c, 1.0).apply_buffer(yo[ch:], 2, n=go)
+    got = np.fromfile(tmp_path / "out.f32", np.float32)
+    assert bits_equal(got, yo)

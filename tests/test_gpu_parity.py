@@ -818,3 +818,40 @@ def test_non_interpolating_kernel(oracle, flags, lowpass, monkeypatch):
                              for a, n, cap in ((0, 1000, 2000), (1000, 7, 30), (1007, 1993, 4000))])
         assert bits_equal(results[("dedicated", espb.MODE_EXACT)][s], yo), s
         assert np.max(np.abs(results[("dedicated", espb.MODE_FAST)][s].astype(np.float64) - yo)) <= TOL
+
+
+@pytest.mark.parametrize("ns", [3, 150])
+def test_growing_calls_without_synchronisation(oracle, ns):
+    """Calls of growing size enqueued back to back on a non-blocking stream with no host synchronisation in between:
+    the staging buffers are re-allocated (and the carried frames moved) while earlier calls may still be running.
+    Everything must come out as from one reference context per stream (the re-allocation waits for the device)."""
+    L = espb.lib()
+    ch, taps = 2, 64
+    ratio = f32(48000) / f32(44100)
+    sizes = [100, 300, 900, 2700, 8100]
+    total = sum(sizes)
+    x = np.stack([noise(total, ch, stream=700 + s, amp=0.8) for s in range(ns)])
+    stream = L.espb_stream_create()
+    b = espb.ResampleBatch(ns, ch, taps, 64, 1.0, 3, mode=espb.MODE_EXACT)
+    b.advance(taps / 2)
+    d_in = espb.DeviceBuffer.from_numpy(x)
+    caps = [int(n * float(ratio)) + 8 for n in sizes]
+    d_outs = [espb.DeviceBuffer(ns * c * ch * 4) for c in caps]
+    results, pos = [], 0
+    for n, cap, d_out in zip(sizes, caps, d_outs):
+        results.append(b.process_interleaved_dev(d_in.ptr + pos * ch * 4, total * ch, n, d_out.ptr, cap * ch, cap,
+                                                 ratio, stream))
+        pos += n
+    espb.capi._check(L.espb_stream_sync(stream), "sync")
+    for s in (0, ns - 1):
+        o = oracle.resampler(ch, taps, 64, 1.0, 3)
+        o.advance(taps / 2)
+        pos = 0
+        for n, cap, d_out, (used, gen) in zip(sizes, caps, d_outs, results):
+            yo, uo, go = o.process_interleaved(x[s, pos * ch:(pos + n) * ch], cap, ratio)
+            assert (used, gen) == (uo, go)
+            got = d_out.download(f32).reshape(ns, cap * ch)[s, : go * ch]
+            assert bits_equal(got, yo), (s, n)
+            pos += n
+    b.free()
+    L.espb_stream_destroy(stream)
