@@ -1368,6 +1368,7 @@ struct EspbBiquadBatch {
   // 0 = one sequential run per series, > 0 = blocks of that many rows.  Exact either way: the hand-over between
   // blocks is verified bit for bit on the device and repaired where the warm-up did not converge.
   int block_rows = -1, warm_rows = 1024;
+  bool one_pass = true;  // ESPB_BIQUAD_ONEPASS=0: always through time-major scratch (three passes)
   DevBuf blk_state;                      // (start, end) state of every block, for the verify kernel
   DevBuf mismatch_dev;                   // [1] blocks repaired so far in the call being enqueued
   unsigned int *mismatch_host = nullptr; // pinned copy of the previous call's count
@@ -1447,6 +1448,7 @@ EspbBiquadBatch *espb_biquad_init(int num_series, int num_sections, const EspbBi
   f->params.b1 = coeffs->b1;
   f->params.b2 = coeffs->b2;
   f->params.first_order = (coeffs->a2 == 0.0f && coeffs->b2 == 0.0f);
+  f->one_pass = env_long("ESPB_BIQUAD_ONEPASS", 1) != 0;
   const size_t bytes = (size_t) num_series * num_sections * 4 * sizeof(float);
   cudaError_t e = f->state.reserve(bytes);
   if (e == cudaSuccess)
@@ -1490,7 +1492,20 @@ int espb_biquad_apply_buffer(EspbBiquadBatch *f, float *buf, const EspbLayout *l
     return fail(ESPB_ERR_ARG, "biquad_apply_buffer: bad arguments");
   if (num_samples <= 0)
     return ESPB_OK;
-  // caller layout -> time-major scratch -> filter in place -> back; all three are full-bandwidth passes
+  const int blocks = f->blocks_for(num_samples);
+  if (blocks == 0 && f->one_pass) {
+    // many series (or a short call): ONE pass on the caller's layout — 8 bytes of traffic per sample
+    cudaError_t e = launch_biquad_cl(buf, layout->stream_stride, layout->channel_stride, layout->frame_stride, channels,
+                                     f->num_series, num_samples, f->num_sections, f->params, f->state.as<float>(),
+                                     as_stream(stream));
+    if (e == cudaSuccess)
+      return ESPB_OK;
+    if (e != cudaErrorNotSupported)
+      return cuda_fail(e, "biquad kernel");
+    cudaGetLastError();
+  }
+  // few series and a long call (time blocks), or a layout the one-pass kernel does not take:
+  // caller layout -> time-major scratch -> filter -> back
   const int n_groups = (f->num_series + kSeriesPerRow - 1) / kSeriesPerRow;
   if (num_samples > f->tm_rows) {
     CU_TRY(f->tm.reserve((size_t) n_groups * num_samples * kSeriesPerRow * sizeof(float)), "biquad scratch");
@@ -1501,7 +1516,6 @@ int espb_biquad_apply_buffer(EspbBiquadBatch *f, float *buf, const EspbLayout *l
                           f->num_series, num_samples, f->tm.as<float>(), f->tm_rows, 0, 0, s),
          "transpose kernel");
   float *filtered = f->tm.as<float>();
-  const int blocks = f->blocks_for(num_samples);
   if (blocks > 0) {
     if (f->tm_rows > f->tm2_rows) {
       CU_TRY(f->tm2.reserve((size_t) n_groups * f->tm_rows * kSeriesPerRow * sizeof(float)), "biquad scratch");

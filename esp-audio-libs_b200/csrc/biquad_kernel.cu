@@ -280,6 +280,180 @@ __global__ void __launch_bounds__(SGN)
     atomicAdd(mismatches, bad);
 }
 
+// ---------------------------------------------------------------------------------
+// One pass on the CALLER'S layout (the stand-alone biquad_apply_buffer): no trip through time-major scratch.
+// A CTA owns 128 series.  Chunks of 32 frames come in by 4-byte cp.async in the caller's memory order (consecutive
+// threads read consecutive addresses: 32 x channels floats per stream when interleaved, 32 frames per plane when
+// planar) and land series-major in a shared-memory tile of pitch 33, so the thread that owns series q walks its 32
+// frames conflict-free; the filtered tile goes back the way it came.  CL_STAGES chunks are in flight per CTA, which
+// hides the load latency behind the (latency-bound) recurrence.  8 algorithmic bytes per sample, in place.
+// ---------------------------------------------------------------------------------
+constexpr int CL_ROWS = 32, CL_STAGES = 4;
+// tile pitch: 33 floats (conflict-free columns) with 4-byte copies; 36 (16-byte aligned rows, 4-way conflicts on the
+// cheap side) when frames are contiguous and aligned, so that the copies are 16 bytes wide
+__host__ __device__ constexpr int cl_pitch(bool vec) { return vec ? 36 : 33; }
+
+template <int NSEC, bool FIRST_ORDER, bool VEC>
+__global__ void __launch_bounds__(SGN)
+    espb_biquad_cl_kernel(float *buf, int64_t ss, int64_t cs, int64_t fs, int channels, int lu, int n_series,
+                          int n_frames, BiquadParams c, float *__restrict__ state) {
+  constexpr int CL_PITCH = cl_pitch(VEC);
+  extern __shared__ __align__(16) unsigned char cl_smem[];
+  float (*tile)[SGN * CL_PITCH] = reinterpret_cast<float (*)[SGN * CL_PITCH]>(cl_smem);  // [CL_STAGES][128 x pitch]
+  int64_t *base_tab = reinterpret_cast<int64_t *>(cl_smem + sizeof(float) * CL_STAGES * SGN * CL_PITCH);  // [128]
+  const int tid = threadIdx.x;
+  const int q0 = blockIdx.x * SGN;
+  const int q = q0 + tid;
+  const int n_chunks = (n_frames + CL_ROWS - 1) / CL_ROWS;
+  // where frame 0 of every series of this CTA lies (-1: no such series); frame j is j * fs further
+  {
+    const int st = q / channels, ch = q - st * channels;
+    base_tab[tid] = q < n_series ? (int64_t) st * ss + (int64_t) ch * cs : (int64_t) -1;
+  }
+  __syncthreads();
+  // Memory-order enumeration of a chunk: a unit (a stream when interleaved, a plane when planar) holds 2^lu series;
+  // element e of a unit's run of 32 << lu floats is frame e >> lu of its series e & (2^lu - 1).  Consecutive threads
+  // touch consecutive addresses; everything is shifts.
+  const int run_mask = (CL_ROWS << lu) - 1, unit_mask = (1 << lu) - 1, run_shift = 5 + lu;
+  const int unit_pitch = (CL_ROWS << lu) + 4;  // VEC tile: [unit][frame][series of the unit] + 4 floats of padding
+  auto load_chunk = [&](int k) {
+    float *t = tile[k % CL_STAGES];
+    const int j0 = k * CL_ROWS;
+    if (VEC && j0 + CL_ROWS <= n_frames) {
+      // 16-byte copies: a unit's 32 << lu floats of this chunk are contiguous and aligned in memory and stay in
+      // memory order in the tile (unit pitch (32 << lu) + 4)
+#pragma unroll
+      for (int i = tid; i < SGN * (CL_ROWS / 4); i += SGN) {
+        const int u = i >> (3 + lu), v4 = (i & ((8 << lu) - 1)) * 4;
+        const int64_t base = base_tab[u << lu];
+        if (base >= 0)
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem_u32(t + u * unit_pitch + v4)),
+                       "l"(buf + base + (int64_t) j0 * fs + v4)
+                       : "memory");
+      }
+    } else {
+#pragma unroll 4
+      for (int i = tid; i < SGN * CL_ROWS; i += SGN) {
+        const int e = i & run_mask;
+        const int jj = e >> lu, sl = ((i >> run_shift) << lu) + (e & unit_mask);
+        const int64_t base = base_tab[sl];
+        if (base >= 0 && j0 + jj < n_frames)
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(smem_u32(t + sl * CL_PITCH + jj)),
+                       "l"(buf + base + (int64_t) (j0 + jj) * fs)
+                       : "memory");
+      }
+    }
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
+  };
+  Section sec[NSEC];
+  if (q < n_series) {
+#pragma unroll
+    for (int k = 0; k < NSEC; ++k) {
+      const float4 v = *reinterpret_cast<const float4 *>(state + ((int64_t) q * NSEC + k) * 4);
+      sec[k].in_d1 = v.x, sec[k].in_d2 = v.y, sec[k].out_d1 = v.z, sec[k].out_d2 = v.w;
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < NSEC; ++k)
+      sec[k].in_d1 = sec[k].in_d2 = sec[k].out_d1 = sec[k].out_d2 = 0.0f;
+  }
+  for (int k = 0; k < CL_STAGES - 1; ++k) {
+    if (k < n_chunks)
+      load_chunk(k);
+    else
+      asm volatile("cp.async.commit_group;\n" ::: "memory");
+  }
+  for (int k = 0; k < n_chunks; ++k) {
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(CL_STAGES - 2) : "memory");
+    __syncthreads();  // chunk k has landed for every thread; the stage refilled below was stored before this barrier
+    if (k + CL_STAGES - 1 < n_chunks)
+      load_chunk(k + CL_STAGES - 1);
+    else
+      asm volatile("cp.async.commit_group;\n" ::: "memory");
+    float *t = tile[k % CL_STAGES];
+    const int j0 = k * CL_ROWS;
+    const int rows = j0 + CL_ROWS <= n_frames ? CL_ROWS : n_frames - j0;
+    // this thread's series: column tid of the series-major tile, or (unit tid >> lu, series tid & mask) of the VEC tile
+    const bool vec_tile = VEC && rows == CL_ROWS;
+    float *mine = vec_tile ? t + (tid >> lu) * unit_pitch + (tid & unit_mask) : t + tid * CL_PITCH;
+    const int rstep = vec_tile ? (1 << lu) : 1;
+    if (rows == CL_ROWS) {
+#pragma unroll 8
+      for (int r = 0; r < CL_ROWS; ++r) {
+        float v = mine[r * rstep];
+#pragma unroll
+        for (int s2 = 0; s2 < NSEC; ++s2)
+          v = section_step<FIRST_ORDER>(sec[s2], v, c);
+        mine[r * rstep] = v;
+      }
+    } else {
+      for (int r = 0; r < rows; ++r) {
+        float v = mine[r];
+#pragma unroll
+        for (int s2 = 0; s2 < NSEC; ++s2)
+          v = section_step<FIRST_ORDER>(sec[s2], v, c);
+        mine[r] = v;
+      }
+    }
+    __syncthreads();
+    if (VEC && rows == CL_ROWS) {
+#pragma unroll
+      for (int i = tid; i < SGN * (CL_ROWS / 4); i += SGN) {
+        const int u = i >> (3 + lu), v4 = (i & ((8 << lu) - 1)) * 4;
+        const int64_t base = base_tab[u << lu];
+        if (base >= 0)
+          *reinterpret_cast<float4 *>(buf + base + (int64_t) j0 * fs + v4) =
+              *reinterpret_cast<const float4 *>(t + u * unit_pitch + v4);
+      }
+    } else {
+#pragma unroll 4
+      for (int i = tid; i < SGN * CL_ROWS; i += SGN) {
+        const int e = i & run_mask;
+        const int jj = e >> lu, sl = ((i >> run_shift) << lu) + (e & unit_mask);
+        const int64_t base = base_tab[sl];
+        if (base >= 0 && j0 + jj < n_frames)
+          buf[base + (int64_t) (j0 + jj) * fs] = t[sl * CL_PITCH + jj];
+      }
+    }
+  }
+  asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+  if (q < n_series) {
+#pragma unroll
+    for (int k = 0; k < NSEC; ++k)
+      *reinterpret_cast<float4 *>(state + ((int64_t) q * NSEC + k) * 4) =
+          make_float4(sec[k].in_d1, sec[k].in_d2, sec[k].out_d1, sec[k].out_d2);
+  }
+}
+
+template <int NSEC, bool VEC>
+cudaError_t launch_cl(float *buf, int64_t ss, int64_t cs, int64_t fs, int channels, int lu, int n_series,
+                      int n_frames, const BiquadParams &c, float *state, cudaStream_t stream) {
+  const int grid = (n_series + SGN - 1) / SGN;
+  const size_t smem = sizeof(float) * CL_STAGES * SGN * cl_pitch(VEC) + SGN * sizeof(int64_t);
+  static PerDeviceOnce once;
+  if (once.first()) {
+    cudaError_t e = cudaSuccess;
+    const void *fns[2] = {reinterpret_cast<const void *>(espb_biquad_cl_kernel<NSEC, true, VEC>),
+                          reinterpret_cast<const void *>(espb_biquad_cl_kernel<NSEC, false, VEC>)};
+    for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
+      e = cudaFuncSetAttribute(fns[i], cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+      if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(fns[i], cudaFuncAttributePreferredSharedMemoryCarveout,
+                                 (int) cudaSharedmemCarveoutMaxShared);
+    }
+    if (e != cudaSuccess)
+      return e;
+  }
+  if (c.first_order)
+    espb_biquad_cl_kernel<NSEC, true, VEC><<<grid, SGN, smem, stream>>>(buf, ss, cs, fs, channels, lu, n_series,
+                                                                     n_frames, c, state);
+  else
+    espb_biquad_cl_kernel<NSEC, false, VEC><<<grid, SGN, smem, stream>>>(buf, ss, cs, fs, channels, lu, n_series,
+                                                                      n_frames, c, state);
+  count_launch();
+  return cudaGetLastError();
+}
+
 template <int NSEC>
 cudaError_t launch_tm(const float *src, float *dst, int64_t rows_cap, int row_first, int n_rows, int n_series,
                       const BiquadParams &c, float *state, int block_rows, int warm_rows, float *blk_state,
@@ -319,6 +493,40 @@ cudaError_t launch_tm(const float *src, float *dst, int64_t rows_cap, int row_fi
 }
 
 }  // namespace
+
+// One-pass filter on the caller's layout.  Returns cudaErrorNotSupported when the layout is neither interleaved with
+// a channel count that divides 128 nor frame-contiguous (the caller then takes the time-major route).
+cudaError_t launch_biquad_cl(float *buf, int64_t ss, int64_t cs, int64_t fs, int channels, int n_series, int n_frames,
+                             int n_sections, BiquadParams c, float *state, cudaStream_t stream) {
+  if (n_series <= 0 || n_frames <= 0)
+    return cudaSuccess;
+  int unit_series = -1;  // log2 of the series per contiguous run
+  if (fs == 1)
+    unit_series = 0;  // planar (or mono): a plane's frames are contiguous
+  else if (cs == 1 && fs == channels && (channels == 2 || channels == 4 || channels == 8))
+    unit_series = channels == 2 ? 1 : (channels == 4 ? 2 : 3);  // interleaved: frames x channels of a stream are
+  else
+    return cudaErrorNotSupported;
+  // 16-byte copies: every unit's frame 0 on a 16-byte boundary (a unit is a stream when interleaved, a plane else)
+  const bool vec = (uintptr_t) buf % 16 == 0 && ss % 4 == 0 &&
+                   (unit_series > 0 || cs % 4 == 0 || channels == 1);
+  switch (n_sections) {
+    case 1:
+      return vec ? launch_cl<1, true>(buf, ss, cs, fs, channels, unit_series, n_series, n_frames, c, state, stream)
+                 : launch_cl<1, false>(buf, ss, cs, fs, channels, unit_series, n_series, n_frames, c, state, stream);
+    case 2:
+      return vec ? launch_cl<2, true>(buf, ss, cs, fs, channels, unit_series, n_series, n_frames, c, state, stream)
+                 : launch_cl<2, false>(buf, ss, cs, fs, channels, unit_series, n_series, n_frames, c, state, stream);
+    case 3:
+      return vec ? launch_cl<3, true>(buf, ss, cs, fs, channels, unit_series, n_series, n_frames, c, state, stream)
+                 : launch_cl<3, false>(buf, ss, cs, fs, channels, unit_series, n_series, n_frames, c, state, stream);
+    case 4:
+      return vec ? launch_cl<4, true>(buf, ss, cs, fs, channels, unit_series, n_series, n_frames, c, state, stream)
+                 : launch_cl<4, false>(buf, ss, cs, fs, channels, unit_series, n_series, n_frames, c, state, stream);
+    default:
+      return cudaErrorInvalidValue;
+  }
+}
 
 size_t biquad_block_state_floats(int n_series, int n_sections, int n_rows, int block_rows) {
   if (block_rows <= 0 || block_rows >= n_rows)

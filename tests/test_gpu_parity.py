@@ -493,23 +493,33 @@ def _le_to_int(bytes_, nb):
 
 
 # ---------------------------------------------------------------- full-size properties (BASELINE configs[1])
-def test_full_size_batch_properties(oracle):
+@pytest.mark.parametrize("mode", ["fast", "exact"])
+def test_full_size_batch_properties(oracle, mode):
     """4096 stereo streams, 256 taps, 44.1 -> 48 kHz (0.25 s each to keep the test short): every stream
     with the same input gives the same output (a checksum of checksums), sampled streams match the
-    oracle, and the device checksum equals the host's."""
+    oracle (bit for bit in exact mode), and the device checksum equals the host's.  Run three times on fresh
+    contexts: the checksum must not move (the kernel's stage hand-over — a relaxed shared-memory counter and
+    mbarriers, resample_kernel.cu — would show up here as run-to-run differences; compute-sanitizer is closed on
+    this pool, see profiles/r02_sanitizer_note.md)."""
     ns, ch, taps, n_in = 4096, 2, 256, 11025
+    exact = mode == "exact"
     ratio = f32(48000) / f32(44100)
     base = [noise(n_in, ch, stream=s, amp=0.5) for s in range(8)]
     x = np.stack([base[s % 8] for s in range(ns)])
     cap = int(n_in * float(ratio)) + 16
-    b = espb.ResampleBatch(ns, ch, taps, 256, 1.0, 3)
-    b.advance(taps / 2)
     d_in = espb.DeviceBuffer.from_numpy(x)
     d_out = espb.DeviceBuffer(ns * cap * ch * 4)
-    d_out.zero()
-    used, gen = b.process_interleaved_dev(d_in.ptr, n_in * ch, n_in, d_out.ptr, cap * ch, cap, ratio)
+    sums_seen = set()
+    for _run in range(3):
+        b = espb.ResampleBatch(ns, ch, taps, 256, 1.0, 3, mode=espb.MODE_EXACT if exact else espb.MODE_FAST)
+        b.advance(taps / 2)
+        d_out.zero()
+        used, gen = b.process_interleaved_dev(d_in.ptr, n_in * ch, n_in, d_out.ptr, cap * ch, cap, ratio)
+        dev_sum = espb.checksum_u32(d_out.ptr, ns * cap * ch)
+        sums_seen.add(dev_sum)
+        b.free()
+    assert len(sums_seen) == 1
     y = d_out.download(f32).reshape(ns, cap * ch)
-    dev_sum = espb.checksum_u32(d_out.ptr, ns * cap * ch)
     assert dev_sum == int(y.view(np.uint32).astype(np.uint64).sum() & np.uint64(0xFFFFFFFFFFFFFFFF))
     o = oracle.resampler(ch, taps, 256, 1.0, 3)
     o.advance(taps / 2)
@@ -520,7 +530,10 @@ def test_full_size_batch_properties(oracle):
         oo = oracle.resampler(ch, taps, 256, 1.0, 3)
         oo.advance(taps / 2)
         yo, _, _ = oo.process_interleaved(base[s], cap, ratio)
-        assert np.max(np.abs(y[s, : gen * ch].astype(np.float64) - yo)) <= TOL
+        if exact:
+            assert bits_equal(y[s, : gen * ch], yo[: gen * ch]) and bits_equal(y[ns - 8 + s, : gen * ch], yo[: gen * ch])
+        else:
+            assert np.max(np.abs(y[s, : gen * ch].astype(np.float64) - yo)) <= TOL
     assert np.all(y[:, gen * ch:] == 0)  # nothing written past the generated frames
 
 
