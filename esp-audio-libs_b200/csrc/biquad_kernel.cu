@@ -282,21 +282,26 @@ __global__ void __launch_bounds__(SGN)
 
 // ---------------------------------------------------------------------------------
 // One pass on the CALLER'S layout (the stand-alone biquad_apply_buffer): no trip through time-major scratch.
-// A CTA owns 128 series.  Chunks of 32 frames come in by 4-byte cp.async in the caller's memory order (consecutive
-// threads read consecutive addresses: 32 x channels floats per stream when interleaved, 32 frames per plane when
-// planar) and land series-major in a shared-memory tile of pitch 33, so the thread that owns series q walks its 32
-// frames conflict-free; the filtered tile goes back the way it came.  CL_STAGES chunks are in flight per CTA, which
-// hides the load latency behind the (latency-bound) recurrence.  8 algorithmic bytes per sample, in place.
+// A CTA owns 128 series.  Chunks of 64 frames come in by 16-byte cp.async in the caller's memory order — a "unit" is
+// what is contiguous there: the 64 x channels floats of a stream when interleaved, 64 frames of a plane when planar —
+// and stay in that order in the shared-memory tile (unit pitch + 4 floats); the thread that owns a series walks its
+// column of the tile (stride = series per unit, a compile-time constant), and the filtered tile goes back by 128-bit
+// stores.  CL_STAGES chunks are in flight per CTA.  8 algorithmic bytes per sample, in place.  The recurrence is the
+// floor: ~40 cycles per frame (two sections) for every series, however many there are.  Unaligned rows and the last
+// partial chunk take 4-byte copies into a series-major tile of pitch 65.
 // ---------------------------------------------------------------------------------
-constexpr int CL_ROWS = 32, CL_STAGES = 4;
-// tile pitch: 33 floats (conflict-free columns) with 4-byte copies; 36 (16-byte aligned rows, 4-way conflicts on the
-// cheap side) when frames are contiguous and aligned, so that the copies are 16 bytes wide
-__host__ __device__ constexpr int cl_pitch(bool vec) { return vec ? 36 : 33; }
+constexpr int CL_ROWS = 64, CL_LOG_ROWS = 6, CL_STAGES = 3;  // 64-frame chunks: half the barriers per frame of 32
+__host__ __device__ constexpr int cl_pitch(bool vec) { return vec ? CL_ROWS + 4 : CL_ROWS + 1; }
 
-template <int NSEC, bool FIRST_ORDER, bool VEC>
+// LUT >= 0: log2(series per unit) known at compile time (the 16-byte form: the column stride of the filter loop must
+// be a constant, or the compiler cannot move a row's load above the previous row's store and the recurrence waits
+// for shared memory every row — measured 1.7x slower); LUT < 0: the 4-byte form, taken from the argument.
+template <int NSEC, bool FIRST_ORDER, int LUT>
 __global__ void __launch_bounds__(SGN)
-    espb_biquad_cl_kernel(float *buf, int64_t ss, int64_t cs, int64_t fs, int channels, int lu, int n_series,
+    espb_biquad_cl_kernel(float *buf, int64_t ss, int64_t cs, int64_t fs, int channels, int lu_arg, int n_series,
                           int n_frames, BiquadParams c, float *__restrict__ state) {
+  constexpr bool VEC = LUT >= 0;
+  const int lu = VEC ? LUT : lu_arg;
   constexpr int CL_PITCH = cl_pitch(VEC);
   extern __shared__ __align__(16) unsigned char cl_smem[];
   float (*tile)[SGN * CL_PITCH] = reinterpret_cast<float (*)[SGN * CL_PITCH]>(cl_smem);  // [CL_STAGES][128 x pitch]
@@ -314,7 +319,7 @@ __global__ void __launch_bounds__(SGN)
   // Memory-order enumeration of a chunk: a unit (a stream when interleaved, a plane when planar) holds 2^lu series;
   // element e of a unit's run of 32 << lu floats is frame e >> lu of its series e & (2^lu - 1).  Consecutive threads
   // touch consecutive addresses; everything is shifts.
-  const int run_mask = (CL_ROWS << lu) - 1, unit_mask = (1 << lu) - 1, run_shift = 5 + lu;
+  const int run_mask = (CL_ROWS << lu) - 1, unit_mask = (1 << lu) - 1, run_shift = CL_LOG_ROWS + lu;
   const int unit_pitch = (CL_ROWS << lu) + 4;  // VEC tile: [unit][frame][series of the unit] + 4 floats of padding
   auto load_chunk = [&](int k) {
     float *t = tile[k % CL_STAGES];
@@ -324,7 +329,7 @@ __global__ void __launch_bounds__(SGN)
       // memory order in the tile (unit pitch (32 << lu) + 4)
 #pragma unroll
       for (int i = tid; i < SGN * (CL_ROWS / 4); i += SGN) {
-        const int u = i >> (3 + lu), v4 = (i & ((8 << lu) - 1)) * 4;
+        const int u = i >> (CL_LOG_ROWS - 2 + lu), v4 = (i & (((CL_ROWS / 4) << lu) - 1)) * 4;
         const int64_t base = base_tab[u << lu];
         if (base >= 0)
           asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem_u32(t + u * unit_pitch + v4)),
@@ -374,10 +379,9 @@ __global__ void __launch_bounds__(SGN)
     const int j0 = k * CL_ROWS;
     const int rows = j0 + CL_ROWS <= n_frames ? CL_ROWS : n_frames - j0;
     // this thread's series: column tid of the series-major tile, or (unit tid >> lu, series tid & mask) of the VEC tile
-    const bool vec_tile = VEC && rows == CL_ROWS;
-    float *mine = vec_tile ? t + (tid >> lu) * unit_pitch + (tid & unit_mask) : t + tid * CL_PITCH;
-    const int rstep = vec_tile ? (1 << lu) : 1;
     if (rows == CL_ROWS) {
+      constexpr int rstep = VEC ? (1 << (LUT < 0 ? 0 : LUT)) : 1;
+      float *mine = VEC ? t + (tid >> lu) * unit_pitch + (tid & unit_mask) : t + tid * CL_PITCH;
 #pragma unroll 8
       for (int r = 0; r < CL_ROWS; ++r) {
         float v = mine[r * rstep];
@@ -387,6 +391,7 @@ __global__ void __launch_bounds__(SGN)
         mine[r * rstep] = v;
       }
     } else {
+      float *mine = t + tid * CL_PITCH;
       for (int r = 0; r < rows; ++r) {
         float v = mine[r];
 #pragma unroll
@@ -399,7 +404,7 @@ __global__ void __launch_bounds__(SGN)
     if (VEC && rows == CL_ROWS) {
 #pragma unroll
       for (int i = tid; i < SGN * (CL_ROWS / 4); i += SGN) {
-        const int u = i >> (3 + lu), v4 = (i & ((8 << lu) - 1)) * 4;
+        const int u = i >> (CL_LOG_ROWS - 2 + lu), v4 = (i & (((CL_ROWS / 4) << lu) - 1)) * 4;
         const int64_t base = base_tab[u << lu];
         if (base >= 0)
           *reinterpret_cast<float4 *>(buf + base + (int64_t) j0 * fs + v4) =
@@ -425,16 +430,16 @@ __global__ void __launch_bounds__(SGN)
   }
 }
 
-template <int NSEC, bool VEC>
+template <int NSEC, int LUT>
 cudaError_t launch_cl(float *buf, int64_t ss, int64_t cs, int64_t fs, int channels, int lu, int n_series,
                       int n_frames, const BiquadParams &c, float *state, cudaStream_t stream) {
   const int grid = (n_series + SGN - 1) / SGN;
-  const size_t smem = sizeof(float) * CL_STAGES * SGN * cl_pitch(VEC) + SGN * sizeof(int64_t);
+  const size_t smem = sizeof(float) * CL_STAGES * SGN * cl_pitch(LUT >= 0) + SGN * sizeof(int64_t);
   static PerDeviceOnce once;
   if (once.first()) {
     cudaError_t e = cudaSuccess;
-    const void *fns[2] = {reinterpret_cast<const void *>(espb_biquad_cl_kernel<NSEC, true, VEC>),
-                          reinterpret_cast<const void *>(espb_biquad_cl_kernel<NSEC, false, VEC>)};
+    const void *fns[2] = {reinterpret_cast<const void *>(espb_biquad_cl_kernel<NSEC, true, LUT>),
+                          reinterpret_cast<const void *>(espb_biquad_cl_kernel<NSEC, false, LUT>)};
     for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
       e = cudaFuncSetAttribute(fns[i], cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
       if (e == cudaSuccess)
@@ -445,13 +450,30 @@ cudaError_t launch_cl(float *buf, int64_t ss, int64_t cs, int64_t fs, int channe
       return e;
   }
   if (c.first_order)
-    espb_biquad_cl_kernel<NSEC, true, VEC><<<grid, SGN, smem, stream>>>(buf, ss, cs, fs, channels, lu, n_series,
+    espb_biquad_cl_kernel<NSEC, true, LUT><<<grid, SGN, smem, stream>>>(buf, ss, cs, fs, channels, lu, n_series,
                                                                      n_frames, c, state);
   else
-    espb_biquad_cl_kernel<NSEC, false, VEC><<<grid, SGN, smem, stream>>>(buf, ss, cs, fs, channels, lu, n_series,
+    espb_biquad_cl_kernel<NSEC, false, LUT><<<grid, SGN, smem, stream>>>(buf, ss, cs, fs, channels, lu, n_series,
                                                                       n_frames, c, state);
   count_launch();
   return cudaGetLastError();
+}
+
+template <int NSEC>
+cudaError_t launch_cl_any(bool vec, float *buf, int64_t ss, int64_t cs, int64_t fs, int channels, int lu, int n_series,
+                          int n_frames, const BiquadParams &c, float *state, cudaStream_t stream) {
+  if (!vec)
+    return launch_cl<NSEC, -1>(buf, ss, cs, fs, channels, lu, n_series, n_frames, c, state, stream);
+  switch (lu) {
+    case 0:
+      return launch_cl<NSEC, 0>(buf, ss, cs, fs, channels, lu, n_series, n_frames, c, state, stream);
+    case 1:
+      return launch_cl<NSEC, 1>(buf, ss, cs, fs, channels, lu, n_series, n_frames, c, state, stream);
+    case 2:
+      return launch_cl<NSEC, 2>(buf, ss, cs, fs, channels, lu, n_series, n_frames, c, state, stream);
+    default:
+      return launch_cl<NSEC, 3>(buf, ss, cs, fs, channels, lu, n_series, n_frames, c, state, stream);
+  }
 }
 
 template <int NSEC>
@@ -512,17 +534,13 @@ cudaError_t launch_biquad_cl(float *buf, int64_t ss, int64_t cs, int64_t fs, int
                    (unit_series > 0 || cs % 4 == 0 || channels == 1);
   switch (n_sections) {
     case 1:
-      return vec ? launch_cl<1, true>(buf, ss, cs, fs, channels, unit_series, n_series, n_frames, c, state, stream)
-                 : launch_cl<1, false>(buf, ss, cs, fs, channels, unit_series, n_series, n_frames, c, state, stream);
+      return launch_cl_any<1>(vec, buf, ss, cs, fs, channels, unit_series, n_series, n_frames, c, state, stream);
     case 2:
-      return vec ? launch_cl<2, true>(buf, ss, cs, fs, channels, unit_series, n_series, n_frames, c, state, stream)
-                 : launch_cl<2, false>(buf, ss, cs, fs, channels, unit_series, n_series, n_frames, c, state, stream);
+      return launch_cl_any<2>(vec, buf, ss, cs, fs, channels, unit_series, n_series, n_frames, c, state, stream);
     case 3:
-      return vec ? launch_cl<3, true>(buf, ss, cs, fs, channels, unit_series, n_series, n_frames, c, state, stream)
-                 : launch_cl<3, false>(buf, ss, cs, fs, channels, unit_series, n_series, n_frames, c, state, stream);
+      return launch_cl_any<3>(vec, buf, ss, cs, fs, channels, unit_series, n_series, n_frames, c, state, stream);
     case 4:
-      return vec ? launch_cl<4, true>(buf, ss, cs, fs, channels, unit_series, n_series, n_frames, c, state, stream)
-                 : launch_cl<4, false>(buf, ss, cs, fs, channels, unit_series, n_series, n_frames, c, state, stream);
+      return launch_cl_any<4>(vec, buf, ss, cs, fs, channels, unit_series, n_series, n_frames, c, state, stream);
     default:
       return cudaErrorInvalidValue;
   }
