@@ -367,6 +367,13 @@ struct EspbResampleBatch {
   PodBuffer<SchedSegment> spare_segs;
   DevBuf d_ptrs;  // device copy of the plane-pointer tables of espb_resampleProcessPlanes: [2][n_series]
   DevBuf d_segs;
+  // small calls: runs, chunks and pass prefix travel as ONE pageable blob (one upload instead of three); the pointers
+  // below are where the kernels find the tables of the current plan, whichever way they arrived
+  DevBuf d_tables;
+  std::vector<unsigned char> h_tables;
+  const SchedSegment *p_segs = nullptr;
+  const ChunkEntry *p_chunks = nullptr;
+  const int32_t *p_pcb = nullptr;
   bool sched_segments = true;  // closed-form schedule expanded on the device (ESPB_SCHED=seq: per-output host schedule)
   PodBuffer<ChunkEntry> spare_chunks;
   PodBuffer<int32_t> spare_pcb;
@@ -496,14 +503,45 @@ int prepare_call(EspbResampleBatch *c, int n_in, int n_out, float ratio, cudaStr
     return ESPB_OK;
   }
   CU_TRY(c->d_outs.reserve((size_t) c->sched.generated * sizeof(OutEntry)), "cudaMalloc schedule");
-  CU_TRY(c->d_chunks.reserve((c->plan.chunks.size() + 1) * sizeof(ChunkEntry)), "cudaMalloc chunks");
-  CU_TRY(c->d_pcb.reserve(c->plan.pass_chunk_begin.size() * sizeof(int32_t)), "cudaMalloc passes");
+  const size_t seg_bytes = c->sched.segmented ? c->sched.segs.size() * sizeof(SchedSegment) : 0;
+  const size_t chunk_bytes = c->fs_call ? 0 : c->plan.chunks.size() * sizeof(ChunkEntry);
+  const size_t pcb_bytes = c->fs_call ? 0 : c->plan.pass_chunk_begin.size() * sizeof(int32_t);
+  auto up16 = [](size_t v) { return (v + 15) & ~(size_t) 15; };
+  const size_t blob_bytes = up16(seg_bytes) + up16(chunk_bytes) + up16(pcb_bytes);
+  if (c->sched.segmented && blob_bytes <= ((size_t) 48 << 10)) {
+    // one upload: the driver copies a pageable source of this size out before cudaMemcpyAsync returns
+    CU_TRY(c->d_tables.reserve(blob_bytes + sizeof(ChunkEntry)), "cudaMalloc tables");
+    c->h_tables.resize(blob_bytes);
+    unsigned char *h = c->h_tables.data(), *d = c->d_tables.as<unsigned char>();
+    memcpy(h, c->sched.segs.data(), seg_bytes);
+    if (chunk_bytes)
+      memcpy(h + up16(seg_bytes), c->plan.chunks.data(), chunk_bytes);
+    if (pcb_bytes)
+      memcpy(h + up16(seg_bytes) + up16(chunk_bytes), c->plan.pass_chunk_begin.data(), pcb_bytes);
+    CU_TRY(cudaMemcpyAsync(d, h, blob_bytes, cudaMemcpyHostToDevice, stream), "upload tables");
+    c->p_segs = reinterpret_cast<const SchedSegment *>(d);
+    c->p_chunks = reinterpret_cast<const ChunkEntry *>(d + up16(seg_bytes));
+    c->p_pcb = reinterpret_cast<const int32_t *>(d + up16(seg_bytes) + up16(chunk_bytes));
+  } else {
+    CU_TRY(c->d_chunks.reserve((c->plan.chunks.size() + 1) * sizeof(ChunkEntry)), "cudaMalloc chunks");
+    CU_TRY(c->d_pcb.reserve(c->plan.pass_chunk_begin.size() * sizeof(int32_t)), "cudaMalloc passes");
+    if (c->sched.segmented) {
+      CU_TRY(c->d_segs.reserve(seg_bytes), "cudaMalloc schedule");
+      CU_TRY(cudaMemcpyAsync(c->d_segs.p, c->sched.segs.data(), seg_bytes, cudaMemcpyHostToDevice, stream),
+             "upload schedule");
+    }
+    if (!c->fs_call) {
+      CU_TRY(cudaMemcpyAsync(c->d_chunks.p, c->plan.chunks.data(), chunk_bytes, cudaMemcpyHostToDevice, stream),
+             "upload chunks");
+      CU_TRY(cudaMemcpyAsync(c->d_pcb.p, c->plan.pass_chunk_begin.data(), pcb_bytes, cudaMemcpyHostToDevice, stream),
+             "upload passes");
+    }
+    c->p_segs = c->d_segs.as<SchedSegment>();
+    c->p_chunks = c->d_chunks.as<ChunkEntry>();
+    c->p_pcb = c->d_pcb.as<int32_t>();
+  }
   if (c->sched.segmented) {
-    CU_TRY(c->d_segs.reserve(c->sched.segs.size() * sizeof(SchedSegment)), "cudaMalloc schedule");
-    CU_TRY(cudaMemcpyAsync(c->d_segs.p, c->sched.segs.data(), c->sched.segs.size() * sizeof(SchedSegment),
-                           cudaMemcpyHostToDevice, stream),
-           "upload schedule");
-    CU_TRY(launch_expand_schedule(c->d_segs.as<SchedSegment>(), (int) c->sched.segs.size(), c->d_outs.as<OutEntry>(),
+    CU_TRY(launch_expand_schedule(c->p_segs, (int) c->sched.segs.size(), c->d_outs.as<OutEntry>(),
                                   (int) c->sched.generated, c->geo.filters, (c->geo.flags & kFlagLowpass) != 0,
                                   (c->geo.flags & kFlagInterpolate) != 0, stream),
            "schedule kernel");
@@ -514,14 +552,6 @@ int prepare_call(EspbResampleBatch *c, int n_in, int n_out, float ratio, cudaStr
     CU_TRY(launch_finalize(c->d_outs.as<OutEntry>(), (int) c->sched.outs.size(), c->geo.filters,
                            (c->geo.flags & kFlagLowpass) != 0, (c->geo.flags & kFlagInterpolate) != 0, stream),
            "finalize kernel");
-  }
-  if (!c->fs_call) {
-    CU_TRY(cudaMemcpyAsync(c->d_chunks.p, c->plan.chunks.data(), c->plan.chunks.size() * sizeof(ChunkEntry),
-                           cudaMemcpyHostToDevice, stream),
-           "upload chunks");
-    CU_TRY(cudaMemcpyAsync(c->d_pcb.p, c->plan.pass_chunk_begin.data(),
-                           c->plan.pass_chunk_begin.size() * sizeof(int32_t), cudaMemcpyHostToDevice, stream),
-           "upload passes");
   }
   if (!c->tables_uploaded)
     CU_TRY(cudaEventCreateWithFlags(&c->tables_uploaded, cudaEventDisableTiming), "cudaEventCreate");
@@ -555,7 +585,7 @@ int ensure_g(EspbResampleBatch *c, int chunk_first, int chunk_end, cudaStream_t 
     return ESPB_OK;
   const size_t chunk_floats = g_chunk_floats(c->bpp, c->chunk_rows, c->g_row_floats());
   CU_TRY(c->d_G.reserve((size_t) (chunk_end - chunk_first) * chunk_floats * sizeof(float)), "cudaMalloc G");
-  CU_TRY(launch_expand(c->bank.as<float>(), c->d_outs.as<OutEntry>(), c->d_chunks.as<ChunkEntry>(),
+  CU_TRY(launch_expand(c->bank.as<float>(), c->d_outs.as<OutEntry>(), c->p_chunks,
                        c->d_G.as<float>(), chunk_first, chunk_end - chunk_first, (int) c->sched.generated,
                        c->geo.taps, c->bpp, c->chunk_rows, c->direct_call, stream, c->g_row_floats()),
          "expand kernel");
@@ -708,6 +738,8 @@ int make_input_map(CUtensorMap *map, const float *in, int64_t stream_stride, int
   return ESPB_OK;
 }
 
+constexpr int kSmallCallFrames = 4096;  // calls up to this many input frames are staged by one fused kernel
+
 // Stage + resample series [series_first, series_first + n_series) of the batch (series_first is a
 // multiple of 128).  The carried frames and the new input go to the spare staging buffer.  `pre`
 // filters the staged input in place (time-major); with `post` the resampler writes time-major
@@ -727,10 +759,19 @@ int run_series_range(EspbResampleBatch *c, int series_first, int n_series, const
   const bool direct = c->direct_call && !pre && !post && !pcm_in && !pcm_out && !ptrs;
   if (c->direct_call && !direct)
     return fail(ESPB_ERR_STATE, "direct-input plan with library stages around the resampler");
-  if (!direct)
-  CU_TRY(cudaMemcpy2DAsync(x_new, rows * row_bytes, x_old + (size_t) c->carry_row * kSeriesPerRow, rows * row_bytes,
-                           taps * row_bytes, ng, cudaMemcpyDeviceToDevice, stream),
-         "carry copy");
+  // real-time chunks of float input: carried frames, transposition and padding in one launch (the three separate
+  // operations cost more in launch gaps than in work)
+  const bool pre_on_ = pre && pre->params && n_in > 0;
+  const bool small_stage = !direct && !pcm_in && !ptrs && n_in <= kSmallCallFrames &&
+                           !(pre_on_ && pre->block_rows > 0 && n_in > pre->block_rows);
+  if (small_stage)
+    CU_TRY(launch_stage_small(x_old, c->carry_row, taps, in, il.stream_stride, il.channel_stride, il.frame_stride,
+                              c->channels, n_series, n_in, x_new, rows, kChunkRows, stream),
+           "staging kernel");
+  else if (!direct)
+    CU_TRY(cudaMemcpy2DAsync(x_new, rows * row_bytes, x_old + (size_t) c->carry_row * kSeriesPerRow, rows * row_bytes,
+                             taps * row_bytes, ng, cudaMemcpyDeviceToDevice, stream),
+           "carry copy");
   // caller's frames -> rows [taps, taps + n_in) of `dst` (+ `pad` zero rows): float layouts through the
   // transposing stage; packed PCM through the fused conversion, with the stage-by-stage path for the tail
   auto stage_input = [&](float *dst, int pad) -> int {
@@ -784,8 +825,9 @@ int run_series_range(EspbResampleBatch *c, int series_first, int n_series, const
                             pre->block_rows, pre->warm_rows, stream, pre->blk_state, pre->mismatches),
            "biquad kernel");
   } else {
-    if (int rc = stage_input(x_new, kChunkRows))
-      return rc;
+    if (!small_stage)
+      if (int rc = stage_input(x_new, kChunkRows))
+        return rc;
     if (pre_on)  // resampler.cpp:126-133, on the staged rows [taps, taps + n_in)
       CU_TRY(launch_biquad_tm(x_new, x_new, rows, taps, n_in, n_series, pre->sections, *pre->params, pre->state, 0,
                               0, stream),
@@ -846,8 +888,8 @@ int run_series_range(EspbResampleBatch *c, int series_first, int n_series, const
     p.out_ss = ol.stream_stride;
     p.out_cs = ol.channel_stride;
     p.out_fs = ol.frame_stride;
-    p.chunks = c->d_chunks.as<ChunkEntry>();
-    p.pass_chunk_begin = c->d_pcb.as<int32_t>();
+    p.chunks = c->p_chunks;
+    p.pass_chunk_begin = c->p_pcb;
     p.outs = c->d_outs.as<OutEntry>();
     p.n_series = n_series;
     p.channels = c->channels;
@@ -1052,6 +1094,7 @@ void espb_resampleFree(EspbResampleBatch *c) {
   c->yt2.release();
   c->d_outs.release();
   c->d_segs.release();
+  c->d_tables.release();
   c->d_ptrs.release();
   c->d_chunks.release();
   c->d_pcb.release();

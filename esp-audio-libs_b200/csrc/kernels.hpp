@@ -87,6 +87,10 @@ struct FsGroupDesc {
   int32_t seg_begin, n_segs;    // its runs in the concatenated segment table
   int32_t carry_row;            // row of the previous staging buffer where the carried frames start
 };
+// small calls: carried frames (rows [carry_row, carry_row + taps) of old_xt) + new input + zero padding in one launch
+cudaError_t launch_stage_small(const float *old_xt, int carry_row, int taps, const float *in, int64_t in_ss,
+                               int64_t in_cs, int64_t in_fs, int channels, int n_series, int n_in, float *xt,
+                               int64_t rows_cap, int pad_rows, cudaStream_t stream);
 // planar buffers given as one device pointer per (stream, channel) plane (the table itself in device memory)
 cudaError_t launch_transpose_ptrs(const float *const *planes_dev, int n_series, int n_in, float *xt, int64_t rows_cap,
                                   int row_first, int pad_rows, cudaStream_t stream);
@@ -106,7 +110,7 @@ struct FsParams {
   const OutEntry *outs;  // finalized
   int n_series, channels, n_out, taps;
   int kt, slice_floats;
-  int q_per_out, x_tile_floats, out_vec;  // set by the launcher
+  int q_per_out, x_tile_floats, out_vec, x_pitch, stages;  // set by the launcher
   const FsGroupDesc *groups;              // fused clock groups: per-group offsets and counts (blockIdx.y), else NULL
 };
 struct FsGeometry {

@@ -40,7 +40,7 @@ namespace {
 
 constexpr int FS_THREADS = 128;
 constexpr int FS_WARPS = FS_THREADS / 32;
-constexpr int FS_STAGES = 3;
+constexpr int FS_MAX_STAGES = 4;
 
 template <int SV>
 struct XVec;
@@ -83,23 +83,27 @@ __global__ void __launch_bounds__(FS_THREADS) espb_resample_fs_kernel(const FsPa
       return;
   }
   extern __shared__ __align__(128) unsigned char fs_smem[];
-  float *slices = reinterpret_cast<float *>(fs_smem);                            // [FS_STAGES][slice_floats]
-  float *xtile = slices + (size_t) FS_STAGES * p.slice_floats;                   // [x_rows][Q * SV]
-  uint64_t *full = reinterpret_cast<uint64_t *>(xtile + (size_t) p.x_tile_floats);  // [FS_STAGES]
-  int *done = reinterpret_cast<int *>(full + FS_STAGES);                            // [FS_STAGES]
+  const int FS_STAGES = p.stages;
+  float *slices = reinterpret_cast<float *>(fs_smem);                            // [stages][slice_floats]
+  float *xtile = slices + (size_t) FS_STAGES * p.slice_floats;                   // [x_rows][x_pitch]
+  uint64_t *full = reinterpret_cast<uint64_t *>(xtile + (size_t) p.x_tile_floats);  // [stages]
+  int *done = reinterpret_cast<int *>(full + FS_MAX_STAGES);                        // [stages]
 
   const int tid = threadIdx.x, lane = tid & 31;
   const int Q = p.q_per_out, NL = FS_THREADS / Q;  // series chunks per output, outputs per round of the CTA
   const int n_local = tid / Q, qc = tid - n_local * Q;
   const bool active_lane = n_local < NL;
-  const int svt = Q * SV;  // floats per x-tile row
+  const int svt = Q * SV;  // series slots per input row
+  // floats per x-tile row: an ODD number of 16-byte units, so that the rows of neighbouring outputs (2-3 apart when
+  // down-sampling) fall into different bank groups (an even pitch folds them onto half of the banks: measured 91 %
+  // LSU-wavefront utilisation at 14 % of the FMA peak for 8 series before this)
+  const int xpitch = p.x_pitch;
   const int M = NL * B;    // outputs per CTA
   const int n0 = blockIdx.x * M;
   const int n_end = n0 + M < p.n_out ? n0 + M : p.n_out;
   const int T = p.taps, KT = p.kt, pitch = KT + 1, n_slices = T / KT;
 
   if (tid == 0) {
-#pragma unroll
     for (int s = 0; s < FS_STAGES; ++s) {
       mbar_init(&full[s], 1);
       done[s] = 0;
@@ -127,7 +131,7 @@ __global__ void __launch_bounds__(FS_THREADS) espb_resample_fs_kernel(const FsPa
       const int upr = svt / 4;
       for (int i = tid; i < rows * upr; i += FS_THREADS) {
         const int r = i / upr, u = i - r * upr;
-        cp_async_16(xtile + (size_t) r * svt + u * 4, src + (int64_t) r * p.x_fs + u * 4);
+        cp_async_16(xtile + (size_t) r * xpitch + u * 4, src + (int64_t) r * p.x_fs + u * 4);
       }
     } else {  // SV = 2, one chunk: 8 bytes per row
       for (int i = tid; i < rows; i += FS_THREADS)
@@ -150,7 +154,7 @@ __global__ void __launch_bounds__(FS_THREADS) espb_resample_fs_kernel(const FsPa
     if (active_lane && n < n_end)
       e = p.outs[n];
     ph_off[i] = e.phase * pitch;
-    x_off[i] = (e.ws - j0) * svt + qc * SV;
+    x_off[i] = (e.ws - j0) * xpitch + qc * SV;
     wgt[i] = e.w;
     kind[i] = e.kind;
   }
@@ -176,13 +180,13 @@ __global__ void __launch_bounds__(FS_THREADS) espb_resample_fs_kernel(const FsPa
 #pragma unroll
     for (int i = 0; i < B; ++i) {
       const float *c0 = sl + ph_off[i];
-      const float *xp = xtile + x_off[i] + (size_t) t * KT * svt;
+      const float *xp = xtile + x_off[i] + (size_t) t * KT * xpitch;
       for (int kk = 0; kk < KT; kk += 4) {
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           const float h0 = c0[kk + u], h1 = c0[pitch + kk + u];
           XVec<SV> xv;
-          xv.load(xp + (size_t) (kk + u) * svt);
+          xv.load(xp + (size_t) (kk + u) * xpitch);
 #pragma unroll
           for (int s = 0; s < SV; ++s) {
             if constexpr (EXACT) {
@@ -228,7 +232,7 @@ __global__ void __launch_bounds__(FS_THREADS) espb_resample_fs_kernel(const FsPa
       else if (kind[i] == kKindSingle)
         v[s] = sum1;
       else  // pass-through: *source = tap numTaps/2-1 of the window
-        v[s] = xtile[x_off[i] + (size_t) (T / 2 - 1) * svt + s];
+        v[s] = xtile[x_off[i] + (size_t) (T / 2 - 1) * xpitch + s];
     }
     const int q0 = qc * SV;  // first series of this lane
     if (p.out_tm) {
@@ -397,8 +401,12 @@ cudaError_t launch_expand_schedule_groups(const FsGroupDesc *groups, int n_group
 // Tap-range width of the slices: the widest power of two (4..64) that divides `taps` and keeps one slice of all
 // filters+2 rows (pitch kt+1) within 21 KB, so that three stages and the input tile leave room for two CTAs per SM.
 int fs_slice_taps(int taps, int filters) {
+  long budget = 21 * 1024;  // bytes per slice
+  if (const char *v = getenv("ESPB_FS_SLICE_KB"))
+    if (atoi(v) > 0)
+      budget = atol(v) * 1024;
   int kt = 4;
-  while (kt < 64 && taps % (kt * 2) == 0 && (size_t) (filters + 2) * (kt * 2 + 1) * sizeof(float) <= 21 * 1024)
+  while (kt < 64 && taps % (kt * 2) == 0 && (long) ((filters + 2) * (kt * 2 + 1) * sizeof(float)) <= budget)
     kt *= 2;
   return kt;
 }
@@ -429,9 +437,24 @@ FsGeometry fs_geometry(int n_series) {
   return g;
 }
 
+int fs_x_pitch(const FsGeometry &g) {
+  const int svt = g.q * g.sv;
+  return (svt >= 8 && (svt / 4) % 2 == 0) ? svt + 4 : svt;
+}
+
+int fs_stages() {
+  static int st = 0;
+  if (!st) {
+    const char *v = getenv("ESPB_FS_STAGES");
+    const int n = v ? atoi(v) : 0;
+    st = (n >= 2 && n <= FS_MAX_STAGES) ? n : 2;  // measured: 2 stages (more CTAs per SM) >= 3 on every shape
+  }
+  return st;
+}
+
 size_t fs_smem_bytes(const FsGeometry &g, size_t slice_floats, int x_rows) {
-  return (FS_STAGES * slice_floats + (size_t) x_rows * g.q * g.sv) * sizeof(float) + FS_STAGES * sizeof(uint64_t) +
-         FS_STAGES * sizeof(int) + 16;
+  return (fs_stages() * slice_floats + (((size_t) x_rows * fs_x_pitch(g) + 3) & ~(size_t) 3)) * sizeof(float) +
+         FS_MAX_STAGES * (sizeof(uint64_t) + sizeof(int)) + 16;
 }
 
 cudaError_t launch_resample_fs(const FsParams &p_in, const FsGeometry &g, int x_rows, bool exact,
@@ -440,9 +463,10 @@ cudaError_t launch_resample_fs(const FsParams &p_in, const FsGeometry &g, int x_
     return cudaSuccess;
   FsParams p = p_in;
   p.q_per_out = g.q;
-  p.x_tile_floats = (int) (((size_t) x_rows * g.q * g.sv + 3) & ~(size_t) 3);
-  const size_t smem = (FS_STAGES * (size_t) p.slice_floats + (size_t) p.x_tile_floats) * sizeof(float) +
-                      FS_STAGES * sizeof(uint64_t) + FS_STAGES * sizeof(int) + 16;
+  p.x_pitch = fs_x_pitch(g);
+  p.stages = fs_stages();
+  p.x_tile_floats = (int) (((size_t) x_rows * p.x_pitch + 3) & ~(size_t) 3);
+  const size_t smem = fs_smem_bytes(g, (size_t) p.slice_floats, x_rows);
   if (smem > 200 * 1024)
     return cudaErrorInvalidValue;
   // vector stores: interleaved caller layout whose channel count keeps a lane's series inside one frame

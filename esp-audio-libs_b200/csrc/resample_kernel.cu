@@ -299,6 +299,59 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// Small calls (real-time chunks): the carried frames, the new input and the zero padding of a call in ONE launch
+// instead of a strided device copy plus two transposition kernels.  blockIdx.y < hist_tiles copies history rows
+// (time-major to time-major), the other tiles are the generic transposing tiles.
+__global__ void __launch_bounds__(256)
+    espb_stage_small_kernel(const float *__restrict__ old_xt, int carry_row, int taps, int hist_tiles,
+                            const float *__restrict__ in, int64_t in_ss, int64_t in_cs, int64_t in_fs, int channels,
+                            int n_series, int n_in, float *__restrict__ xt, int64_t rows_cap, int pad_rows) {
+  __shared__ float tile[TR_ROWS][SGN + 1];
+  const int g = blockIdx.x;
+  const int tid = threadIdx.x;
+  if ((int) blockIdx.y < hist_tiles) {
+    const int r0 = blockIdx.y * TR_ROWS;
+    const float4 *src = reinterpret_cast<const float4 *>(old_xt + ((int64_t) g * rows_cap + carry_row + r0) * SGN);
+    float4 *dst = reinterpret_cast<float4 *>(xt + ((int64_t) g * rows_cap + r0) * SGN);
+    for (int i = tid; i < TR_ROWS * (SGN / 4); i += 256)
+      if (r0 + i / (SGN / 4) < taps)
+        dst[i] = __ldg(src + i);
+    return;
+  }
+  const int j0 = ((int) blockIdx.y - hist_tiles) * TR_ROWS;
+  const int total_rows = n_in + pad_rows;
+  const int mapping = (in_fs == 1) ? 0 : ((in_cs == 1 && in_fs == channels && SGN % channels == 0) ? 1 : 2);
+  for (int i = tid; i < SGN * TR_ROWS; i += 256) {
+    int sl, t;
+    if (mapping == 0) {
+      sl = i / TR_ROWS;
+      t = i - sl * TR_ROWS;
+    } else if (mapping == 1) {
+      const int per = TR_ROWS * channels;
+      const int stl = i / per, r = i - stl * per;
+      t = r / channels;
+      sl = stl * channels + (r - t * channels);
+    } else {
+      t = i / SGN;
+      sl = i - t * SGN;
+    }
+    const int q = g * SGN + sl, j = j0 + t;
+    float v = 0.0f;
+    if (q < n_series && j < n_in) {
+      const int st = q / channels, ch = q - st * channels;
+      v = __ldg(in + (int64_t) st * in_ss + (int64_t) ch * in_cs + (int64_t) j * in_fs);
+    }
+    tile[t][sl] = v;
+  }
+  __syncthreads();
+  float4 *dst = reinterpret_cast<float4 *>(xt + ((int64_t) g * rows_cap + taps + j0) * SGN);
+  for (int i = tid; i < TR_ROWS * (SGN / 4); i += 256) {
+    const int t = i / (SGN / 4), c4 = i - t * (SGN / 4);
+    if (j0 + t < total_rows)
+      dst[i] = make_float4(tile[t][c4 * 4], tile[t][c4 * 4 + 1], tile[t][c4 * 4 + 2], tile[t][c4 * 4 + 3]);
+  }
+}
+
 // Planar input given as one pointer per (stream, channel) plane — the reference's resampleProcess signature
 // (`const float *const *inputs`, include/art_resampler.h:36-37): separately allocated channel buffers.  Same tiling
 // as the generic kernel (frames contiguous per plane: a warp reads 32 consecutive frames of one plane).
@@ -809,6 +862,20 @@ cudaError_t launch_transpose(const float *in, int64_t in_ss, int64_t in_cs, int6
                                                     row_first, fast_rows, pad_rows);
     count_launch();
   }
+  return cudaGetLastError();
+}
+
+cudaError_t launch_stage_small(const float *old_xt, int carry_row, int taps, const float *in, int64_t in_ss,
+                               int64_t in_cs, int64_t in_fs, int channels, int n_series, int n_in, float *xt,
+                               int64_t rows_cap, int pad_rows, cudaStream_t stream) {
+  const int n_groups = (n_series + SGN - 1) / SGN;
+  if (n_groups <= 0)
+    return cudaSuccess;
+  const int hist_tiles = (taps + TR_ROWS - 1) / TR_ROWS;
+  dim3 grid(n_groups, hist_tiles + (n_in + pad_rows + TR_ROWS - 1) / TR_ROWS);
+  espb_stage_small_kernel<<<grid, 256, 0, stream>>>(old_xt, carry_row, taps, hist_tiles, in, in_ss, in_cs, in_fs,
+                                                    channels, n_series, n_in, xt, rows_cap, pad_rows);
+  count_launch();
   return cudaGetLastError();
 }
 

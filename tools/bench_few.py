@@ -74,10 +74,20 @@ def run(ns, ch, taps, filters, lowpass, flags, src, dst, seconds, fs, mode, peak
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--seconds", type=float, default=10.0)
+    ap.add_argument("--quick", action="store_true", help="few-series kernel only: 1 and 4 stereo streams, 1 x 8 ch")
     args = ap.parse_args()
     espb.set_device(0)
     _, peak = espb.measure_fp32_fma_peak2()
     print(json.dumps(dict(ffma2_probe_tflops=peak)), flush=True)
+    if args.quick:
+        lp = float(f32(44100) / f32(96000) * (f32(1.0) - f32(10.24) / f32(1024)))
+        run(1, 2, 256, 256, 1.0, 3, 44100, 48000, args.seconds, None, espb.MODE_FAST, peak)
+        run(2, 2, 256, 256, 1.0, 3, 44100, 48000, args.seconds, None, espb.MODE_FAST, peak)
+        run(4, 2, 256, 256, 1.0, 3, 44100, 48000, args.seconds, None, espb.MODE_FAST, peak)
+        run(1, 8, 1024, 256, lp, 1 | 4, 96000, 44100, args.seconds, None, espb.MODE_FAST, peak)
+        run(1, 2, 256, 256, float(f32(44100) / f32(48000) * f32(0.96)), 1, 48000, 44100, args.seconds, None,
+            espb.MODE_FAST, peak)
+        return
     for ns in (1, 2, 4, 16, 64):
         for fs in ((None, "0") if ns <= 16 else ("0",)):
             run(ns, 2, 256, 256, 1.0, 3, 44100, 48000, args.seconds, fs, espb.MODE_FAST, peak)
