@@ -369,6 +369,10 @@ struct EspbResampleBatch {
   DevBuf d_segs;
   // small calls: runs, chunks and pass prefix travel as ONE pageable blob (one upload instead of three); the pointers
   // below are where the kernels find the tables of the current plan, whichever way they arrived
+  // coefficient expansion on a side stream, next to the (HBM-bound) input staging of the same call
+  cudaStream_t aux = nullptr;
+  cudaEvent_t aux_fork = nullptr, aux_join = nullptr;
+  bool aux_join_pending = false;
   DevBuf d_tables;
   std::vector<unsigned char> h_tables;
   const SchedSegment *p_segs = nullptr;
@@ -897,6 +901,10 @@ int run_series_range(EspbResampleBatch *c, int series_first, int n_series, const
     p.taps = taps;
     const int n_passes = c->plan.n_passes();
     const int pps = passes_per_slab(c);
+    if (c->aux_join_pending) {  // the coefficients were expanded on the side stream
+      CU_TRY(cudaStreamWaitEvent(stream, c->aux_join, 0), "cudaStreamWaitEvent");
+      c->aux_join_pending = false;
+    }
     for (int pf = 0; pf < n_passes; pf += pps) {
       const int pe = pf + pps < n_passes ? pf + pps : n_passes;
       const int cf = c->plan.pass_chunk_begin[pf], ce = c->plan.pass_chunk_begin[pe];
@@ -1095,6 +1103,11 @@ void espb_resampleFree(EspbResampleBatch *c) {
   c->d_outs.release();
   c->d_segs.release();
   c->d_tables.release();
+  if (c->aux)
+    cudaStreamDestroy(c->aux);
+  for (cudaEvent_t ev : {c->aux_fork, c->aux_join})
+    if (ev)
+      cudaEventDestroy(ev);
   c->d_ptrs.release();
   c->d_chunks.release();
   c->d_pcb.release();
@@ -1217,7 +1230,37 @@ EspbResampleResult espb_resampleProcessLayout(EspbResampleBatch *c, const float 
   if (prepare_call(c, numInputFrames, numOutputFrames, ratio, as_stream(stream), direct_input_layout(c, in, *il)) !=
       ESPB_OK)
     return res;
-  if (run_series_range(c, 0, c->n_series(), in, *il, out, *ol, numInputFrames, as_stream(stream), false) != ESPB_OK)
+  // Long calls: expand the coefficients on a side stream while this stream stages the input (two bandwidth-bound
+  // kernels that do not depend on each other); the resampler launch waits for both.
+  bool pre = false;
+  if (!c->fs_call && c->sched.generated > 4096 && passes_per_slab(c) >= c->plan.n_passes() &&
+      !(c->g_resident_first == 0 && c->g_resident_end == (int) c->plan.chunks.size())) {
+    cudaError_t e = cudaSuccess;
+    if (!c->aux) {
+      e = cudaStreamCreateWithFlags(&c->aux, cudaStreamNonBlocking);
+      if (e == cudaSuccess)
+        e = cudaEventCreateWithFlags(&c->aux_fork, cudaEventDisableTiming);
+      if (e == cudaSuccess)
+        e = cudaEventCreateWithFlags(&c->aux_join, cudaEventDisableTiming);
+    }
+    if (e == cudaSuccess)
+      e = cudaEventRecord(c->aux_fork, as_stream(stream));
+    if (e == cudaSuccess)
+      e = cudaStreamWaitEvent(c->aux, c->aux_fork, 0);
+    if (e != cudaSuccess) {
+      cuda_fail(e, "side stream");
+      return res;
+    }
+    if (ensure_g(c, 0, (int) c->plan.chunks.size(), c->aux) != ESPB_OK)
+      return res;
+    if (cudaEventRecord(c->aux_join, c->aux) != cudaSuccess) {
+      fail(ESPB_ERR_CUDA, "side stream event");
+      return res;
+    }
+    c->aux_join_pending = true;
+    pre = true;
+  }
+  if (run_series_range(c, 0, c->n_series(), in, *il, out, *ol, numInputFrames, as_stream(stream), pre) != ESPB_OK)
     return res;
   res.input_used = c->sched.used;
   res.output_generated = c->sched.generated;

@@ -283,3 +283,22 @@ def test_closed_form_schedule_is_the_sequential_machine():
             n_out = int(rng.choice([0, 1, 5, 480, 1200, 6000, 30000, 200000]))
             a, _ = same(taps, filters, flags, float(off), idx, n_in, n_out, ratio)
             off, idx = a["end_offset"], a["end_index"]
+
+
+def test_shard_ranges_and_multi_gpu_symbols():
+    """espb_shard_range (C) == the Python helper; contiguous, covering, sizes differ by at most one; NCCL resolves at
+    run time (the library loads and these host-only entry points work without a GPU)."""
+    import ctypes as C
+    L = espb.lib()
+    for n in (0, 1, 7, 4096, 65536, 65537):
+        for world in (1, 2, 3, 8):
+            nxt = 0
+            for r in range(world):
+                first, count = C.c_int64(0), C.c_int64(0)
+                L.espb_shard_range(n, r, world, C.byref(first), C.byref(count))
+                assert (first.value, count.value) == espb.shard_range(n, r, world)
+                assert first.value == nxt and count.value in (n // world, n // world + 1)
+                nxt += count.value
+            assert nxt == n
+    assert L.espb_nccl_version() >= 0          # 0: no NCCL on this machine; the single-GPU path does not need it
+    assert L.espb_multi_size(None) == 0 and L.espb_dist_world(None) == 0
