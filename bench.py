@@ -257,13 +257,17 @@ def timed_steps(espb, ranks, stream, step, steps, warmup):
     """W warm-up steps, then K steps between CUDA events on `stream`, bracketed by barrier + device sync on both
     sides; returns (ms per step, max over ranks)."""
     L = espb.lib()
+    dbg = os.environ.get("ESPB_BENCH_DEBUG")
     for _ in range(warmup):
         step()
     ranks.barrier()
     ev0, ev1 = L.espb_event_create(), L.espb_event_create()
     L.espb_event_record(ev0, stream)
     for _ in range(steps):
+        t0 = time.perf_counter()
         step()
+        if dbg:
+            print(f"[bench] step enqueued in {(time.perf_counter() - t0) * 1e3:.2f} ms", file=sys.stderr)
     L.espb_event_record(ev1, stream)
     ms = espb.capi.C.c_float(0)
     espb.capi._check(L.espb_event_elapsed_ms(ev0, ev1, espb.capi.C.byref(ms)), "elapsed")
@@ -594,6 +598,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-configs", action="store_true", help="skip the C3 / C4 / C5 sub-records")
+    ap.add_argument("--configs", default="C5,C3,C4", help="which sub-records to run (comma-separated)")
     ap.add_argument("--mode", default="fast", choices=["fast", "exact"],
                     help="arithmetic of the dot products: fast = FFMA2 chain (the metric), exact = un-fused, bit-exact")
     args = ap.parse_args()
@@ -771,9 +776,9 @@ def main():
     configs, checks = {}, ([] if (rank == 0 and world == 1 and not args.no_cpu_baseline) else None)
     if not args.no_configs and ns == STREAMS_PER_GPU:
         sub_steps = max(3, min(args.steps, 5))
-        configs["C5"] = bench_c5(espb, ranks, stream, fma_tflops, link, sub_steps, not args.no_e2e, checks)
-        configs["C3"] = bench_c3(espb, ranks, stream, fma_tflops, link, sub_steps, not args.no_e2e, checks)
-        configs["C4"] = bench_c4(espb, ranks, stream, fma_tflops, link, sub_steps, not args.no_e2e, checks)
+        for name, fn in (("C5", bench_c5), ("C3", bench_c3), ("C4", bench_c4)):
+            if name in args.configs.split(","):
+                configs[name] = fn(espb, ranks, stream, fma_tflops, link, sub_steps, not args.no_e2e, checks)
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -190,6 +190,8 @@ namespace {
 struct DevBuf {
   void *p = nullptr;
   size_t cap = 0;
+  // Grows with head-room: in a stream of calls the sizes wander by a few entries (frame counts alternate between n
+  // and n + 1), and every re-allocation is a cudaFree — a device-wide synchronisation in the middle of the stream.
   cudaError_t reserve(size_t bytes) {
     if (bytes <= cap)
       return cudaSuccess;
@@ -197,9 +199,16 @@ struct DevBuf {
       cudaFree(p);
     p = nullptr;
     cap = 0;
-    cudaError_t e = cudaMalloc(&p, bytes);
-    if (e == cudaSuccess)
-      cap = bytes;
+    const size_t want = bytes + bytes / 16 + 4096;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) {  // no room for the slack: the exact size
+      cudaGetLastError();
+      e = cudaMalloc(&p, bytes);
+      if (e == cudaSuccess)
+        cap = bytes;
+      return e;
+    }
+    cap = want;
     return e;
   }
   void release() {
@@ -632,6 +641,8 @@ int pick_passes_per_cta(const EspbResampleBatch *c, int n_series, int pass_first
 int ensure_xt(EspbResampleBatch *c, int64_t rows) {
   if (rows <= c->xt_rows)
     return ESPB_OK;
+  if (c->xt_rows > 0)
+    rows += rows / 64 + 64;  // (head-room: see DevBuf::reserve)
   const int taps = c->geo.taps;
   const size_t row_bytes = kSeriesPerRow * sizeof(float);
   const size_t bytes = (size_t) c->n_groups() * rows * row_bytes;
@@ -991,6 +1002,7 @@ int run_series_range(EspbResampleBatch *c, int series_first, int n_series, const
 // Scratch for time-major resampler output (post-filter path): at least `rows` rows per group.
 int ensure_yt(EspbResampleBatch *c, int64_t rows, bool second) {
   if (rows > c->yt_rows) {
+    rows += rows / 64 + 64;  // (head-room: see DevBuf::reserve)
     CU_TRY(c->yt.reserve((size_t) c->n_groups() * rows * kSeriesPerRow * sizeof(float)), "output scratch");
     c->yt_rows = rows;
     c->yt2_rows = 0;

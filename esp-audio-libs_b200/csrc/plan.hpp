@@ -51,6 +51,7 @@ struct PodBuffer {
   }
   void reserve(size_t n) {
     if (n > cap) {
+      n += n / 8 + 64;  // head-room: table sizes wander from call to call, and moving a page-locked table is costly
       if (ptr && on_release)
         on_release(ptr);
       ptr = static_cast<T *>(realloc(ptr, n * sizeof(T)));
