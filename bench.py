@@ -741,10 +741,18 @@ def main():
         ranks.barrier()
         # (1.5 GiB per direction, the size of the step's own buffers: smaller probes partly run out of the host's
         # last-level cache and overstate what a sustained stream gets)
-        link = espb.measure_host_link(None, 1536 << 20, 64 << 20, 2)
+        # every rank runs the SAME pattern at the same time: a barrier before each of the three
+        rates = []
+        for pattern in (0, 1, 2):
+            ranks.barrier()
+            rates.append(espb.measure_host_link_pattern(pattern, 1536 << 20, 64 << 20, 5))  # median of 5
         ranks.barrier()
-        link["what"] = ("pinned cudaMemcpyAsync, 64 MiB slabs: H2D alone, D2H alone, both at once, on this rank's GPU "
-                        f"while the other {world - 1} rank(s) do the same; GB/s of this rank")
+        link = {"h2d_gbs": rates[0], "d2h_gbs": rates[1], "duplex_each_gbs": rates[2], "duplex_sum_gbs": 2 * rates[2],
+                "bytes_per_direction": 1536 << 20, "slab_bytes": 64 << 20,
+                "all_ranks_duplex_sum_gbs": sum(ranks.all_floats(2 * rates[2])),
+                "what": "pinned cudaMemcpyAsync, 64 MiB slabs: H2D alone, D2H alone, both at once, on this rank's GPU "
+                        f"while the other {world - 1} rank(s) run the same pattern at the same time (a barrier before "
+                        "each); GB/s of this rank"}
 
     # ---- end to end: host buffers through the public C-ABI call, H2D + D2H inside the timed region
     e2e, e2e_last = None, None

@@ -11,5 +11,5 @@ from .capi import (BLACKMAN_HARRIS, INCLUDE_LOWPASS, MODE_EXACT, MODE_FAST,  # n
                    biquad_lowpass, checksum_u32, declared_symbols, dsps_add_s16, dsps_mulc_s16, device_count, device_info, float_to_quantized,
                    launch_count, lib, library_path, measure_fp32_fma_peak, measure_fp32_fma_peak2, measure_fp32_tile_pattern, plan_filter_bank, plan_passes, plan_policy,
                    plan_schedule, plan_schedule_segments, quantized_to_float, set_device)
-from .capi import measure_host_link, ResampleGroups, WavDecoder, wav_write_header, _Q15Backend  # noqa: F401,E402
+from .capi import measure_host_link, measure_host_link_pattern, ResampleGroups, WavDecoder, wav_write_header, _Q15Backend  # noqa: F401,E402
 from .sharding import NcclGather, combine_checksums, gather_words, shard_range  # noqa: F401,E402

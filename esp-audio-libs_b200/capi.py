@@ -124,6 +124,7 @@ def lib():
         "espb_resampleGroupsReset": (i, [vp, i, vp]),
         "espb_nccl_version": (i, []),
         "espb_measure_host_link": (i, [i, vp, sz, sz, i, C.POINTER(C.c_double)]),
+        "espb_measure_host_link_pattern": (i, [i, sz, sz, i, C.POINTER(C.c_double)]),
         "espb_multi_last_error": (C.c_char_p, []),
         "espb_shard_range": (None, [i64, i, i, C.POINTER(i64), C.POINTER(i64)]),
         "espb_multi_create": (vp, [i, vp]),
@@ -308,6 +309,13 @@ def measure_host_link(devices=None, nbytes=1 << 30, slab_bytes=64 << 20, reps=3)
     _check(rc, "measure_host_link")
     return dict(h2d_gbs=out[0], d2h_gbs=out[1], duplex_each_gbs=out[2], duplex_sum_gbs=out[4], duplex_seconds=out[5],
                 bytes_per_direction_per_device=nbytes, slab_bytes=slab_bytes)
+
+
+def measure_host_link_pattern(pattern, nbytes=1 << 30, slab_bytes=64 << 20, reps=2):
+    """GB/s per direction of one pattern (0 H2D, 1 D2H, 2 both) on the current device."""
+    v = C.c_double(0)
+    _check(lib().espb_measure_host_link_pattern(pattern, nbytes, slab_bytes, reps, C.byref(v)), "measure_host_link")
+    return float(v.value)
 
 
 def measure_fp32_tile_pattern():

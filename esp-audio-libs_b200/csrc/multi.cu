@@ -357,8 +357,8 @@ int espb_dist_barrier(EspbDist *d) {
 // per slab, separate streams per direction), all devices concurrently; results are aggregate GB/s per direction
 // over all devices, wall clock between device-wide synchronisations, best of `reps`.
 // out[6] = {h2d_only, d2h_only, duplex_h2d, duplex_d2h, duplex_sum, seconds_of_the_duplex_run}.
-extern "C" int espb_measure_host_link(int n_devices, const int *devices, size_t bytes, size_t slab_bytes, int reps,
-                                      double *out) {
+static int measure_host_link_impl(int n_devices, const int *devices, size_t bytes, size_t slab_bytes, int reps,
+                                  int only_pattern, double *out) {
   if (!out || bytes == 0)
     return multi_fail(ESPB_ERR_ARG, "measure_host_link: bad arguments");
   int have = 0;
@@ -414,7 +414,10 @@ extern "C" int espb_measure_host_link(int n_devices, const int *devices, size_t 
     }
   };
   double best[3] = {0, 0, 0}, secs_duplex = 0.0;
+  std::vector<double> seen;  // single-pattern form: the MEDIAN run (other processes drift in and out of step)
   for (int pattern = 0; pattern < 3 && e == cudaSuccess; ++pattern) {
+    if (only_pattern >= 0 && pattern != only_pattern)
+      continue;
     for (int rep = 0; rep < reps + 1 && e == cudaSuccess; ++rep) {  // first run of each pattern is a warm-up
       sync_all();
       timespec t0, t1;
@@ -434,6 +437,8 @@ extern "C" int espb_measure_host_link(int n_devices, const int *devices, size_t 
       clock_gettime(CLOCK_MONOTONIC, &t1);
       const double s = (t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec);
       const double gbs = (double) bytes * n / s / 1e9;  // per direction, all devices
+      if (rep > 0 && only_pattern >= 0)
+        seen.push_back(gbs);
       if (rep > 0 && gbs > best[pattern]) {
         best[pattern] = gbs;
         if (pattern == 2)
@@ -459,6 +464,16 @@ extern "C" int espb_measure_host_link(int n_devices, const int *devices, size_t 
   cudaSetDevice(prev);
   if (e != cudaSuccess)
     return multi_fail(ESPB_ERR_CUDA, "measure_host_link", cudaGetErrorString(e));
+  if (only_pattern >= 0 && !seen.empty()) {
+    for (size_t a = 0; a < seen.size(); ++a)
+      for (size_t b = a + 1; b < seen.size(); ++b)
+        if (seen[b] < seen[a]) {
+          const double t = seen[a];
+          seen[a] = seen[b];
+          seen[b] = t;
+        }
+    best[only_pattern] = seen[seen.size() / 2];
+  }
   out[0] = best[0];
   out[1] = best[1];
   out[2] = best[2];
@@ -466,4 +481,20 @@ extern "C" int espb_measure_host_link(int n_devices, const int *devices, size_t 
   out[4] = 2.0 * best[2];
   out[5] = secs_duplex;
   return ESPB_OK;
+}
+
+extern "C" int espb_measure_host_link(int n_devices, const int *devices, size_t bytes, size_t slab_bytes, int reps,
+                                      double *out) {
+  return measure_host_link_impl(n_devices, devices, bytes, slab_bytes, reps, -1, out);
+}
+
+// One pattern only (0: H2D alone, 1: D2H alone, 2: both) on the current device, so that several processes — one per
+// GPU — can run the SAME pattern at the same time with a barrier between patterns.  *gbs = GB/s per direction.
+extern "C" int espb_measure_host_link_pattern(int pattern, size_t bytes, size_t slab_bytes, int reps, double *gbs) {
+  if (pattern < 0 || pattern > 2 || !gbs)
+    return multi_fail(ESPB_ERR_ARG, "measure_host_link_pattern: bad arguments");
+  double out[6] = {0, 0, 0, 0, 0, 0};
+  const int rc = measure_host_link_impl(0, nullptr, bytes, slab_bytes, reps, pattern, out);
+  *gbs = out[pattern];
+  return rc;
 }

@@ -406,6 +406,9 @@ void espb_shard_range(int64_t n_streams, int rank, int world, int64_t *first, in
  * the current device).  out[6] = aggregate GB/s per direction {H2D alone, D2H alone, H2D while D2H runs, D2H while
  * H2D runs, both directions summed, seconds of the duplex run}: the ceiling of the host-buffer entry points. */
 int espb_measure_host_link(int n_devices, const int *devices, size_t bytes, size_t slab_bytes, int reps, double *out);
+/* one pattern (0: H2D alone, 1: D2H alone, 2: both at once) on the current device, GB/s per direction: lets one process
+ * per GPU run the same pattern at the same time, with a barrier of the caller's between patterns */
+int espb_measure_host_link_pattern(int pattern, size_t bytes, size_t slab_bytes, int reps, double *gbs);
 
 /* one process drives all devices: ncclCommInitAll over `devices` (NULL: 0 .. n_devices-1; n_devices <= 0: all) */
 typedef struct EspbMulti EspbMulti;
