@@ -741,11 +741,22 @@ def main():
         ranks.barrier()
         # (1.5 GiB per direction, the size of the step's own buffers: smaller probes partly run out of the host's
         # last-level cache and overstate what a sustained stream gets)
-        # every rank runs the SAME pattern at the same time: a barrier before each of the three
+        # every rank runs the SAME pattern at the same time: buffers are page-locked first (that takes a second and
+        # differs from rank to rank), then each timed run starts on a barrier; median of 3 runs per pattern
+        C = espb.capi.C
+        probe = L.espb_link_probe_create(1536 << 20, 64 << 20)
+        if not probe:
+            raise SystemExit("bench.py: link probe allocation failed")
         rates = []
         for pattern in (0, 1, 2):
-            ranks.barrier()
-            rates.append(espb.measure_host_link_pattern(pattern, 1536 << 20, 64 << 20, 5))  # median of 5
+            seen = []
+            for _rep in range(4):
+                ranks.barrier()
+                v = C.c_double(0)
+                espb.capi._check(L.espb_link_probe_run(probe, pattern, C.byref(v), None), "link probe")
+                seen.append(float(v.value))
+            rates.append(sorted(seen[1:])[1])
+        L.espb_link_probe_free(probe)
         ranks.barrier()
         link = {"h2d_gbs": rates[0], "d2h_gbs": rates[1], "duplex_each_gbs": rates[2], "duplex_sum_gbs": 2 * rates[2],
                 "bytes_per_direction": 1536 << 20, "slab_bytes": 64 << 20,

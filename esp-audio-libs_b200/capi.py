@@ -125,6 +125,9 @@ def lib():
         "espb_nccl_version": (i, []),
         "espb_measure_host_link": (i, [i, vp, sz, sz, i, C.POINTER(C.c_double)]),
         "espb_measure_host_link_pattern": (i, [i, sz, sz, i, C.POINTER(C.c_double)]),
+        "espb_link_probe_create": (vp, [sz, sz]),
+        "espb_link_probe_run": (i, [vp, i, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+        "espb_link_probe_free": (None, [vp]),
         "espb_multi_last_error": (C.c_char_p, []),
         "espb_shard_range": (None, [i64, i, i, C.POINTER(i64), C.POINTER(i64)]),
         "espb_multi_create": (vp, [i, vp]),

@@ -498,3 +498,92 @@ extern "C" int espb_measure_host_link_pattern(int pattern, size_t bytes, size_t 
   *gbs = out[pattern];
   return rc;
 }
+
+// ---------------------------------------------------------------- host link probe, prepared form
+// Buffers and streams are set up once (page-locking gigabytes takes about a second and differs from process to
+// process); the timed runs can then start on a barrier of the caller's, so that one process per GPU measures the link
+// while every other process is copying too — not while they are still allocating.
+struct EspbLinkProbe {
+  int device = 0;
+  size_t bytes = 0, slab = 0;
+  void *h_in = nullptr, *h_out = nullptr, *d_in = nullptr, *d_out = nullptr;
+  cudaStream_t s_in = nullptr, s_out = nullptr;
+};
+
+extern "C" void espb_link_probe_free(EspbLinkProbe *p) {
+  if (!p)
+    return;
+  if (p->h_in)
+    cudaFreeHost(p->h_in);
+  if (p->h_out)
+    cudaFreeHost(p->h_out);
+  if (p->d_in)
+    cudaFree(p->d_in);
+  if (p->d_out)
+    cudaFree(p->d_out);
+  if (p->s_in)
+    cudaStreamDestroy(p->s_in);
+  if (p->s_out)
+    cudaStreamDestroy(p->s_out);
+  delete p;
+}
+
+extern "C" EspbLinkProbe *espb_link_probe_create(size_t bytes, size_t slab_bytes) {
+  if (bytes == 0)
+    return nullptr;
+  EspbLinkProbe *p = new EspbLinkProbe();
+  p->bytes = bytes;
+  p->slab = (slab_bytes == 0 || slab_bytes > bytes) ? bytes : slab_bytes;
+  cudaGetDevice(&p->device);
+  cudaError_t e = cudaMallocHost(&p->h_in, bytes);
+  if (e == cudaSuccess)
+    e = cudaMallocHost(&p->h_out, bytes);
+  if (e == cudaSuccess)
+    e = cudaMalloc(&p->d_in, bytes);
+  if (e == cudaSuccess)
+    e = cudaMalloc(&p->d_out, bytes);
+  if (e == cudaSuccess)
+    e = cudaStreamCreateWithFlags(&p->s_in, cudaStreamNonBlocking);
+  if (e == cudaSuccess)
+    e = cudaStreamCreateWithFlags(&p->s_out, cudaStreamNonBlocking);
+  if (e == cudaSuccess) {
+    memset(p->h_in, 1, bytes);
+    memset(p->h_out, 0, bytes);
+    e = cudaMemset(p->d_out, 2, bytes);
+  }
+  if (e == cudaSuccess)
+    e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) {
+    multi_fail(ESPB_ERR_CUDA, "link_probe_create", cudaGetErrorString(e));
+    espb_link_probe_free(p);
+    return nullptr;
+  }
+  return p;
+}
+
+// One timed run of pattern 0 (H2D alone) / 1 (D2H alone) / 2 (both): `bytes` per direction in slabs, wall clock
+// between device synchronisations.  *gbs = GB/s per direction.
+extern "C" int espb_link_probe_run(EspbLinkProbe *p, int pattern, double *gbs, double *seconds) {
+  if (!p || pattern < 0 || pattern > 2 || !gbs)
+    return multi_fail(ESPB_ERR_ARG, "link_probe_run: bad arguments");
+  cudaError_t e = cudaDeviceSynchronize();
+  timespec t0, t1;
+  clock_gettime(CLOCK_MONOTONIC, &t0);
+  for (size_t off = 0; off < p->bytes && e == cudaSuccess; off += p->slab) {
+    const size_t len = off + p->slab <= p->bytes ? p->slab : p->bytes - off;
+    if (pattern != 1)
+      e = cudaMemcpyAsync((char *) p->d_in + off, (char *) p->h_in + off, len, cudaMemcpyHostToDevice, p->s_in);
+    if (pattern != 0 && e == cudaSuccess)
+      e = cudaMemcpyAsync((char *) p->h_out + off, (char *) p->d_out + off, len, cudaMemcpyDeviceToHost, p->s_out);
+  }
+  if (e == cudaSuccess)
+    e = cudaDeviceSynchronize();
+  clock_gettime(CLOCK_MONOTONIC, &t1);
+  if (e != cudaSuccess)
+    return multi_fail(ESPB_ERR_CUDA, "link_probe_run", cudaGetErrorString(e));
+  const double s = (t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec);
+  *gbs = (double) p->bytes / s / 1e9;
+  if (seconds)
+    *seconds = s;
+  return ESPB_OK;
+}

@@ -409,6 +409,12 @@ int espb_measure_host_link(int n_devices, const int *devices, size_t bytes, size
 /* one pattern (0: H2D alone, 1: D2H alone, 2: both at once) on the current device, GB/s per direction: lets one process
  * per GPU run the same pattern at the same time, with a barrier of the caller's between patterns */
 int espb_measure_host_link_pattern(int pattern, size_t bytes, size_t slab_bytes, int reps, double *gbs);
+/* prepared form: buffers page-locked once (that takes a process-dependent second), then single timed runs that the
+ * caller can start on a barrier of its own — so that one process per GPU measures the link while all others copy */
+typedef struct EspbLinkProbe EspbLinkProbe;
+EspbLinkProbe *espb_link_probe_create(size_t bytes, size_t slab_bytes);
+int espb_link_probe_run(EspbLinkProbe *p, int pattern, double *gbs, double *seconds);
+void espb_link_probe_free(EspbLinkProbe *p);
 
 /* one process drives all devices: ncclCommInitAll over `devices` (NULL: 0 .. n_devices-1; n_devices <= 0: all) */
 typedef struct EspbMulti EspbMulti;
