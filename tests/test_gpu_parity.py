@@ -868,3 +868,35 @@ def test_growing_calls_without_synchronisation(oracle, ns):
             pos += n
     b.free()
     L.espb_stream_destroy(stream)
+
+
+def test_bad_ratios_are_refused_not_executed():
+    """A NaN / non-positive / infinite ratio, or one so small that a single pass of 32 outputs spans more input than
+    the kernel's per-CTA chunk table, must fail the call (ESPB_ERR_ARG through espb_last_status) and leave the context
+    usable — not index shared memory out of bounds."""
+    L = espb.lib()
+    ns, ch, taps = 70, 2, 256          # 140 series: the standard kernel (chunk table in shared memory)
+    x = np.stack([noise(3000, ch, stream=s) for s in range(ns)])
+    b = espb.ResampleBatch(ns, ch, taps, 256, 1.0, 3, mode=espb.MODE_EXACT)
+    b.advance(taps / 2)
+    d_in, d_out = espb.DeviceBuffer.from_numpy(x), espb.DeviceBuffer(ns * 4000 * ch * 4)
+    for bad in (float("nan"), 0.0, -1.0, float("inf")):
+        with pytest.raises(espb.EspbError):
+            b.process_interleaved_dev(d_in.ptr, 3000 * ch, 3000, d_out.ptr, 4000 * ch, 4000, f32(bad))
+        assert L.espb_last_status() == -1  # ESPB_ERR_ARG
+    # ratio 0.002 over 40000 frames: 80 outputs, a pass of 32 of them spans 16000 input rows = 500 chunks > 320
+    d_long = espb.DeviceBuffer(ns * 40000 * ch * 4)
+    d_long.zero()
+    with pytest.raises(espb.EspbError):
+        b.process_interleaved_dev(d_long.ptr, 40000 * ch, 40000, d_out.ptr, 4000 * ch, 4000, f32(0.002))
+    assert L.espb_last_status() == -1
+    # the context is untouched: the next good call equals a fresh oracle context
+    y, used, gen = b.process_interleaved(x, 3300, f32(48000) / f32(44100))
+    o = espb  # noqa: F841
+    from oracle_lib import Oracle
+    oc = Oracle().resampler(ch, taps, 256, 1.0, 3)
+    oc.advance(taps / 2)
+    yo, uo, go = oc.process_interleaved(x[5], 3300, f32(48000) / f32(44100))
+    assert (used, gen) == (uo, go) and bits_equal(y[5], yo)
+    assert L.espb_last_status() == 0
+    b.free()
