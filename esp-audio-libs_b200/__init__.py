@@ -6,7 +6,7 @@ tests and bench.py use.  There is no CPU compute path: importing works anywhere 
 `-m "not gpu"` tests check the exported symbols), computing needs a B200.
 """
 from .capi import (BLACKMAN_HARRIS, INCLUDE_LOWPASS, MODE_EXACT, MODE_FAST,  # noqa: F401
-                   OPT_KERNEL_TIMING, OPT_PLAN_CACHE, SUBSAMPLE_INTERPOLATE,
+                   OPT_KERNEL_TIMING, OPT_OVERLAP_STAGING, OPT_PLAN_CACHE, SUBSAMPLE_INTERPOLATE,
                    BiquadBatch, DeviceBuffer, EspbError, PinnedBuffer, ResampleBatch, Resampler, biquad_highpass,
                    biquad_lowpass, checksum_u32, declared_symbols, dsps_add_s16, dsps_mulc_s16, device_count, device_info, float_to_quantized,
                    launch_count, lib, library_path, measure_fp32_fma_peak, measure_fp32_fma_peak2, measure_fp32_tile_pattern, plan_filter_bank, plan_passes, plan_policy,

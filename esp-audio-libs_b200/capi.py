@@ -13,7 +13,7 @@ _HEADER = os.path.join(_ROOT, "include", "esp_audio_b200.h")
 
 SUBSAMPLE_INTERPOLATE, BLACKMAN_HARRIS, INCLUDE_LOWPASS = 0x1, 0x2, 0x4
 MODE_FAST, MODE_EXACT = 0, 1
-OPT_PLAN_CACHE, OPT_KERNEL_TIMING = 1, 2
+OPT_PLAN_CACHE, OPT_KERNEL_TIMING, OPT_OVERLAP_STAGING = 1, 2, 3
 
 
 class EspbError(RuntimeError):

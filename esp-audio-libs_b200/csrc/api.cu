@@ -392,6 +392,11 @@ struct EspbResampleBatch {
   PodBuffer<int32_t> spare_pcb;
   cudaEvent_t spare_uploaded = nullptr;
   bool spare_upload_pending = false;
+  // staging overlap: the resampler starts while the transposing kernel is still running and waits
+  // per CTA on per-row-tile counters; device-buffer calls of the standard kernel only.  ESPB_OVERLAP=0 switches it off
+  int overlap_staging = 1;
+  int stage_ctas_per_sm = 2;  // (negative: that many CTAs in all)
+  DevBuf d_ready;  // [row tiles] counters of the current call
   int n_series() const { return num_streams * channels; }
 };
 
@@ -762,7 +767,8 @@ constexpr int kSmallCallFrames = 4096;  // calls up to this many input frames ar
 int run_series_range(EspbResampleBatch *c, int series_first, int n_series, const float *in, const EspbLayout &il,
                      float *out, const EspbLayout &ol, int n_in, cudaStream_t stream, bool g_preexpanded,
                      const StageFilter *pre = nullptr, const StageFilter *post = nullptr,
-                     const PcmIn *pcm_in = nullptr, const PcmOut *pcm_out = nullptr, const PtrIO *ptrs = nullptr) {
+                     const PcmIn *pcm_in = nullptr, const PcmOut *pcm_out = nullptr, const PtrIO *ptrs = nullptr,
+                     bool overlap_ok = false) {
   const int taps = c->geo.taps;
   const int g0 = series_first / kSeriesPerRow, ng = (n_series + kSeriesPerRow - 1) / kSeriesPerRow;
   const int64_t rows = c->xt_rows;
@@ -824,6 +830,7 @@ int run_series_range(EspbResampleBatch *c, int series_first, int n_series, const
     return ESPB_OK;
   };
   const bool pre_on = pre && pre->params && n_in > 0;
+  int ready_tiles = 0;  // > 0: the staging kernel just enqueued signals this many row tiles (overlap with the resampler)
   const bool pre_blocks = pre_on && pre->block_rows > 0 && n_in > pre->block_rows;
   if (direct) {
     // (no staging)
@@ -840,7 +847,26 @@ int run_series_range(EspbResampleBatch *c, int series_first, int n_series, const
                             pre->block_rows, pre->warm_rows, stream, pre->blk_state, pre->mismatches),
            "biquad kernel");
   } else {
-    if (!small_stage)
+    // Long float calls of the standard kernel: the transposition signals its progress per row tile and the resampler
+    // is launched right behind it as a programmatic dependent (nothing may be enqueued between the two), so the
+    // HBM-bound staging hides behind the FMA-bound kernel instead of preceding it.
+    if (overlap_ok && c->overlap_staging && !small_stage && !pcm_in && !ptrs && !pre_on && !c->fs_call &&
+        !c->non_interp && !c->kernel_timing && c->sched.generated > 0 &&
+        passes_per_slab(c) >= c->plan.n_passes() && n_in >= 8 * kReadyTileRows) {
+      CU_TRY(c->d_ready.reserve((size_t) (n_in / kReadyTileRows + 1) * sizeof(int)), "cudaMalloc ready counters");
+      if (c->aux_join_pending) {  // the coefficients were expanded on the side stream
+        CU_TRY(cudaStreamWaitEvent(stream, c->aux_join, 0), "cudaStreamWaitEvent");
+        c->aux_join_pending = false;
+      } else if (!g_preexpanded) {  // (a no-op when the cached plan's coefficients are still resident)
+        if (int rc = ensure_g(c, 0, (int) c->plan.chunks.size(), stream))
+          return rc;
+      }
+      CU_TRY(launch_transpose_flags(in, il.stream_stride, il.channel_stride, il.frame_stride, c->channels, n_series,
+                                    n_in, x_new, rows, taps, kChunkRows, c->d_ready.as<int>(), c->stage_ctas_per_sm,
+                                    stream, &ready_tiles),
+             "transpose kernel");
+    }
+    if (!small_stage && ready_tiles == 0)
       if (int rc = stage_input(x_new, kChunkRows))
         return rc;
     if (pre_on)  // resampler.cpp:126-133, on the staged rows [taps, taps + n_in)
@@ -910,6 +936,11 @@ int run_series_range(EspbResampleBatch *c, int series_first, int n_series, const
     p.channels = c->channels;
     p.n_out = (int) c->sched.generated;
     p.taps = taps;
+    if (ready_tiles > 0) {
+      p.ready = c->d_ready.as<int>();
+      p.ready_tiles = ready_tiles;
+      p.ready_target = ng;
+    }
     const int n_passes = c->plan.n_passes();
     const int pps = passes_per_slab(c);
     if (c->aux_join_pending) {  // the coefficients were expanded on the side stream
@@ -1082,6 +1113,8 @@ EspbResampleBatch *espb_resampleInit(int num_streams, int numChannels, int numTa
     return nullptr;
   }
   c->fs_policy = (int) env_long("ESPB_FS", -1);
+  c->overlap_staging = (int) env_long("ESPB_OVERLAP", 1);
+  c->stage_ctas_per_sm = (int) env_long("ESPB_STAGE_CTAS", 2);
   if (e == cudaSuccess && c->n_series() <= kFsMaxSeries && c->fs_policy != 0) {  // few-series form: slice-major bank
     c->fs_kt = fs_slice_taps(numTaps, numFilters);
     c->fs_slice = fs_slice_floats(numFilters, c->fs_kt);
@@ -1114,6 +1147,7 @@ void espb_resampleFree(EspbResampleBatch *c) {
   c->yt2.release();
   c->d_outs.release();
   c->d_segs.release();
+  c->d_ready.release();
   c->d_tables.release();
   if (c->aux)
     cudaStreamDestroy(c->aux);
@@ -1190,6 +1224,9 @@ int espb_resampleSetOption(EspbResampleBatch *c, int option, int value) {
     case ESPB_OPT_KERNEL_TIMING:
       c->kernel_timing = value != 0;
       c->ev_used = 0;
+      return ESPB_OK;
+    case ESPB_OPT_OVERLAP_STAGING:
+      c->overlap_staging = value != 0;
       return ESPB_OK;
     default:
       return fail(ESPB_ERR_ARG, "resampleSetOption: unknown option");
@@ -1272,7 +1309,8 @@ EspbResampleResult espb_resampleProcessLayout(EspbResampleBatch *c, const float 
     c->aux_join_pending = true;
     pre = true;
   }
-  if (run_series_range(c, 0, c->n_series(), in, *il, out, *ol, numInputFrames, as_stream(stream), pre) != ESPB_OK)
+  if (run_series_range(c, 0, c->n_series(), in, *il, out, *ol, numInputFrames, as_stream(stream), pre, nullptr, nullptr,
+                       nullptr, nullptr, nullptr, /*overlap_ok=*/true) != ESPB_OK)
     return res;
   res.input_used = c->sched.used;
   res.output_generated = c->sched.generated;

@@ -39,7 +39,13 @@ struct ResampleParams {
   int n_series, channels, n_out, taps;
   int pass_first, pass_end, passes_per_cta, g_chunk_base;
   int out_vec;  // OutVec: set by launch_resample from the output layout
+  // staging overlap: if not NULL, input frames [t * 32, t * 32 + 32) of every group are in xt once ready[t] has
+  // reached ready_target (t < ready_tiles; rows past the last tile were staged before the launch) — the kernel was
+  // launched as a programmatic dependent of the transposing kernel and waits per CTA for the tiles it reads
+  const int *ready;
+  int ready_tiles, ready_target;
 };
+constexpr int kReadyTileRows = 32;
 // Direct input (interleaved stereo float; resample_direct_kernel.cu): rows j >= 0 come from the caller's buffer
 // through a TMA tensor map (dim0 = frame x channel floats, dim1 = stream; box 32 floats x 64 streams, 128-byte
 // swizzle, zero fill outside).  Kept out of ResampleParams: the standard kernel's register allocation is sensitive
@@ -74,6 +80,10 @@ cudaError_t launch_resample_direct(const ResampleParams &p, const DirectInput &d
 cudaError_t launch_transpose(const float *in, int64_t in_ss, int64_t in_cs, int64_t in_fs, int channels, int n_series,
                              int n_in, float *xt, int64_t rows_cap, int row_first, int pad_rows,
                              cudaStream_t stream);
+// staging arranged for overlap with the resampler launch that must follow immediately (ResampleParams::ready)
+cudaError_t launch_transpose_flags(const float *in, int64_t in_ss, int64_t in_cs, int64_t in_fs, int channels,
+                                   int n_series, int n_in, float *xt, int64_t rows_cap, int row_first, int pad_rows,
+                                   int *ready, int ctas_per_sm, cudaStream_t stream, int *n_tiles);
 
 // Fused clock groups (groups.cu): one launch serves every group of a set; blockIdx.y selects the group.  Offsets are
 // in floats / entries relative to the pointers in FsParams.

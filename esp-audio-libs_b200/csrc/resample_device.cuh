@@ -61,6 +61,51 @@ __device__ __forceinline__ void cp_async_16(void *dst_smem, const void *src) {
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
 
+// ---- staging overlap: the resampler is launched as a programmatic dependent of the transposing
+// kernel and starts while that kernel is still filling xt; a CTA waits for the row tiles it reads on per-tile
+// counters the transposing CTAs bump (release) after their stores.
+__device__ __forceinline__ int ld_acquire_gpu(const int *p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+// generic-proxy writes (made visible by the acquire above) -> async-proxy reads (the TMA bulk copies of xt)
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;\n" ::: "memory"); }
+// primary side: dependants may be scheduled as soon as every CTA of this grid has got here
+__device__ __forceinline__ void grid_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory"); }
+
+// L2 eviction-priority policies (createpolicy) and accesses that carry one
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;\n" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;\n" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ float4 ld_global_hint(const float4 *p, uint64_t pol) {
+  float4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;\n"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(p), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ void st_global_hint(float4 *p, float4 v, uint64_t pol) {
+  asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;\n" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z),
+               "f"(v.w), "l"(pol)
+               : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s_hint(void *dst_smem, const void *src, uint32_t bytes, uint64_t *bar,
+                                                  uint64_t pol) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;\n" ::"r"(
+          smem_u32(dst_smem)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol)
+      : "memory");
+}
+
 // Counting arrival on a shared-memory word.  Relaxed is enough: every shared-memory load of the stage
 // has already returned its value (the FMAs consumed them) when the warp gets here, so nothing of this
 // warp can still observe the refill; the refill itself is published by the mbarrier arrive (release).

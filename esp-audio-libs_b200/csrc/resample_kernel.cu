@@ -204,16 +204,14 @@ constexpr int TF_THREADS = 256;
 // Fast path: interleaved input (channel stride 1, frame stride CH) with CH in {1,2,4,8}, or planar
 // input (frame stride 1; CH = 1 and one "stream" per series), 16-byte aligned rows, full tiles only.
 // VEC-float loads along time (4, 2 or 1 as the alignment of the rows allows), index arithmetic by shifts only.
-template <int CH, bool PLANAR, int VEC>
-__global__ void __launch_bounds__(TF_THREADS)
-    espb_transpose_fast_kernel(const float *__restrict__ in, int64_t in_ss, int64_t in_cs, int channels,
-                               int n_series, float *__restrict__ xt, int64_t rows_cap, int row_first) {
-  __shared__ float tile[TF_ROWS][SGN + 1];
-  const int g = blockIdx.x;
-  const int j0 = blockIdx.y * TF_ROWS;
+// One tile: ROWS frames x 128 series of group g starting at frame j0, through `tile` (ROWS x (SGN + 1) floats).
+template <int CH, bool PLANAR, int VEC, int ROWS>
+__device__ __forceinline__ void transpose_fast_tile(float (*tile)[SGN + 1], int g, int j0, const float *__restrict__ in,
+                                                    int64_t in_ss, int64_t in_cs, int channels, int n_series,
+                                                    float *__restrict__ xt, int64_t rows_cap, int row_first) {
   const int tid = threadIdx.x;
-  constexpr int UNITS = SGN / CH;         // contiguous runs per group (streams, or series when planar)
-  constexpr int V_PER_UNIT = TF_ROWS * CH / VEC;  // vectors per run
+  constexpr int UNITS = SGN / CH;              // contiguous runs per group (streams, or series when planar)
+  constexpr int V_PER_UNIT = ROWS * CH / VEC;  // vectors per run
 #pragma unroll 4
   for (int v = tid; v < UNITS * V_PER_UNIT; v += TF_THREADS) {
     const int unit = v / V_PER_UNIT, off4 = v % V_PER_UNIT;  // powers of two: shifts
@@ -250,9 +248,81 @@ __global__ void __launch_bounds__(TF_THREADS)
   __syncthreads();
   float4 *dst = reinterpret_cast<float4 *>(xt + ((int64_t) g * rows_cap + row_first + j0) * SGN);
 #pragma unroll 4
-  for (int i = tid; i < TF_ROWS * (SGN / 4); i += TF_THREADS) {
+  for (int i = tid; i < ROWS * (SGN / 4); i += TF_THREADS) {
     const int t = i / (SGN / 4), c4 = i % (SGN / 4);
     dst[i] = make_float4(tile[t][c4 * 4], tile[t][c4 * 4 + 1], tile[t][c4 * 4 + 2], tile[t][c4 * 4 + 3]);
+  }
+}
+
+template <int CH, bool PLANAR, int VEC>
+__global__ void __launch_bounds__(TF_THREADS)
+    espb_transpose_fast_kernel(const float *__restrict__ in, int64_t in_ss, int64_t in_cs, int channels,
+                               int n_series, float *__restrict__ xt, int64_t rows_cap, int row_first) {
+  __shared__ float tile[TF_ROWS][SGN + 1];
+  transpose_fast_tile<CH, PLANAR, VEC, TF_ROWS>(tile, blockIdx.x, blockIdx.y * TF_ROWS, in, in_ss, in_cs, channels,
+                                                n_series, xt, rows_cap, row_first);
+}
+
+// The same tiles (32 rows each) from a resident grid that signals its progress: CTAs stride over the tiles in time
+// order (all groups of row tile 0, then of row tile 1, ...) and bump ready[row tile] once a tile's stores are out.
+// The resampler kernel is launched behind it as a programmatic dependent (griddepcontrol.launch_dependents at the
+// top: it may start as soon as every CTA of this grid is running) and its CTAs wait on those counters for the rows
+// they read, so the FMA-bound kernel starts a few row tiles after this one and hides part of it.
+// This grid never waits for anything and is fully resident (two CTAs per SM): the dependants cannot starve it.
+// POLICY: the caller's frames are read once — loads carry an L2 evict-first policy.
+// Deliberately NOT software-pipelined: a 512-thread version with the next tile's loads in flight during the stores
+// finishes in half the time but slows the resampler next to it by more than it saves (measured, §4.5) — what the
+// resampler pays for is the memory traffic beside its own latency-critical TMA loads, not the occupied slot.
+template <int CH, bool PLANAR, bool POLICY>
+__global__ void __launch_bounds__(TF_THREADS)
+    espb_transpose_flags_kernel(const float *__restrict__ in, int64_t in_ss, int64_t in_cs, int channels, int n_series,
+                                float *__restrict__ xt, int64_t rows_cap, int row_first, int n_groups, int n_tiles,
+                                int *__restrict__ ready) {
+  constexpr int ROWS = kReadyTileRows;
+  __shared__ float tile[ROWS][SGN + 1];
+  grid_launch_dependents();
+  const int tid = threadIdx.x;
+  constexpr int UNITS = SGN / CH;            // contiguous runs per group (streams, or series when planar)
+  constexpr int V_PER_UNIT = ROWS * CH / 4;  // float4 per run
+  uint64_t pol = 0;
+  if (POLICY)
+    pol = l2_policy_evict_first();
+  for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+    const int y = t / n_groups, g = t - y * n_groups, j0 = y * ROWS;
+#pragma unroll 4
+    for (int v = tid; v < UNITS * V_PER_UNIT; v += TF_THREADS) {
+      const int unit = v / V_PER_UNIT, off4 = v % V_PER_UNIT;  // powers of two: shifts
+      const int q0 = g * SGN + unit * CH;                       // first series of the run
+      float4 x = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+      if (q0 < n_series) {
+        const float *src;
+        if (PLANAR) {
+          const int st = q0 / channels, ch = q0 - st * channels;
+          src = in + (int64_t) st * in_ss + (int64_t) ch * in_cs + j0;
+        } else {
+          src = in + (int64_t) (q0 / CH) * in_ss + (int64_t) j0 * CH;
+        }
+        x = POLICY ? ld_global_hint(reinterpret_cast<const float4 *>(src) + off4, pol)
+                   : __ldg(reinterpret_cast<const float4 *>(src) + off4);
+      }
+      const float xv[4] = {x.x, x.y, x.z, x.w};
+      const int e0 = off4 * 4;
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        tile[(e0 + k) / CH][unit * CH + ((e0 + k) % CH)] = xv[k];
+    }
+    __syncthreads();
+    float4 *dst = reinterpret_cast<float4 *>(xt + ((int64_t) g * rows_cap + row_first + j0) * SGN);
+#pragma unroll 4
+    for (int i = tid; i < ROWS * (SGN / 4); i += TF_THREADS) {
+      const int row = i / (SGN / 4), c4 = i % (SGN / 4);
+      dst[i] = make_float4(tile[row][c4 * 4], tile[row][c4 * 4 + 1], tile[row][c4 * 4 + 2], tile[row][c4 * 4 + 3]);
+    }
+    __syncthreads();  // every thread's stores are issued (and the tile may be overwritten)
+    if (tid == 0) {
+      __threadfence();  // ... and visible device-wide before the count
+      atomicAdd(ready + y, 1);
+    }
   }
 }
 
@@ -492,6 +562,11 @@ __global__ void __launch_bounds__(256)
 // ---------------------------------------------------------------------------------
 // BPP: output blocks (= warps) per pass; NST: ring stages.  <8,3>: two 8-warp CTAs per SM; <4,2>: four 4-warp
 // CTAs per SM (shorter passes: less idle time at the pass edges, twice the x traffic from L2).
+// (Results in the caller's layout are written once and never read back, but streaming / evict-first stores are not
+// the answer: __stcs and st.global.L2::cache_hint(evict_first) were both measured 5 % slower — 7.39 against 7.02 ms —
+// a lane's 64 contiguous bytes leave as four 16-byte stores and the hinted forms give up their merging in L2.)
+__device__ __forceinline__ void out_store4(float4 *p, float4 v) { *p = v; }
+
 template <int BPP, int NST, int CJ, bool EXACT, bool TMCAP>
 __global__ void __launch_bounds__(BPP * 32, 16 / BPP) espb_resample_kernel(const ResampleParams p) {
   constexpr int NTHREADS = BPP * 32;
@@ -578,6 +653,28 @@ __global__ void __launch_bounds__(BPP * 32, 16 / BPP) espb_resample_kernel(const
     tma_bulk_g2s(gs + st * GS_STAGE, p.G + (size_t) (hdr[0] + c) * GS_STAGE, G_BYTES, &full[st]);
     tma_bulk_g2s(xs + st * XS_STAGE, xt_group + (int64_t) (jtab[c] + T) * SGN, X_BYTES, &full[st]);
   };
+  // Staging overlap: this grid may have started while the transposing kernel is still writing xt.  Wait for the
+  // row tiles this CTA reads (one poller per tile; the writers never wait for anything and are all resident, so
+  // this always ends — the trap only turns a protocol error into a loud failure instead of a hung device).
+  if (p.ready != nullptr && n_chunks > 0) {
+    const int j_hi = jtab[n_chunks - 1] + CJ - 1;
+    if (j_hi >= 0) {
+      const int j_lo = jtab[0];
+      const int y_lo = j_lo > 0 ? j_lo / kReadyTileRows : 0;
+      int y_hi = j_hi / kReadyTileRows;
+      y_hi = y_hi < p.ready_tiles ? y_hi : p.ready_tiles - 1;
+      for (int y = y_lo + tid; y <= y_hi; y += NTHREADS) {
+        const long long t0 = clock64();
+        while (ld_acquire_gpu(p.ready + y) < p.ready_target) {
+          __nanosleep(200);
+          if (clock64() - t0 > (4ll << 31))  // ~4 s
+            __trap();
+        }
+      }
+    }
+    __syncthreads();
+    fence_proxy_async();
+  }
   if (tid == 0)
     for (int c = 0; c < STAGES && c < n_chunks; ++c)
       issue_chunk(c);
@@ -709,13 +806,13 @@ __global__ void __launch_bounds__(BPP * 32, 16 / BPP) espb_resample_kernel(const
         if (series0 < p.n_series) {
 #pragma unroll
           for (int k = 0; k < NB / 2; ++k)
-            reinterpret_cast<float4 *>(dst)[k] = make_float4(v[0][2 * k], v[1][2 * k], v[0][2 * k + 1], v[1][2 * k + 1]);
+            out_store4(reinterpret_cast<float4 *>(dst) + k, make_float4(v[0][2 * k], v[1][2 * k], v[0][2 * k + 1], v[1][2 * k + 1]));
         }
         if (series0 + 2 < p.n_series) {
           dst += p.out_ss;
 #pragma unroll
           for (int k = 0; k < NB / 2; ++k)
-            reinterpret_cast<float4 *>(dst)[k] = make_float4(v[2][2 * k], v[3][2 * k], v[2][2 * k + 1], v[3][2 * k + 1]);
+            out_store4(reinterpret_cast<float4 *>(dst) + k, make_float4(v[2][2 * k], v[3][2 * k], v[2][2 * k + 1], v[3][2 * k + 1]));
         }
       } else if (p.out_vec == kOutVecFrame4 && o0 + NB <= p.n_out) {
         // interleaved, channel count a multiple of 4: the lane's 4 series are 16 contiguous bytes of every frame
@@ -724,7 +821,7 @@ __global__ void __launch_bounds__(BPP * 32, 16 / BPP) espb_resample_kernel(const
           float *dst = p.out + (int64_t) sidx * p.out_ss + ch + (int64_t) o0 * p.channels;
 #pragma unroll
           for (int n = 0; n < NB; ++n)
-            *reinterpret_cast<float4 *>(dst + n * p.channels) = make_float4(v[0][n], v[1][n], v[2][n], v[3][n]);
+            out_store4(reinterpret_cast<float4 *>(dst + n * p.channels), make_float4(v[0][n], v[1][n], v[2][n], v[3][n]));
         }
       } else if (p.out_vec == kOutVecPlanar && o0 + NB <= p.n_out) {
         // frames contiguous per series (planar, or interleaved mono): 8 frames = 32 contiguous bytes per series
@@ -734,8 +831,8 @@ __global__ void __launch_bounds__(BPP * 32, 16 / BPP) espb_resample_kernel(const
           if (series < p.n_series) {
             const int sidx = series / p.channels, ch = series - sidx * p.channels;
             float4 *dst = reinterpret_cast<float4 *>(p.out + (int64_t) sidx * p.out_ss + (int64_t) ch * p.out_cs + o0);
-            dst[0] = make_float4(v[e][0], v[e][1], v[e][2], v[e][3]);
-            dst[1] = make_float4(v[e][4], v[e][5], v[e][6], v[e][7]);
+            out_store4(dst, make_float4(v[e][0], v[e][1], v[e][2], v[e][3]));
+            out_store4(dst + 1, make_float4(v[e][4], v[e][5], v[e][6], v[e][7]));
           }
         }
       } else {  // any layout, partial blocks
@@ -862,6 +959,79 @@ cudaError_t launch_transpose(const float *in, int64_t in_ss, int64_t in_cs, int6
                                                     row_first, fast_rows, pad_rows);
     count_launch();
   }
+  return cudaGetLastError();
+}
+
+// The staging of a long call arranged for overlap with the resampler (see espb_transpose_flags_kernel): everything
+// the flagged kernel does not cover (frames past the last full 32-row tile, the zero padding) goes first, then the
+// counters are cleared, then the flagged kernel — which must be the last thing enqueued before the resampler.
+// *n_tiles = row tiles it will signal; 0 = layout not covered, nothing was enqueued (use launch_transpose).
+cudaError_t launch_transpose_flags(const float *in, int64_t in_ss, int64_t in_cs, int64_t in_fs, int channels,
+                                   int n_series, int n_in, float *xt, int64_t rows_cap, int row_first, int pad_rows,
+                                   int *ready, int ctas_per_sm, cudaStream_t stream, int *n_tiles) {
+  *n_tiles = 0;
+  const int n_groups = (n_series + SGN - 1) / SGN;
+  const bool interleaved = (in_cs == 1 && in_fs == channels);
+  const bool planar = (in_fs == 1);
+  const bool cs_ok4 = interleaved || in_cs % 4 == 0;
+  const bool covered = (interleaved && (channels == 1 || channels == 2 || channels == 4 || channels == 8)) || planar;
+  if (n_groups <= 0 || n_in < kReadyTileRows || !covered || (uintptr_t) in % 16 != 0 || in_ss % 4 != 0 || !cs_ok4)
+    return cudaSuccess;
+  const int tiles_y = n_in / kReadyTileRows, fast_rows = tiles_y * kReadyTileRows;
+  const int rest = n_in + pad_rows - fast_rows;
+  if (rest > 0) {
+    dim3 grid(n_groups, (rest + TR_ROWS - 1) / TR_ROWS);
+    espb_transpose_kernel<<<grid, 256, 0, stream>>>(in, in_ss, in_cs, in_fs, channels, n_series, n_in, xt, rows_cap,
+                                                    row_first, fast_rows, pad_rows);
+    count_launch();
+  }
+  cudaError_t e = cudaMemsetAsync(ready, 0, (size_t) tiles_y * sizeof(int), stream);
+  if (e != cudaSuccess)
+    return e;
+  int sms = 148, dev = 0;
+  if (cudaGetDevice(&dev) == cudaSuccess)
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const long total = (long) tiles_y * n_groups;
+  // ctas_per_sm > 0: that many per SM (at most 4); < 0: -ctas_per_sm CTAs in all (never more than one wave)
+  long resident = ctas_per_sm < 0 ? -ctas_per_sm : (long) sms * (ctas_per_sm < 1 ? 1 : (ctas_per_sm > 4 ? 4 : ctas_per_sm));
+  if (resident > (long) sms * 4)
+    resident = (long) sms * 4;
+  static const bool evict_first = getenv("ESPB_STAGE_POLICY") == nullptr || atoi(getenv("ESPB_STAGE_POLICY")) != 0;
+  const int grid = (int) (total < resident ? total : resident);
+  // The resampler's CTAs can only join an SM that is already configured for their shared-memory carve-out (an SM
+  // re-partitions L1 / shared memory only when idle): run this kernel under the same, maximal, carve-out.
+#define ESPB_TRF1(CH_, PL_, POL_)                                                                               \
+  do {                                                                                                          \
+    static PerDeviceOnce once;                                                                                  \
+    if (once.first())                                                                                           \
+      cudaFuncSetAttribute(espb_transpose_flags_kernel<CH_, PL_, POL_>,                                         \
+                           cudaFuncAttributePreferredSharedMemoryCarveout, (int) cudaSharedmemCarveoutMaxShared); \
+    espb_transpose_flags_kernel<CH_, PL_, POL_><<<grid, TF_THREADS, 0, stream>>>(in, in_ss, in_cs, channels,    \
+                                                                                 n_series, xt, rows_cap,        \
+                                                                                 row_first, n_groups,           \
+                                                                                 (int) total, ready);           \
+  } while (0)
+#define ESPB_TRF(CH_, PL_)        \
+  do {                            \
+    if (evict_first)              \
+      ESPB_TRF1(CH_, PL_, true);  \
+    else                          \
+      ESPB_TRF1(CH_, PL_, false); \
+  } while (0)
+  if (interleaved && channels == 1)
+    ESPB_TRF(1, false);
+  else if (interleaved && channels == 2)
+    ESPB_TRF(2, false);
+  else if (interleaved && channels == 4)
+    ESPB_TRF(4, false);
+  else if (interleaved && channels == 8)
+    ESPB_TRF(8, false);
+  else
+    ESPB_TRF(1, true);
+#undef ESPB_TRF1
+#undef ESPB_TRF
+  count_launch();
+  *n_tiles = tiles_y;
   return cudaGetLastError();
 }
 
@@ -1002,6 +1172,23 @@ static cudaError_t launch_resample_t(const ResampleParams &p, int n_groups, int 
     }
   }
   dim3 grid(n_groups, n_ctas_y);
+  if (p.ready != nullptr) {
+    // programmatic dependent of the kernel launched just before on this stream (espb_transpose_flags_kernel): the
+    // CTAs start while it runs and synchronise with it through p.ready, not through the stream
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(BPP * 32);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, espb_resample_kernel<BPP, NST, CJ, EXACT, TMCAP>, p);
+    count_launch();
+    return e != cudaSuccess ? e : cudaGetLastError();
+  }
   espb_resample_kernel<BPP, NST, CJ, EXACT, TMCAP><<<grid, BPP * 32, smem, stream>>>(p);
   count_launch();
   return cudaGetLastError();

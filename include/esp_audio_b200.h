@@ -108,6 +108,10 @@ int espb_resampleSetMode(EspbResampleBatch *cxt, int mode);            /* ESPB_M
  * resampler kernel (read with espb_resampleGetKernelTime) */
 #define ESPB_OPT_PLAN_CACHE 1
 #define ESPB_OPT_KERNEL_TIMING 2
+/* staging overlap (default on): long device-buffer calls launch the resampler kernel as a programmatic dependent of
+ * the transposing stage, so the HBM-bound staging hides behind the FMA-bound kernel; results are identical either
+ * way.  Kernel timing switches it off for the calls it measures (the events must bracket the kernel alone). */
+#define ESPB_OPT_OVERLAP_STAGING 3
 int espb_resampleSetOption(EspbResampleBatch *cxt, int option, int value);
 /* sum of the resampler-kernel durations recorded since the last query, and their count */
 int espb_resampleGetKernelTime(EspbResampleBatch *cxt, float *total_ms, int *launches);
