@@ -350,6 +350,8 @@ struct EspbResampleBatch {
   // without SUBSAMPLE_INTERPOLATE an output is one dot product: its own kernel and half-size G rows (default geometry)
   bool non_interp = false;
   int g_row_floats() const { return non_interp ? kGRowFloatsNI : kGRowFloats; }
+  // output blocks per pass of the plan and of G (the non-interpolating kernel's 4 warps own two blocks each)
+  int plan_bpp() const { return non_interp ? bpp * kNiBlocksPerWarp : bpp; }
   bool direct_ok = false;    // ESPB_DIRECT=1 switches it on
   // few-series form (resample_fs_kernel.cu): lanes own outputs; chosen per context when n_series <= kFsMaxSeries
   int fs_policy = -1;        // ESPB_FS: 0 never, 1 / unset whenever the geometry allows it
@@ -505,7 +507,7 @@ int prepare_call(EspbResampleBatch *c, int n_in, int n_out, float ratio, cudaStr
     c->plan.pass_chunk_begin.clear();
     c->plan.pass_chunk_begin.push_back(0);
   } else {
-    build_pass_plan(c->sched, c->geo.taps, c->bpp, c->chunk_rows, c->plan, c->direct_call);
+    build_pass_plan(c->sched, c->geo.taps, c->plan_bpp(), c->chunk_rows, c->plan, c->direct_call);
     // the kernel keeps the chunk table of its passes in shared memory: one pass must fit it.  (32 outputs at a
     // ratio below ~0.004 span more than 320 chunks of input — far outside audio use; refused, not truncated.)
     const int limit = max_chunks_per_cta(c->bpp, c->chunk_rows);
@@ -588,7 +590,7 @@ int prepare_call(EspbResampleBatch *c, int n_in, int n_out, float ratio, cudaStr
 // Number of passes per time slab so that the expanded coefficients fit the G budget.
 int passes_per_slab(const EspbResampleBatch *c) {
   const int n_passes = c->plan.n_passes();
-  const size_t chunk_bytes = g_chunk_floats(c->bpp, c->chunk_rows, c->g_row_floats()) * sizeof(float);
+  const size_t chunk_bytes = g_chunk_floats(c->plan_bpp(), c->chunk_rows, c->g_row_floats()) * sizeof(float);
   const size_t total = c->plan.chunks.size() * chunk_bytes;
   if (total <= c->g_budget_bytes || n_passes <= 1)
     return n_passes;
@@ -601,11 +603,11 @@ int passes_per_slab(const EspbResampleBatch *c) {
 int ensure_g(EspbResampleBatch *c, int chunk_first, int chunk_end, cudaStream_t stream) {
   if (c->g_resident_first == chunk_first && c->g_resident_end == chunk_end)
     return ESPB_OK;
-  const size_t chunk_floats = g_chunk_floats(c->bpp, c->chunk_rows, c->g_row_floats());
+  const size_t chunk_floats = g_chunk_floats(c->plan_bpp(), c->chunk_rows, c->g_row_floats());
   CU_TRY(c->d_G.reserve((size_t) (chunk_end - chunk_first) * chunk_floats * sizeof(float)), "cudaMalloc G");
   CU_TRY(launch_expand(c->bank.as<float>(), c->d_outs.as<OutEntry>(), c->p_chunks,
                        c->d_G.as<float>(), chunk_first, chunk_end - chunk_first, (int) c->sched.generated,
-                       c->geo.taps, c->bpp, c->chunk_rows, c->direct_call, stream, c->g_row_floats()),
+                       c->geo.taps, c->plan_bpp(), c->chunk_rows, c->direct_call, stream, c->g_row_floats()),
          "expand kernel");
   c->g_resident_first = chunk_first;
   c->g_resident_end = chunk_end;

@@ -10,6 +10,7 @@ constexpr int kChunkRows = 40;        // most input frames staged per pipeline s
 constexpr int kSeriesPerRow = 128;    // series (stream x channel) per warp row: 32 lanes x 4
 constexpr int kGRowFloats = 2 * kOutputsPerBlock;  // 16 coefficients per (row, output block)
 constexpr int kGRowFloatsNI = kOutputsPerBlock;    // 8 in the non-interpolating form (one filter per output)
+constexpr int kNiBlocksPerWarp = 2;  // ... whose warps own two adjacent blocks each: its pass plan has 8 blocks per pass
 // chunk-table entries a CTA caches in shared memory (fewer for the 4-warp variant: four CTAs share an SM)
 #ifdef __CUDACC__
 #define ESPB_HD __host__ __device__
