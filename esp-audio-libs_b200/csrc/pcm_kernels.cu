@@ -8,6 +8,7 @@
 // is undefined behaviour in the reference; here it saturates).
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "common.hpp"
 #include "kernels.hpp"
@@ -75,9 +76,17 @@ __global__ void __launch_bounds__(256)
   for (uint32_t g = blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += stride) {
     const uint32_t *wp = reinterpret_cast<const uint32_t *>(irow) + (size_t) g * NBYTES;
     uint32_t w[NBYTES];
+    if (NBYTES == 2 && vec_ok == 2) {  // (16-byte aligned rows: a group's 8 bytes are one 64-bit load)
+      const uint2 t = __ldg(reinterpret_cast<const uint2 *>(wp));
+      w[0] = t.x, w[NBYTES > 1 ? 1 : 0] = t.y;
+    } else if (NBYTES == 4 && vec_ok == 2) {
+      const uint4 t = __ldg(reinterpret_cast<const uint4 *>(wp));
+      w[0] = t.x, w[NBYTES > 1 ? 1 : 0] = t.y, w[NBYTES > 2 ? 2 : 0] = t.z, w[NBYTES > 3 ? 3 : 0] = t.w;
+    } else {
 #pragma unroll
-    for (int i = 0; i < NBYTES; ++i)
-      w[i] = __ldg(wp + i);
+      for (int i = 0; i < NBYTES; ++i)
+        w[i] = __ldg(wp + i);
+    }
     int32_t v[4];
     decode_words<NBYTES>(w, v);
     float4 f;
@@ -351,7 +360,11 @@ inline unsigned grid_x_for(uint32_t n, int rows) {
   uint64_t want = ((uint64_t) n / 4 + 255) / 256;
   if (want < 1)
     want = 1;
-  const uint64_t cap = rows >= 148 * 8 ? 4 : (148 * 16 + rows - 1) / rows;
+  // (grid-stride loops over FEW resident CTAs were the reason these kernels sat at 0.81-0.88 of the copy peak: with
+  //  16 CTAs per SM every thread walks ~55 iterations and the whole grid touches one narrow moving window of the
+  //  buffers; 512 per SM — a few iterations per thread — measured 0.95-1.08 for all six conversions)
+  static const int per_sm = getenv("ESPB_PCM_CTAS") ? atoi(getenv("ESPB_PCM_CTAS")) : 512;
+  const uint64_t cap = rows >= 148 * 8 ? 4 : (148 * per_sm + rows - 1) / rows;
   if (want > cap)
     want = cap;
   return (unsigned) want;
