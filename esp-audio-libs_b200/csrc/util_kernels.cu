@@ -187,8 +187,8 @@ cudaError_t launch_checksum(const uint32_t *words, uint64_t n, unsigned long lon
   if (n == 0)
     return cudaSuccess;
   uint64_t blocks = (n + 256 * 8 - 1) / (256 * 8);
-  if (blocks > 148 * 16)
-    blocks = 148 * 16;
+  if (blocks > 148 * 128)  // (many short grid-stride loops rather than few long ones: pcm_kernels.cu:grid_x_for)
+    blocks = 148 * 128;
   espb_checksum_kernel<<<(unsigned) blocks, 256, 0, stream>>>(words, n, sum_dev);
   count_launch();
   return cudaGetLastError();

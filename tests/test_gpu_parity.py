@@ -900,3 +900,47 @@ def test_bad_ratios_are_refused_not_executed():
     assert (used, gen) == (uo, go) and bits_equal(y[5], yo)
     assert L.espb_last_status() == 0
     b.free()
+
+
+@pytest.mark.parametrize("ch,planar,ns", [(2, False, 200), (1, False, 300), (4, False, 70), (2, True, 130), (8, False, 40)])
+def test_staging_overlap_is_bit_identical(oracle, ch, planar, ns):
+    """Long device-buffer calls launch the resampler kernel as a programmatic dependent of the transposing kernel and
+    synchronise per CTA on per-row-tile counters (ESPB_OPT_OVERLAP_STAGING, default on).  Three chained calls of
+    uneven length (not multiples of the 32-row tile, so the tail and the padding take the generic kernel) must give
+    the bytes of the serial order, and sampled streams the oracle's bytes (exact mode)."""
+    taps, filters = 64, 128
+    ratio = f32(48000) / f32(44100)
+    sizes = [4111, 6000, 4500]  # > 4096 frames: the fused small-call staging does not take them
+    total = sum(sizes)
+    x = np.stack([noise(total, ch, stream=900 + s, amp=0.7) for s in range(ns)])  # (ns, total*ch) interleaved
+    outs = {}
+    for overlap in (1, 0):
+        b = espb.ResampleBatch(ns, ch, taps, filters, 1.0, 3, mode=espb.MODE_EXACT)
+        b.set_option(espb.OPT_OVERLAP_STAGING, overlap)
+        b.set_option(espb.OPT_PLAN_CACHE, 0)
+        b.advance(taps / 2)
+        got, pos = [], 0
+        for n in sizes:
+            cap = int(n * float(ratio)) + 8
+            seg = x.reshape(ns, total, ch)[:, pos:pos + n, :]
+            if planar:
+                y, used, gen = b.process_planar(np.ascontiguousarray(seg.transpose(0, 2, 1)), cap, ratio)
+                y = np.ascontiguousarray(y.transpose(0, 2, 1)).reshape(ns, -1)
+            else:
+                y, used, gen = b.process_interleaved(seg.reshape(ns, n * ch), cap, ratio)
+            got.append((np.array(y, copy=True), used, gen))
+            pos += n
+        outs[overlap] = got
+        b.free()
+    for (y1, u1, g1), (y0, u0, g0) in zip(outs[1], outs[0]):
+        assert (u1, g1) == (u0, g0) and bits_equal(y1, y0)
+    for s in (0, ns // 2, ns - 1):
+        o = oracle.resampler(ch, taps, filters, 1.0, 3)
+        o.advance(taps / 2)
+        pos = 0
+        for n, (y1, u1, g1) in zip(sizes, outs[1]):
+            cap = int(n * float(ratio)) + 8
+            yo, uo, go = o.process_interleaved(x[s, pos * ch:(pos + n) * ch], cap, ratio)
+            assert (u1, g1) == (uo, go)
+            assert bits_equal(y1[s][: go * ch], yo), (s, n)
+            pos += n
