@@ -483,6 +483,7 @@ def bench_c5(espb, ranks, stream, peak_tf, link, steps, want_e2e, checks):
         out["gen"], out["last"] = g, gg
 
     ms = timed_steps(espb, ranks, stream, step, steps, 3)
+    ms_by_rank = timed_steps.per_rank
     # the kernel alone, from its own CUDA events, in a second loop (kernel timing switches the staging overlap off)
     ctx.set_option(espb.OPT_KERNEL_TIMING, 1)
     ms_serial = timed_steps(espb, ranks, stream, step, steps, 1)
@@ -501,7 +502,7 @@ def bench_c5(espb, ranks, stream, peak_tf, link, steps, want_e2e, checks):
                        "by stream index over the ranks; 1 s per stream per step as 8 streaming calls of 6000 frames",
            "scaling": "strong", "streams_total": total, "streams_per_rank": ns,
            "value": gen * ch * total / (ms * 1e-3) / 1e6, "unit": "Msamples/s", "ms_per_step": ms,
-           "ms_per_step_by_rank": timed_steps.per_rank, "frames_out_per_step": gen,
+           "ms_per_step_by_rank": ms_by_rank, "frames_out_per_step": gen,
            "roofline": {"kernel": "espb_resample_kernel<BPP=4,STAGES=2,CHUNK_ROWS=32>", "bound": "fp32_fma",
                         "achieved": tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": tf / peak_tf if peak_tf else None,
                         "kernel_ms_per_step": k_ms_step,

@@ -895,7 +895,8 @@ cudaError_t launch_expand(const float *bank, const OutEntry *outs, const ChunkEn
   int sms = 148, dev = 0;
   if (cudaGetDevice(&dev) == cudaSuccess)
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const int grid = n_chunks < sms * 8 ? n_chunks : sms * 8;  // 8 resident CTAs of 256 threads per SM
+  static const int per_sm = getenv("ESPB_EXPAND_CTAS") ? atoi(getenv("ESPB_EXPAND_CTAS")) : 64;
+  const int grid = n_chunks < sms * per_sm ? n_chunks : sms * per_sm;  // (a few chunks per CTA at most)
   espb_expand_kernel<<<grid, kExpandThreads, 0, stream>>>(bank, outs, chunks, G, chunk_first, n_chunks, n_out, taps,
                                                           bpp, chunk_rows, split_at_zero ? 1 : 0, grf);
   count_launch();
