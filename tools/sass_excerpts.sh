@@ -38,5 +38,18 @@ echo; echo "Mnemonic counts: $(count biquad_kernel.cu.o $K 'FFMA |FMUL |FADD |UB
 K=$(cuobjdump -sass $B/resample_direct_kernel.cu.o | grep "Function :" | grep "Lb0E" | head -1 | awk '{print $3}')
 echo; echo "## espb_resample_direct_kernel (opt-in) — TMA tensor copies of the caller's interleaved stereo input"
 echo; echo "Mnemonic counts: $(count resample_direct_kernel.cu.o $K 'FFMA2|UBLKCP|UTMALDG[A-Z.0-9]*')"
+K=_ZN4espb27espb_transpose_flags_kernelILi2ELb0ELb1EEEvPKflliiPfliiiPi
+echo; echo "## Staging overlap: espb_transpose_flags_kernel<CH=2, PLANAR=false, POLICY=true> and the resampler's wait"
+echo; echo "\`PREEXIT\` is \`griddepcontrol.launch_dependents\` (the resampler, launched with the programmatic-stream-serialization"
+echo "attribute, may start as soon as every CTA of this grid has executed it); one tile = four evict-first 128-bit loads and four"
+echo "128-bit stores per thread, then fence + one counting atomic per CTA:"; echo; echo '```'
+sass resample_kernel.cu.o $K | grep -E "PREEXIT|LDG|STG|BAR\.SYNC|MEMBAR|ATOMG|EXIT" | head -20
+echo '```'; echo; echo "The waiting side, once per CTA of espb_resample_kernel<4,2,32,false,false> (acquire load of the tile counter, back-off,"
+echo "trap after ~4 s, then the generic-to-async proxy fence before the first TMA copy of xt):"; echo; echo '```'
+sass resample_kernel.cu.o _ZN4espb20espb_resample_kernelILi4ELi2ELi32ELb0ELb0EEEvNS_14ResampleParamsE | grep -E "STRONG\.GPU|NANOSLEEP|BPT|FENCE\.VIEW\.ASYNC|UBLKCP" | head -8
+echo '```'
+K=_ZN4espb23espb_resample_ni_kernelILi4ELi2ELi32ELb0ELb0EEEvNS_14ResampleParamsE
+echo; echo "## espb_resample_ni_kernel<4, 2, 32, EXACT=false, TMCAP=false> — non-interpolating form, 4 series x 16 outputs per warp"
+echo; echo "Mnemonic counts: $(count resample_ni_kernel.cu.o $K 'FFMA2|UBLKCP|LDS\.128|FFMA ')"
 } > "$OUT"
 echo "wrote $OUT ($(wc -l < "$OUT") lines)"
