@@ -986,7 +986,32 @@ int run_series_range(EspbResampleBatch *c, int series_first, int n_series, const
                             il.frame_stride, c->channels, n_series, taps, x_new, rows, 0, 0, stream),
            "carry transpose");
   }
-  if (tm_out) {
+  bool tail_done = false;
+  if (tm_out && post_on && pcm_out && c->channels == 1 && env_long("ESPB_FUSE_POST", 1) != 0 &&
+      !(post->block_rows > 0 && (int) c->sched.generated > post->block_rows && c->yt2_rows >= c->yt_rows)) {
+    // mono PCM output behind a post-filter (resampler.cpp:142-153): the filter's thread quantises and packs its own
+    // results — one pass over the resampler's time-major output instead of two
+    const int gen = (int) c->sched.generated;
+    cudaError_t e = cudaSuccess;
+    const int fast = launch_biquad_tm_pcm(y_tm, c->yt_rows, 0, gen, n_series, post->sections, *post->params,
+                                          post->state, pcm_out->data, pcm_out->row_bytes, pcm_out->bits,
+                                          pcm_out->clipped, stream, &e);
+    CU_TRY(e, "biquad + quantiser kernel");
+    if (fast > 0) {
+      tail_done = true;
+      if (fast < gen) {  // the last partial chunk came back as filtered floats: generic layout stage + quantiser
+        const int nbytes = (pcm_out->bits + 7) / 8;
+        CU_TRY(launch_untranspose_from(y_tm, c->yt_rows, 0, fast, gen, pcm_out->scratch, pcm_out->scratch_row, 1,
+                                       c->channels, c->channels, n_series, stream),
+               "untranspose kernel");
+        CU_TRY(launch_f2q(pcm_out->scratch + (size_t) fast * c->channels, pcm_out->scratch_row,
+                          pcm_out->data + (size_t) fast * c->channels * nbytes, pcm_out->row_bytes, n_series,
+                          (uint32_t) ((gen - fast) * c->channels), pcm_out->bits, pcm_out->clipped, true, stream),
+               "f2q kernel");
+      }
+    }
+  }
+  if (tm_out && !tail_done) {
     const int gen = (int) c->sched.generated;
     float *y_f = y_tm;
     if (post_on) {  // resampler.cpp:142-149

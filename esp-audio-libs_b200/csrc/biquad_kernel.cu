@@ -35,6 +35,7 @@
 
 #include "common.hpp"
 #include "kernels.hpp"
+#include "pcm_device.cuh"
 
 namespace espb {
 
@@ -212,6 +213,139 @@ __global__ void __launch_bounds__(SGN)
     for (int k = 0; k < NSEC; ++k)
       *reinterpret_cast<float4 *>(state + ((int64_t) q * NSEC + k) * 4) =
           make_float4(sec[k].in_d1, sec[k].in_d2, sec[k].out_d1, sec[k].out_d2);
+  }
+}
+
+// ---------------------------------------------------------------------------------
+// Post-filter + float_to_quantized in ONE pass for mono streams (Resampler::resample's tail, resampler.cpp:142-153:
+// biquad_apply_buffer, then float_to_quantized).  For a mono stream the 32 rows of a chunk are 32 consecutive samples
+// of the series' own output row, so the chunk can leave as packed PCM straight from the ring: one read of 4 bytes
+// and one write of NBYTES bytes per sample instead of 4 + 4 (filter in place) + 4 + NBYTES (quantising layout stage).
+// The recurrence is latency-bound with one warp per scheduler, so the quantisation must not sit in its instruction
+// stream (a first version in which the filtering thread quantised its own results ran 1.95 ms for the two stages'
+// 2.14): the CTA is warp-specialised — warps 0-3 filter in place exactly like espb_biquad_tm_kernel, warps 4-11 take
+// each filtered chunk from shared memory, quantise (quantization_utils.cpp:50-94, branch-free), pack 16 samples per
+// thread and store them with 128-bit stores, then hand the stage back for the next TMA load.  Hand-overs are named
+// barriers (filter: bar.arrive, packer: bar.sync).  Full 32-row chunks only; the rows of the last partial chunk are
+// written back as filtered floats for the generic tail path.
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ void named_bar_sync(int id, int count) {
+  asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(count) : "memory");
+}
+__device__ __forceinline__ void named_bar_arrive(int id, int count) {
+  asm volatile("bar.arrive %0, %1;\n" ::"r"(id), "r"(count) : "memory");
+}
+
+constexpr int BQP_THREADS = 3 * SGN;  // 4 filter warps + 8 packer warps (16 rows of a series per packer thread)
+template <int NSEC, bool FIRST_ORDER, int NBYTES, bool BITS32>
+__global__ void __launch_bounds__(BQP_THREADS)
+    espb_biquad_tm_pcm_kernel(float *buf, int64_t rows_cap, int row_first, int n_rows, BiquadParams c,
+                              float *__restrict__ state, int n_series, uint8_t *__restrict__ out, int64_t out_row_bytes,
+                              F2QConst qc, uint32_t *__restrict__ clipped_per_stream) {
+  extern __shared__ __align__(128) unsigned char bq_smem[];
+  float (*ring)[RB][SGN] = reinterpret_cast<float (*)[RB][SGN]>(bq_smem);  // [BSTAGES][RB][SGN]
+  uint64_t *full = reinterpret_cast<uint64_t *>(bq_smem + sizeof(float) * BSTAGES * RB * SGN);
+  const bool packer = threadIdx.x >= SGN;
+  const int tid = threadIdx.x & (SGN - 1);
+  const int q = blockIdx.x * SGN + tid;  // series = stream (mono)
+  float *gbuf = buf + ((int64_t) blockIdx.x * rows_cap + row_first) * SGN;
+  const int n_chunks = (n_rows + RB - 1) / RB;
+  auto chunk_rows = [&](int k) { return (k + 1) * RB <= n_rows ? RB : n_rows - k * RB; };
+  auto load_chunk = [&](int k) {
+    const int st = k % BSTAGES;
+    const uint32_t bytes = (uint32_t) chunk_rows(k) * SGN * sizeof(float);
+    mbar_expect_tx(&full[st], bytes);
+    tma_load(&ring[st][0][0], gbuf + (int64_t) k * RB * SGN, bytes, &full[st]);
+  };
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int s = 0; s < BSTAGES; ++s)
+      mbar_init(&full[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    for (int k = 0; k < BSTAGES && k < n_chunks; ++k)
+      load_chunk(k);
+  }
+  __syncthreads();
+
+  if (!packer) {
+    // ---- filter warps: espb_biquad_tm_kernel's loop, in place in the ring
+    Section sec[NSEC];
+#pragma unroll
+    for (int k = 0; k < NSEC; ++k) {
+      float4 v = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+      if (q < n_series)
+        v = *reinterpret_cast<const float4 *>(state + ((int64_t) q * NSEC + k) * 4);
+      sec[k].in_d1 = v.x, sec[k].in_d2 = v.y, sec[k].out_d1 = v.z, sec[k].out_d2 = v.w;
+    }
+    for (int k = 0; k < n_chunks; ++k) {
+      const int st = k % BSTAGES;
+      const int rows = chunk_rows(k);
+      mbar_wait(&full[st], (uint32_t) ((k / BSTAGES) & 1));
+      float *col = &ring[st][0][tid];
+      if (rows == RB) {
+#pragma unroll 8
+        for (int r = 0; r < RB; ++r) {
+          float v = col[r * SGN];
+#pragma unroll
+          for (int s = 0; s < NSEC; ++s)
+            v = section_step<FIRST_ORDER>(sec[s], v, c);
+          col[r * SGN] = v;
+        }
+        // (the stage is overwritten by a TMA load after the packers are done: order these generic-proxy writes
+        //  before it, as espb_biquad_tm_kernel does before its TMA store)
+        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+        named_bar_arrive(1 + st, BQP_THREADS);  // the chunk is filtered: over to the packers
+      } else {  // the last, partial chunk: filtered floats back to the rows they came from
+        for (int r = 0; r < rows; ++r) {
+          float v = col[r * SGN];
+#pragma unroll
+          for (int s = 0; s < NSEC; ++s)
+            v = section_step<FIRST_ORDER>(sec[s], v, c);
+          gbuf[((int64_t) k * RB + r) * SGN + tid] = v;
+        }
+      }
+    }
+    if (q < n_series) {
+#pragma unroll
+      for (int k = 0; k < NSEC; ++k)
+        *reinterpret_cast<float4 *>(state + ((int64_t) q * NSEC + k) * 4) =
+            make_float4(sec[k].in_d1, sec[k].in_d2, sec[k].out_d1, sec[k].out_d2);
+    }
+  } else {
+    // ---- packer warps: quantise + pack + store each filtered chunk, then refill its stage.  Two threads per series
+    // (16 rows each): a chunk must be packed in less time than it takes to filter the next one, or the ring fills
+    // with filtered chunks and the filter warps starve (one packer thread per series: 18 % of the samples in the
+    // filter's wait for TMA data, 1.82 ms per C3 step).
+    constexpr int HR = RB / 2;
+    const int half = (threadIdx.x - SGN) >> 7;  // 0 / 1: rows [0, 16) / [16, 32) of the chunk
+    uint32_t clipped = 0;
+    uint8_t *orow = out + (int64_t) q * out_row_bytes + (int64_t) half * HR * NBYTES;
+    const int n_full = n_rows / RB;
+    for (int k = 0; k < n_full; ++k) {
+      const int st = k % BSTAGES;
+      named_bar_sync(1 + st, BQP_THREADS);
+      const float *col = &ring[st][half * HR][tid];
+      uint32_t w[HR / 4 * NBYTES];  // 16 samples, packed
+#pragma unroll
+      for (int g = 0; g < HR / 4; ++g) {
+        int32_t s4[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          s4[i] = quantise_one_nb<BITS32>(col[(g * 4 + i) * SGN], qc, clipped);
+        encode_words<NBYTES>(s4, w + g * NBYTES);
+      }
+      named_bar_sync(1 + BSTAGES, 2 * SGN);  // every packer has read the stage
+      if (threadIdx.x == SGN && k + BSTAGES < n_chunks)
+        load_chunk(k + BSTAGES);
+      if (q < n_series) {
+        uint4 *dst = reinterpret_cast<uint4 *>(orow + (int64_t) k * RB * NBYTES);
+#pragma unroll
+        for (int i = 0; i < HR / 16 * NBYTES; ++i)
+          dst[i] = make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
+      }
+    }
+    if (q < n_series && clipped && clipped_per_stream)
+      atomicAdd(clipped_per_stream + q, clipped);
   }
 }
 
@@ -551,6 +685,98 @@ size_t biquad_block_state_floats(int n_series, int n_sections, int n_rows, int b
     return 0;
   const size_t n_blocks = ((size_t) n_rows + block_rows - 1) / block_rows;
   return (size_t) ((n_series + SGN - 1) / SGN) * n_blocks * n_sections * 2 * SGN * 4;
+}
+
+namespace {
+template <int NSEC, int NBYTES>
+cudaError_t launch_tm_pcm(float *buf, int64_t rows_cap, int row_first, int n_rows, int n_series, BiquadParams c,
+                          float *state, uint8_t *out, int64_t out_row_bytes, const F2QConst &qc, uint32_t *clipped,
+                          cudaStream_t stream) {
+  const size_t smem = sizeof(float) * BSTAGES * RB * SGN + BSTAGES * sizeof(uint64_t);
+  constexpr bool B32 = NBYTES == 4;  // (bits == 32 is the only 4-byte depth with its own clipping rule)
+  const bool bits32 = B32 && qc.bits == 32;
+  static PerDeviceOnce once;
+  if (once.first()) {
+    cudaError_t e = cudaFuncSetAttribute(espb_biquad_tm_pcm_kernel<NSEC, true, NBYTES, false>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(espb_biquad_tm_pcm_kernel<NSEC, false, NBYTES, false>,
+                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+    if (e == cudaSuccess && B32)
+      e = cudaFuncSetAttribute(espb_biquad_tm_pcm_kernel<NSEC, true, NBYTES, B32>,
+                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+    if (e == cudaSuccess && B32)
+      e = cudaFuncSetAttribute(espb_biquad_tm_pcm_kernel<NSEC, false, NBYTES, B32>,
+                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+    if (e != cudaSuccess)
+      return e;
+  }
+  const int grid = (n_series + SGN - 1) / SGN;
+#define ESPB_BQP(FO_, B_)                                                                                          \
+  espb_biquad_tm_pcm_kernel<NSEC, FO_, NBYTES, B_><<<grid, BQP_THREADS, smem, stream>>>(buf, rows_cap, row_first, n_rows, c, \
+                                                                                    state, n_series, out,          \
+                                                                                    out_row_bytes, qc, clipped)
+  if (c.first_order) {
+    if (bits32)
+      ESPB_BQP(true, B32);
+    else
+      ESPB_BQP(true, false);
+  } else {
+    if (bits32)
+      ESPB_BQP(false, B32);
+    else
+      ESPB_BQP(false, false);
+  }
+#undef ESPB_BQP
+  count_launch();
+  return cudaGetLastError();
+}
+template <int NSEC>
+cudaError_t launch_tm_pcm_bytes(int nbytes, float *buf, int64_t rows_cap, int row_first, int n_rows, int n_series,
+                                BiquadParams c, float *state, uint8_t *out, int64_t out_row_bytes, const F2QConst &qc,
+                                uint32_t *clipped, cudaStream_t stream) {
+  switch (nbytes) {
+    case 1:
+      return launch_tm_pcm<NSEC, 1>(buf, rows_cap, row_first, n_rows, n_series, c, state, out, out_row_bytes, qc, clipped, stream);
+    case 2:
+      return launch_tm_pcm<NSEC, 2>(buf, rows_cap, row_first, n_rows, n_series, c, state, out, out_row_bytes, qc, clipped, stream);
+    case 3:
+      return launch_tm_pcm<NSEC, 3>(buf, rows_cap, row_first, n_rows, n_series, c, state, out, out_row_bytes, qc, clipped, stream);
+    default:
+      return launch_tm_pcm<NSEC, 4>(buf, rows_cap, row_first, n_rows, n_series, c, state, out, out_row_bytes, qc, clipped, stream);
+  }
+}
+}  // namespace
+
+// Mono streams: filter rows [row_first, row_first + n_rows) of buf (time-major) and write them as packed PCM to
+// out[stream] — frames [0, returned) — in one pass; the filtered floats of the remaining rows (the last partial
+// 32-row chunk) are written back to buf for the caller's generic tail path.  Returns 0 (nothing enqueued) when the
+// output rows are not 16-byte aligned or there is no full chunk.
+int launch_biquad_tm_pcm(float *buf, int64_t rows_cap, int row_first, int n_rows, int n_series, int n_sections,
+                         BiquadParams c, float *state, uint8_t *out, int64_t out_row_bytes, int bits,
+                         uint32_t *clipped_per_stream, cudaStream_t stream, cudaError_t *err) {
+  *err = cudaSuccess;
+  if (n_series <= 0 || n_rows < RB || bits < 1 || bits > 32 || ((uintptr_t) out % 16) || (out_row_bytes % 16))
+    return 0;
+  const int nbytes = (bits + 7) / 8;
+  const F2QConst qc = make_f2q_const(bits);
+  switch (n_sections) {
+    case 1:
+      *err = launch_tm_pcm_bytes<1>(nbytes, buf, rows_cap, row_first, n_rows, n_series, c, state, out, out_row_bytes, qc, clipped_per_stream, stream);
+      break;
+    case 2:
+      *err = launch_tm_pcm_bytes<2>(nbytes, buf, rows_cap, row_first, n_rows, n_series, c, state, out, out_row_bytes, qc, clipped_per_stream, stream);
+      break;
+    case 3:
+      *err = launch_tm_pcm_bytes<3>(nbytes, buf, rows_cap, row_first, n_rows, n_series, c, state, out, out_row_bytes, qc, clipped_per_stream, stream);
+      break;
+    case 4:
+      *err = launch_tm_pcm_bytes<4>(nbytes, buf, rows_cap, row_first, n_rows, n_series, c, state, out, out_row_bytes, qc, clipped_per_stream, stream);
+      break;
+    default:
+      return 0;
+  }
+  return (n_rows / RB) * RB;
 }
 
 cudaError_t launch_biquad_tm(const float *src, float *dst, int64_t rows_cap, int row_first, int n_rows, int n_series,

@@ -183,6 +183,10 @@ cudaError_t launch_biquad_tm(const float *src, float *dst, int64_t rows_cap, int
                              int n_sections, BiquadParams c, float *state /* [series][section][4] */,
                              int block_rows, int warm_rows, cudaStream_t stream, float *blk_state = nullptr,
                              unsigned int *mismatches = nullptr);
+// mono streams: post-filter + float_to_quantized in one pass (biquad_kernel.cu); returns the frames written as PCM
+int launch_biquad_tm_pcm(float *buf, int64_t rows_cap, int row_first, int n_rows, int n_series, int n_sections,
+                         BiquadParams c, float *state, uint8_t *out, int64_t out_row_bytes, int bits,
+                         uint32_t *clipped_per_stream, cudaStream_t stream, cudaError_t *err);
 // time-major -> caller layout (inverse of launch_transpose): rows [row_first, row_first + n_rows)
 cudaError_t launch_untranspose(const float *tm, int64_t rows_cap, int row_first, int n_rows, float *out,
                                int64_t out_ss, int64_t out_cs, int64_t out_fs, int channels, int n_series,

@@ -12,6 +12,7 @@
 
 #include "common.hpp"
 #include "kernels.hpp"
+#include "pcm_device.cuh"
 
 namespace espb {
 
@@ -100,55 +101,7 @@ __global__ void __launch_bounds__(256)
     orow[i] = __fmul_rn(__int2float_rn(decode_bytes<NBYTES>(irow + (size_t) i * NBYTES)), k);
 }
 
-// ---- encode ------------------------------------------------------------------------
-struct F2QConst {
-  float scalar;
-  int32_t offset, hi, lo;
-  int shift, bits;
-};
-
-__device__ __forceinline__ int32_t quantise_one(float x, const F2QConst &c, uint32_t &clipped) {
-  int32_t v = __float2int_rd(__fadd_rn(__fmul_rn(x, c.scalar), 0.5f));  // :61 floorf(x*scalar + 0.5f)
-  if (c.bits < 32) {                                                    // :62-69
-    if (v > c.hi) {
-      ++clipped;
-      v = c.hi;
-    } else if (v < c.lo) {
-      ++clipped;
-      v = c.lo;
-    }
-  } else {  // :70-78
-    if (x >= 1.0f) {
-      ++clipped;
-      v = c.hi;
-    } else if (x < -1.0f) {
-      ++clipped;
-      v = c.lo;
-    }
-  }
-  return (int32_t) ((uint32_t) v << c.shift) + c.offset;  // :80
-}
-
-template <int NBYTES>
-__device__ __forceinline__ void encode_words(const int32_t v[4], uint32_t *w) {
-  if (NBYTES == 1) {
-    w[0] = ((uint32_t) v[0] & 0xffu) | (((uint32_t) v[1] & 0xffu) << 8) | (((uint32_t) v[2] & 0xffu) << 16) |
-           ((uint32_t) v[3] << 24);
-  } else if (NBYTES == 2) {
-    w[0] = ((uint32_t) v[0] & 0xffffu) | ((uint32_t) v[1] << 16);
-    w[1] = ((uint32_t) v[2] & 0xffffu) | ((uint32_t) v[3] << 16);
-  } else if (NBYTES == 3) {
-    const uint32_t a = (uint32_t) v[0] & 0xffffffu, b = (uint32_t) v[1] & 0xffffffu,
-                   c = (uint32_t) v[2] & 0xffffffu, d = (uint32_t) v[3] & 0xffffffu;
-    w[0] = a | (b << 24);
-    w[1] = (b >> 8) | (c << 16);
-    w[2] = (c >> 16) | (d << 8);
-  } else {
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-      w[i] = (uint32_t) v[i];
-  }
-}
+// (F2QConst, quantise_one, encode_words: pcm_device.cuh — shared with the fused filter + quantise kernel)
 
 template <int NBYTES>
 __global__ void __launch_bounds__(256)
@@ -344,16 +297,6 @@ bool launch_tm_to_pcm_ch(int ch, dim3 grid, cudaStream_t s, const float *tm, int
   }
 }
 
-F2QConst make_f2q_const(int bits) {
-  F2QConst c;
-  c.bits = bits;
-  c.scalar = (float) ((uint64_t) 1 << bits) / 2.0f;  // :52
-  c.offset = (bits <= 8) ? 128 : 0;                   // :53
-  c.hi = (int32_t) ((1u << (bits - 1)) - 1u);         // :54
-  c.lo = ~c.hi;                                       // :55
-  c.shift = (32 - bits) % 8;                          // :56
-  return c;
-}
 
 inline unsigned grid_x_for(uint32_t n, int rows) {
   // enough CTAs to cover the row once at 4 samples/thread, capped so rows*grid stays sane

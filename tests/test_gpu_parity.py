@@ -944,3 +944,35 @@ def test_staging_overlap_is_bit_identical(oracle, ch, planar, ns):
             assert (u1, g1) == (uo, go)
             assert bits_equal(y1[s][: go * ch], yo), (s, n)
             pos += n
+
+
+@pytest.mark.parametrize("db,frames", [(16, 2048), (8, 1000), (24, 777), (32, 1500)])
+def test_fused_post_filter_quantiser_mono(oracle, db, frames, monkeypatch):
+    """Mono up-sampling through the wrapper: the post-filter's thread quantises and packs its own results
+    (espb_biquad_tm_pcm_kernel) instead of a filter pass followed by a quantising layout pass.  Same bytes and clip
+    counts as the two-pass form (ESPB_FUSE_POST=0) over three chained calls, loud enough to clip, frame counts that
+    leave a partial last chunk; and bit-exact against the oracle wrapper in exact mode."""
+    sr, dr, sb, ch, ns = 16000, 48000, 16, 1, 150
+    rng = np.random.default_rng(db + frames)
+    calls = [(rng.normal(0, 0.45, size=(ns, frames)).clip(-1, 0.99997) * 32768).astype(np.int16) for _ in range(3)]
+    cap = frames * 3 + 64
+    results = {}
+    for fused in ("1", "0"):
+        monkeypatch.setenv("ESPB_FUSE_POST", fused)
+        r = espb.Resampler(ns, frames * ch, cap * ch, sr, dr, sb, db, ch, True, True, 64, 64, mode=espb.MODE_EXACT)
+        got = []
+        for pcm in calls:
+            out, res = r.resample(pcm.view(np.uint8).reshape(ns, -1), frames, cap, 3.0)
+            got.append((out.copy(), res["frames_generated"], np.array(res["clipped_per_stream"]).copy()))
+        results[fused] = got
+        r.free()
+    clipped_any = 0
+    for (o1, g1, c1), (o0, g0, c0) in zip(results["1"], results["0"]):
+        assert g1 == g0 and bits_equal(o1, o0) and np.array_equal(c1, c0)
+        clipped_any += int(c1.sum())
+    assert clipped_any > 0  # the clip-count path was exercised
+    for s in (0, 77, ns - 1):
+        w = oracle.wrapper(frames * ch, cap * ch, float(sr), float(dr), sb, db, ch, True, True, 64, 64)
+        for pcm, (o1, g1, c1) in zip(calls, results["1"]):
+            yo, ro = w.resample(pcm[s].view(np.uint8), frames, cap, 3.0)
+            assert g1 == ro["frames_generated"] and bits_equal(o1[s], yo) and int(c1[s]) == ro["clipped_samples"]
