@@ -987,7 +987,11 @@ int run_series_range(EspbResampleBatch *c, int series_first, int n_series, const
            "carry transpose");
   }
   bool tail_done = false;
-  if (tm_out && post_on && pcm_out && c->channels == 1 && env_long("ESPB_FUSE_POST", 1) != 0 &&
+  // (worth it for many groups only: the fused kernel's filter warps share their schedulers with the packers and run
+  //  1.7 ms for 48005 rows where the plain filter runs 1.15, whatever the number of groups, while the separate
+  //  quantising stage costs ~8 us per group — slabs of the host pipeline, 4 groups each, stay with two passes)
+  if (tm_out && post_on && pcm_out && c->channels == 1 && ng >= env_long("ESPB_FUSE_POST_GROUPS", 96) &&
+      env_long("ESPB_FUSE_POST", 1) != 0 &&
       !(post->block_rows > 0 && (int) c->sched.generated > post->block_rows && c->yt2_rows >= c->yt_rows)) {
     // mono PCM output behind a post-filter (resampler.cpp:142-153): the filter's thread quantises and packs its own
     // results — one pass over the resampler's time-major output instead of two

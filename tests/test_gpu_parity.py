@@ -957,6 +957,7 @@ def test_fused_post_filter_quantiser_mono(oracle, db, frames, monkeypatch):
     calls = [(rng.normal(0, 0.45, size=(ns, frames)).clip(-1, 0.99997) * 32768).astype(np.int16) for _ in range(3)]
     cap = frames * 3 + 64
     results = {}
+    monkeypatch.setenv("ESPB_FUSE_POST_GROUPS", "1")  # (by default only batches of >= 96 groups take the fused kernel)
     for fused in ("1", "0"):
         monkeypatch.setenv("ESPB_FUSE_POST", fused)
         r = espb.Resampler(ns, frames * ch, cap * ch, sr, dr, sb, db, ch, True, True, 64, 64, mode=espb.MODE_EXACT)
