@@ -853,7 +853,7 @@ int run_series_range(EspbResampleBatch *c, int series_first, int n_series, const
     // is launched right behind it as a programmatic dependent (nothing may be enqueued between the two), so the
     // HBM-bound staging hides behind the FMA-bound kernel instead of preceding it.
     if (overlap_ok && c->overlap_staging && !small_stage && !pcm_in && !ptrs && !pre_on && !c->fs_call &&
-        !c->non_interp && !c->kernel_timing && c->sched.generated > 0 &&
+        !c->kernel_timing && c->sched.generated > 0 &&
         passes_per_slab(c) >= c->plan.n_passes() && n_in >= 8 * kReadyTileRows) {
       CU_TRY(c->d_ready.reserve((size_t) (n_in / kReadyTileRows + 1) * sizeof(int)), "cudaMalloc ready counters");
       if (c->aux_join_pending) {  // the coefficients were expanded on the side stream

@@ -107,6 +107,26 @@ __global__ void __launch_bounds__(BPP * 32, 16 / BPP) espb_resample_ni_kernel(co
     tma_bulk_g2s(gs + st * GS_STAGE, p.G + (size_t) (hdr[0] + c) * GS_STAGE, G_BYTES, &full[st]);
     tma_bulk_g2s(xs + st * XS_STAGE, xt_group + (int64_t) (jtab[c] + T) * SGN, X_BYTES, &full[st]);
   };
+  // staging overlap (resample_kernel.cu has the protocol): wait for the row tiles this CTA reads
+  if (p.ready != nullptr && n_chunks > 0) {
+    const int j_hi = jtab[n_chunks - 1] + CJ - 1;
+    if (j_hi >= 0) {
+      const int j_lo = jtab[0];
+      const int y_lo = j_lo > 0 ? j_lo / kReadyTileRows : 0;
+      int y_hi = j_hi / kReadyTileRows;
+      y_hi = y_hi < p.ready_tiles ? y_hi : p.ready_tiles - 1;
+      for (int y = y_lo + tid; y <= y_hi; y += NTHREADS) {
+        const long long t0 = clock64();
+        while (ld_acquire_gpu(p.ready + y) < p.ready_target) {
+          __nanosleep(200);
+          if (clock64() - t0 > (4ll << 31))  // ~4 s
+            __trap();
+        }
+      }
+    }
+    __syncthreads();
+    fence_proxy_async();
+  }
   if (tid == 0)
     for (int c = 0; c < STAGES && c < n_chunks; ++c)
       issue_chunk(c);
@@ -310,6 +330,21 @@ static cudaError_t launch_ni_t(const ResampleParams &p, int n_groups, int n_ctas
     }
   }
   dim3 grid(n_groups, n_ctas_y);
+  if (p.ready != nullptr) {  // programmatic dependent of the staging kernel launched just before (resample_kernel.cu)
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(BPP * 32);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, espb_resample_ni_kernel<BPP, NST, CJ, EXACT, TMCAP>, p);
+    count_launch();
+    return e != cudaSuccess ? e : cudaGetLastError();
+  }
   espb_resample_ni_kernel<BPP, NST, CJ, EXACT, TMCAP><<<grid, BPP * 32, smem, stream>>>(p);
   count_launch();
   return cudaGetLastError();

@@ -902,8 +902,10 @@ def test_bad_ratios_are_refused_not_executed():
     b.free()
 
 
-@pytest.mark.parametrize("ch,planar,ns", [(2, False, 200), (1, False, 300), (4, False, 70), (2, True, 130), (8, False, 40)])
-def test_staging_overlap_is_bit_identical(oracle, ch, planar, ns):
+@pytest.mark.parametrize("ch,planar,ns,flags", [(2, False, 200, 3), (1, False, 300, 3), (4, False, 70, 3),
+                                                (2, True, 130, 3), (8, False, 40, 3),
+                                                (2, False, 140, 2), (1, False, 150, 0)])  # (last two: non-interpolating)
+def test_staging_overlap_is_bit_identical(oracle, ch, planar, ns, flags):
     """Long device-buffer calls launch the resampler kernel as a programmatic dependent of the transposing kernel and
     synchronise per CTA on per-row-tile counters (ESPB_OPT_OVERLAP_STAGING, default on).  Three chained calls of
     uneven length (not multiples of the 32-row tile, so the tail and the padding take the generic kernel) must give
@@ -915,7 +917,7 @@ def test_staging_overlap_is_bit_identical(oracle, ch, planar, ns):
     x = np.stack([noise(total, ch, stream=900 + s, amp=0.7) for s in range(ns)])  # (ns, total*ch) interleaved
     outs = {}
     for overlap in (1, 0):
-        b = espb.ResampleBatch(ns, ch, taps, filters, 1.0, 3, mode=espb.MODE_EXACT)
+        b = espb.ResampleBatch(ns, ch, taps, filters, 1.0, flags, mode=espb.MODE_EXACT)
         b.set_option(espb.OPT_OVERLAP_STAGING, overlap)
         b.set_option(espb.OPT_PLAN_CACHE, 0)
         b.advance(taps / 2)
@@ -935,7 +937,7 @@ def test_staging_overlap_is_bit_identical(oracle, ch, planar, ns):
     for (y1, u1, g1), (y0, u0, g0) in zip(outs[1], outs[0]):
         assert (u1, g1) == (u0, g0) and bits_equal(y1, y0)
     for s in (0, ns // 2, ns - 1):
-        o = oracle.resampler(ch, taps, filters, 1.0, 3)
+        o = oracle.resampler(ch, taps, filters, 1.0, flags)
         o.advance(taps / 2)
         pos = 0
         for n, (y1, u1, g1) in zip(sizes, outs[1]):

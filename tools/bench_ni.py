@@ -35,7 +35,26 @@ for mode in (espb.MODE_FAST, espb.MODE_EXACT):
     ms, n = b.kernel_time()
     k = ms / n
     samples = gen * ch * ns
+    # whole call, device-resident, with and without the staging overlap (kernel timing off)
+    L = espb.lib()
+    b.set_option(espb.OPT_KERNEL_TIMING, 0)
+    b.set_option(espb.OPT_PLAN_CACHE, 0)
+    call_ms = {}
+    for overlap in (1, 0):
+        b.set_option(espb.OPT_OVERLAP_STAGING, overlap)
+        for it in range(13):
+            if it == 3:
+                ev0, ev1 = L.espb_event_create(), L.espb_event_create()
+                L.espb_event_record(ev0, None)
+            b.reset()
+            b.advance(taps / 2)
+            b.process_interleaved_dev(d_in.ptr, n_in * ch, n_in, d_out.ptr, cap * ch, cap, ratio)
+        L.espb_event_record(ev1, None)
+        t = espb.capi.C.c_float(0)
+        L.espb_event_elapsed_ms(ev0, ev1, espb.capi.C.byref(t))
+        call_ms[overlap] = round(t.value / 10, 3)
     print(json.dumps(dict(mode="fast" if mode == espb.MODE_FAST else "exact", dedicated=os.environ.get("ESPB_NI", "1") != "0",
                           kernel_ms=round(k, 3), gsamples_per_s=round(samples / k / 1e6, 1),
-                          tflops_at_2T=round(2 * taps * samples / k / 1e9, 1))), flush=True)
+                          tflops_at_2T=round(2 * taps * samples / k / 1e9, 1), call_ms_overlap=call_ms[1],
+                          call_ms_serial=call_ms[0])), flush=True)
     b.free()
