@@ -431,7 +431,7 @@ __host__ __device__ constexpr int cl_pitch(bool vec) { return vec ? CL_ROWS + 4 
 // be a constant, or the compiler cannot move a row's load above the previous row's store and the recurrence waits
 // for shared memory every row — measured 1.7x slower); LUT < 0: the 4-byte form, taken from the argument.
 template <int NSEC, bool FIRST_ORDER, int LUT>
-__global__ void __launch_bounds__(SGN)
+__global__ void __launch_bounds__(2 * SGN)
     espb_biquad_cl_kernel(float *buf, int64_t ss, int64_t cs, int64_t fs, int channels, int lu_arg, int n_series,
                           int n_frames, BiquadParams c, float *__restrict__ state) {
   constexpr bool VEC = LUT >= 0;
@@ -440,12 +440,18 @@ __global__ void __launch_bounds__(SGN)
   extern __shared__ __align__(16) unsigned char cl_smem[];
   float (*tile)[SGN * CL_PITCH] = reinterpret_cast<float (*)[SGN * CL_PITCH]>(cl_smem);  // [CL_STAGES][128 x pitch]
   int64_t *base_tab = reinterpret_cast<int64_t *>(cl_smem + sizeof(float) * CL_STAGES * SGN * CL_PITCH);  // [128]
-  const int tid = threadIdx.x;
+  // Warp-specialised: threads [0, 128) own a series each and only run the recurrence; threads [128, 256) only move
+  // data (cp.async in, 128-bit stores out).  With one CTA per SM the recurrence used to stand still during every
+  // copy phase of its own threads (78 cycles per frame for two sections instead of ~45); hand-overs are named
+  // barriers: LOADED[stage] (copiers arrive, filters wait), FILTERED[stage] (the reverse), COPY (copiers only).
+  const bool copier = threadIdx.x >= SGN;
+  const int tid = threadIdx.x & (SGN - 1);
   const int q0 = blockIdx.x * SGN;
   const int q = q0 + tid;
   const int n_chunks = (n_frames + CL_ROWS - 1) / CL_ROWS;
+  constexpr int BAR_LOADED = 1, BAR_FILTERED = 1 + CL_STAGES, BAR_COPY = 1 + 2 * CL_STAGES;
   // where frame 0 of every series of this CTA lies (-1: no such series); frame j is j * fs further
-  {
+  if (!copier) {
     const int st = q / channels, ch = q - st * channels;
     base_tab[tid] = q < n_series ? (int64_t) st * ss + (int64_t) ch * cs : (int64_t) -1;
   }
@@ -484,6 +490,54 @@ __global__ void __launch_bounds__(SGN)
     }
     asm volatile("cp.async.commit_group;\n" ::: "memory");
   };
+  auto store_chunk = [&](int k) {
+    float *t = tile[k % CL_STAGES];
+    const int j0 = k * CL_ROWS;
+    if (VEC && j0 + CL_ROWS <= n_frames) {
+#pragma unroll
+      for (int i = tid; i < SGN * (CL_ROWS / 4); i += SGN) {
+        const int u = i >> (CL_LOG_ROWS - 2 + lu), v4 = (i & (((CL_ROWS / 4) << lu) - 1)) * 4;
+        const int64_t base = base_tab[u << lu];
+        if (base >= 0)
+          *reinterpret_cast<float4 *>(buf + base + (int64_t) j0 * fs + v4) =
+              *reinterpret_cast<const float4 *>(t + u * unit_pitch + v4);
+      }
+    } else {
+#pragma unroll 4
+      for (int i = tid; i < SGN * CL_ROWS; i += SGN) {
+        const int e = i & run_mask;
+        const int jj = e >> lu, sl = ((i >> run_shift) << lu) + (e & unit_mask);
+        const int64_t base = base_tab[sl];
+        if (base >= 0 && j0 + jj < n_frames)
+          buf[base + (int64_t) (j0 + jj) * fs] = t[sl * CL_PITCH + jj];
+      }
+    }
+  };
+  if (copier) {
+    for (int k = 0; k < CL_STAGES - 1; ++k) {
+      if (k < n_chunks)
+        load_chunk(k);
+      else
+        asm volatile("cp.async.commit_group;\n" ::: "memory");
+    }
+    for (int k = 0; k < n_chunks; ++k) {
+      asm volatile("cp.async.wait_group %0;\n" ::"n"(CL_STAGES - 2) : "memory");  // chunk k has landed (this thread's part)
+      named_bar_arrive(BAR_LOADED + k % CL_STAGES, 2 * SGN);
+      if (k >= 1) {
+        named_bar_sync(BAR_FILTERED + (k - 1) % CL_STAGES, 2 * SGN);
+        store_chunk(k - 1);
+        named_bar_sync(BAR_COPY, SGN);  // every copier has read that stage: it may be refilled
+      }
+      if (k + CL_STAGES - 1 < n_chunks)
+        load_chunk(k + CL_STAGES - 1);  // into the stage of chunk k - 1
+      else
+        asm volatile("cp.async.commit_group;\n" ::: "memory");
+    }
+    named_bar_sync(BAR_FILTERED + (n_chunks - 1) % CL_STAGES, 2 * SGN);
+    store_chunk(n_chunks - 1);
+    asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+    return;
+  }
   Section sec[NSEC];
   if (q < n_series) {
 #pragma unroll
@@ -496,19 +550,8 @@ __global__ void __launch_bounds__(SGN)
     for (int k = 0; k < NSEC; ++k)
       sec[k].in_d1 = sec[k].in_d2 = sec[k].out_d1 = sec[k].out_d2 = 0.0f;
   }
-  for (int k = 0; k < CL_STAGES - 1; ++k) {
-    if (k < n_chunks)
-      load_chunk(k);
-    else
-      asm volatile("cp.async.commit_group;\n" ::: "memory");
-  }
   for (int k = 0; k < n_chunks; ++k) {
-    asm volatile("cp.async.wait_group %0;\n" ::"n"(CL_STAGES - 2) : "memory");
-    __syncthreads();  // chunk k has landed for every thread; the stage refilled below was stored before this barrier
-    if (k + CL_STAGES - 1 < n_chunks)
-      load_chunk(k + CL_STAGES - 1);
-    else
-      asm volatile("cp.async.commit_group;\n" ::: "memory");
+    named_bar_sync(BAR_LOADED + k % CL_STAGES, 2 * SGN);
     float *t = tile[k % CL_STAGES];
     const int j0 = k * CL_ROWS;
     const int rows = j0 + CL_ROWS <= n_frames ? CL_ROWS : n_frames - j0;
@@ -534,28 +577,8 @@ __global__ void __launch_bounds__(SGN)
         mine[r] = v;
       }
     }
-    __syncthreads();
-    if (VEC && rows == CL_ROWS) {
-#pragma unroll
-      for (int i = tid; i < SGN * (CL_ROWS / 4); i += SGN) {
-        const int u = i >> (CL_LOG_ROWS - 2 + lu), v4 = (i & (((CL_ROWS / 4) << lu) - 1)) * 4;
-        const int64_t base = base_tab[u << lu];
-        if (base >= 0)
-          *reinterpret_cast<float4 *>(buf + base + (int64_t) j0 * fs + v4) =
-              *reinterpret_cast<const float4 *>(t + u * unit_pitch + v4);
-      }
-    } else {
-#pragma unroll 4
-      for (int i = tid; i < SGN * CL_ROWS; i += SGN) {
-        const int e = i & run_mask;
-        const int jj = e >> lu, sl = ((i >> run_shift) << lu) + (e & unit_mask);
-        const int64_t base = base_tab[sl];
-        if (base >= 0 && j0 + jj < n_frames)
-          buf[base + (int64_t) (j0 + jj) * fs] = t[sl * CL_PITCH + jj];
-      }
-    }
+    named_bar_arrive(BAR_FILTERED + k % CL_STAGES, 2 * SGN);
   }
-  asm volatile("cp.async.wait_group 0;\n" ::: "memory");
   if (q < n_series) {
 #pragma unroll
     for (int k = 0; k < NSEC; ++k)
@@ -584,11 +607,11 @@ cudaError_t launch_cl(float *buf, int64_t ss, int64_t cs, int64_t fs, int channe
       return e;
   }
   if (c.first_order)
-    espb_biquad_cl_kernel<NSEC, true, LUT><<<grid, SGN, smem, stream>>>(buf, ss, cs, fs, channels, lu, n_series,
-                                                                     n_frames, c, state);
+    espb_biquad_cl_kernel<NSEC, true, LUT><<<grid, 2 * SGN, smem, stream>>>(buf, ss, cs, fs, channels, lu, n_series,
+                                                                         n_frames, c, state);
   else
-    espb_biquad_cl_kernel<NSEC, false, LUT><<<grid, SGN, smem, stream>>>(buf, ss, cs, fs, channels, lu, n_series,
-                                                                      n_frames, c, state);
+    espb_biquad_cl_kernel<NSEC, false, LUT><<<grid, 2 * SGN, smem, stream>>>(buf, ss, cs, fs, channels, lu, n_series,
+                                                                          n_frames, c, state);
   count_launch();
   return cudaGetLastError();
 }
