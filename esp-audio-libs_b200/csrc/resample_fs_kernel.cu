@@ -24,7 +24,7 @@
 // Per tap a lane issues 2 LDS.32 (coefficients of phase and phase+1) + one LDS of SV floats (x) for SV FFMA2: the
 // loop is bound by shared-memory wavefronts, not by the FMA pipe (2+SV/... wavefronts per 2 SV FMA cycles: about 25 %
 // of the FMA peak for one stereo stream, 40 % for 8 series) — every x value and every coefficient pair is used by
-// exactly SV or one FFMA2, and no tiling can raise that for a single series (DESIGN.md §4.3).
+// exactly SV or one FFMA2, and no tiling can raise that for a single series (DESIGN.md §4.2).
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
