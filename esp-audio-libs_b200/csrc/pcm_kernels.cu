@@ -13,6 +13,7 @@
 #include "common.hpp"
 #include "kernels.hpp"
 #include "pcm_device.cuh"
+#include "resample_device.cuh"
 
 namespace espb {
 
@@ -169,7 +170,7 @@ __global__ void __launch_bounds__(256)
 // conversion rides on the transposing pass, so the wrapper path never materialises a stream-major float
 // copy.  Tiles of 128 series x 64 frames through shared memory; 32-bit word accesses on the PCM side
 // (4 samples = NBYTES words), 128-bit on the float side.  CH in {1,2,4,8}; full tiles only.
-constexpr int SGN = kSeriesPerRow;  // 128
+// (SGN = kSeriesPerRow = 128: resample_device.cuh)
 constexpr int PT_ROWS = 64;
 constexpr int PT_THREADS = 256;
 
@@ -177,7 +178,8 @@ template <int NBYTES, int CH>
 __global__ void __launch_bounds__(PT_THREADS)
     espb_pcm_to_tm_kernel(const uint8_t *__restrict__ in, int64_t in_row_bytes, float *__restrict__ tm,
                           int64_t rows_cap, int row_first, int n_series, float k) {
-  __shared__ float tile[PT_ROWS][SGN + 1];
+  __shared__ __align__(16) float tile_s[PT_ROWS * SGN];
+  const SwzTile tile{tile_s};
   const int g = blockIdx.x, j0 = blockIdx.y * PT_ROWS, tid = threadIdx.x;
   constexpr int UNITS = SGN / CH;            // streams per group
   constexpr int GROUPS = PT_ROWS * CH / 4;   // 4-sample groups per stream per tile
@@ -198,7 +200,7 @@ __global__ void __launch_bounds__(PT_THREADS)
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int e = grp * 4 + i;
-      tile[e / CH][unit * CH + (e % CH)] = (q0 < n_series) ? __fmul_rn(__int2float_rn(s[i]), k) : 0.0f;
+      tile.at(e / CH, unit * CH + (e % CH)) = (q0 < n_series) ? __fmul_rn(__int2float_rn(s[i]), k) : 0.0f;
     }
   }
   __syncthreads();
@@ -206,7 +208,7 @@ __global__ void __launch_bounds__(PT_THREADS)
 #pragma unroll 4
   for (int i = tid; i < PT_ROWS * (SGN / 4); i += PT_THREADS) {
     const int t = i / (SGN / 4), c4 = i % (SGN / 4);
-    dst[i] = make_float4(tile[t][c4 * 4], tile[t][c4 * 4 + 1], tile[t][c4 * 4 + 2], tile[t][c4 * 4 + 3]);
+    dst[i] = tile.vec(t, c4);
   }
 }
 
@@ -214,17 +216,14 @@ template <int NBYTES, int CH>
 __global__ void __launch_bounds__(PT_THREADS)
     espb_tm_to_pcm_kernel(const float *__restrict__ tm, int64_t rows_cap, int row_first, uint8_t *__restrict__ out,
                           int64_t out_row_bytes, int n_series, F2QConst c, uint32_t *__restrict__ clipped_per_stream) {
-  __shared__ float tile[PT_ROWS][SGN + 1];
+  __shared__ __align__(16) float tile_s[PT_ROWS * SGN];
+  const SwzTile tile{tile_s};
   const int g = blockIdx.x, j0 = blockIdx.y * PT_ROWS, tid = threadIdx.x;
   const float4 *src = reinterpret_cast<const float4 *>(tm + ((int64_t) g * rows_cap + row_first + j0) * SGN);
 #pragma unroll 4
   for (int i = tid; i < PT_ROWS * (SGN / 4); i += PT_THREADS) {
     const int t = i / (SGN / 4), c4 = i % (SGN / 4);
-    const float4 v = __ldg(src + i);
-    tile[t][c4 * 4] = v.x;
-    tile[t][c4 * 4 + 1] = v.y;
-    tile[t][c4 * 4 + 2] = v.z;
-    tile[t][c4 * 4 + 3] = v.w;
+    tile.vec(t, c4) = __ldg(src + i);
   }
   __syncthreads();
   constexpr int UNITS = SGN / CH;
@@ -241,7 +240,7 @@ __global__ void __launch_bounds__(PT_THREADS)
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int e = grp * 4 + i;
-      s[i] = quantise_one(tile[e / CH][unit * CH + (e % CH)], c, clipped);
+      s[i] = quantise_one(tile.at(e / CH, unit * CH + (e % CH)), c, clipped);
     }
     uint32_t w[NBYTES];
     encode_words<NBYTES>(s, w);

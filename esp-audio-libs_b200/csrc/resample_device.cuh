@@ -61,6 +61,23 @@ __device__ __forceinline__ void cp_async_16(void *dst_smem, const void *src) {
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
 
+// Shared-memory tile of `rows` x 128 series for the layout stages (caller layout <-> time-major).  The 16-byte units
+// of a row are XOR-permuted by a function of the row: the time-major side moves whole units (one conflict-free
+// LDS.128 / STS.128 per lane: consecutive lanes, consecutive units of one row), the stream-major side — consecutive
+// frames of one stream, i.e. consecutive rows of one column — spreads over the banks because rows 4m + i map m and i
+// into different bits of the permutation.  8 shared-memory wavefronts per 512 bytes moved instead of the 24 of the
+// padded scalar tile (pitch 129: two-way conflicts on the scalar stores, four scalar loads per 128-bit store).
+struct SwzTile {
+  float *p;
+  __device__ __forceinline__ static int unit(int row, int u) { return u ^ (((row >> 2) ^ ((row & 3) << 3)) & 31); }
+  __device__ __forceinline__ float &at(int row, int col) const {
+    return p[row * kSeriesPerRow + (unit(row, col >> 2) << 2) + (col & 3)];
+  }
+  __device__ __forceinline__ float4 &vec(int row, int u) const {
+    return *reinterpret_cast<float4 *>(p + row * kSeriesPerRow + (unit(row, u) << 2));
+  }
+};
+
 // ---- staging overlap: the resampler is launched as a programmatic dependent of the transposing
 // kernel and starts while that kernel is still filling xt; a CTA waits for the row tiles it reads on per-tile
 // counters the transposing CTAs bump (release) after their stores.

@@ -206,7 +206,7 @@ constexpr int TF_THREADS = 256;
 // VEC-float loads along time (4, 2 or 1 as the alignment of the rows allows), index arithmetic by shifts only.
 // One tile: ROWS frames x 128 series of group g starting at frame j0, through `tile` (ROWS x (SGN + 1) floats).
 template <int CH, bool PLANAR, int VEC, int ROWS>
-__device__ __forceinline__ void transpose_fast_tile(float (*tile)[SGN + 1], int g, int j0, const float *__restrict__ in,
+__device__ __forceinline__ void transpose_fast_tile(const SwzTile tile, int g, int j0, const float *__restrict__ in,
                                                     int64_t in_ss, int64_t in_cs, int channels, int n_series,
                                                     float *__restrict__ xt, int64_t rows_cap, int row_first) {
   const int tid = threadIdx.x;
@@ -242,7 +242,7 @@ __device__ __forceinline__ void transpose_fast_tile(float (*tile)[SGN + 1], int 
 #pragma unroll
     for (int k = 0; k < VEC; ++k) {
       const int e = e0 + k;
-      tile[e / CH][unit * CH + (e % CH)] = xv[k];
+      tile.at(e / CH, unit * CH + (e % CH)) = xv[k];
     }
   }
   __syncthreads();
@@ -250,7 +250,7 @@ __device__ __forceinline__ void transpose_fast_tile(float (*tile)[SGN + 1], int 
 #pragma unroll 4
   for (int i = tid; i < ROWS * (SGN / 4); i += TF_THREADS) {
     const int t = i / (SGN / 4), c4 = i % (SGN / 4);
-    dst[i] = make_float4(tile[t][c4 * 4], tile[t][c4 * 4 + 1], tile[t][c4 * 4 + 2], tile[t][c4 * 4 + 3]);
+    dst[i] = tile.vec(t, c4);
   }
 }
 
@@ -258,7 +258,8 @@ template <int CH, bool PLANAR, int VEC>
 __global__ void __launch_bounds__(TF_THREADS)
     espb_transpose_fast_kernel(const float *__restrict__ in, int64_t in_ss, int64_t in_cs, int channels,
                                int n_series, float *__restrict__ xt, int64_t rows_cap, int row_first) {
-  __shared__ float tile[TF_ROWS][SGN + 1];
+  __shared__ __align__(16) float tile_s[TF_ROWS * SGN];
+  const SwzTile tile{tile_s};
   transpose_fast_tile<CH, PLANAR, VEC, TF_ROWS>(tile, blockIdx.x, blockIdx.y * TF_ROWS, in, in_ss, in_cs, channels,
                                                 n_series, xt, rows_cap, row_first);
 }
@@ -279,7 +280,8 @@ __global__ void __launch_bounds__(TF_THREADS)
                                 float *__restrict__ xt, int64_t rows_cap, int row_first, int n_groups, int n_tiles,
                                 int *__restrict__ ready) {
   constexpr int ROWS = kReadyTileRows;
-  __shared__ float tile[ROWS][SGN + 1];
+  __shared__ __align__(16) float tile_s[ROWS * SGN];
+  const SwzTile tile{tile_s};
   grid_launch_dependents();
   const int tid = threadIdx.x;
   constexpr int UNITS = SGN / CH;            // contiguous runs per group (streams, or series when planar)
@@ -309,14 +311,14 @@ __global__ void __launch_bounds__(TF_THREADS)
       const int e0 = off4 * 4;
 #pragma unroll
       for (int k = 0; k < 4; ++k)
-        tile[(e0 + k) / CH][unit * CH + ((e0 + k) % CH)] = xv[k];
+        tile.at((e0 + k) / CH, unit * CH + ((e0 + k) % CH)) = xv[k];
     }
     __syncthreads();
     float4 *dst = reinterpret_cast<float4 *>(xt + ((int64_t) g * rows_cap + row_first + j0) * SGN);
 #pragma unroll 4
     for (int i = tid; i < ROWS * (SGN / 4); i += TF_THREADS) {
       const int row = i / (SGN / 4), c4 = i % (SGN / 4);
-      dst[i] = make_float4(tile[row][c4 * 4], tile[row][c4 * 4 + 1], tile[row][c4 * 4 + 2], tile[row][c4 * 4 + 3]);
+      dst[i] = tile.vec(row, c4);
     }
     __syncthreads();  // every thread's stores are issued (and the tile may be overwritten)
     if (tid == 0) {
@@ -479,7 +481,8 @@ template <int CH, bool PLANAR>
 __global__ void __launch_bounds__(TF_THREADS)
     espb_untranspose_fast_kernel(const float *__restrict__ tm, int64_t rows_cap, int row_first, float *__restrict__ out,
                                  int64_t out_ss, int64_t out_cs, int channels, int n_series) {
-  __shared__ float tile[TF_ROWS][SGN + 1];
+  __shared__ __align__(16) float tile_s[TF_ROWS * SGN];
+  const SwzTile tile{tile_s};
   const int g = blockIdx.x;
   const int j0 = blockIdx.y * TF_ROWS;
   const int tid = threadIdx.x;
@@ -487,11 +490,7 @@ __global__ void __launch_bounds__(TF_THREADS)
 #pragma unroll 4
   for (int i = tid; i < TF_ROWS * (SGN / 4); i += TF_THREADS) {
     const int t = i / (SGN / 4), c4 = i % (SGN / 4);
-    const float4 v = __ldg(src + i);
-    tile[t][c4 * 4] = v.x;
-    tile[t][c4 * 4 + 1] = v.y;
-    tile[t][c4 * 4 + 2] = v.z;
-    tile[t][c4 * 4 + 3] = v.w;
+    tile.vec(t, c4) = __ldg(src + i);
   }
   __syncthreads();
   constexpr int UNITS = SGN / CH;
@@ -514,7 +513,7 @@ __global__ void __launch_bounds__(TF_THREADS)
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const int e = e0 + k;
-      x[k] = tile[e / CH][unit * CH + (e % CH)];
+      x[k] = tile.at(e / CH, unit * CH + (e % CH));
     }
     reinterpret_cast<float4 *>(dst)[off4] = make_float4(x[0], x[1], x[2], x[3]);
   }
