@@ -130,9 +130,16 @@ class ClockSampler:
             for bit, name in self.REASONS.items():
                 if r[4] & bit:
                     reasons.add(name)
-        return {"sm_mhz": float(np.median([r[1] for r in loaded])), "sm_max_mhz": max(r[2] for r in use),
-                "power_w_max": pmax, "samples": len(use), "samples_in_timed_region": len(timed),
-                "window": "timed region" if use is timed else "warm-up + timed region", "reasons": sorted(reasons)}
+        out = {"sm_mhz": float(np.median([r[1] for r in loaded])), "sm_max_mhz": max(r[2] for r in use),
+               "power_w_max": pmax, "samples": len(use), "samples_in_timed_region": len(timed),
+               "window": "timed region" if use is timed else "warm-up + timed region", "reasons": sorted(reasons)}
+        if len(self.marks) >= 4:  # the second timed loop (per-launch kernel events: the roofline's numerator)
+            second = [r for r in rows if self.marks[2] <= r[0] <= self.marks[3]]
+            if second:
+                out["roofline_loop"] = {"sm_mhz": float(np.median([r[1] for r in second])),
+                                        "sm_mhz_min": min(r[1] for r in second),
+                                        "power_w_max": max(r[3] for r in second), "samples": len(second)}
+        return out
 
 
 def host_threads():
@@ -690,12 +697,14 @@ def main():
     step()
     ctx.kernel_time()  # drop the warm-up record
     ranks.barrier()
+    sampler.mark()
     L.espb_event_record(ev0, stream)
     for _ in range(args.steps):
         step()
     L.espb_event_record(ev1, stream)
     espb.capi._check(L.espb_event_elapsed_ms(ev0, ev1, espb.capi.C.byref(ms)), "elapsed")
     ranks.barrier()
+    sampler.mark()
     kernel_ms, kernel_launches = ctx.kernel_time()
     serial_ms_per_step = float(ms.value) / args.steps
     ctx.set_option(espb.OPT_KERNEL_TIMING, 0)
