@@ -718,6 +718,7 @@ struct StageFilter {
   int block_rows = 0, warm_rows = 0;     // time-block mode of the biquad kernel (0 = sequential)
   float *blk_state = nullptr;            // per-block state record of the first group of the range (time-block mode)
   unsigned int *mismatches = nullptr;    // counter of repaired blocks
+  unsigned int *chain_broken = nullptr;  // one scratch word per group of the range (parallel hand-over check)
 };
 
 // cuTensorMapEncodeTiled through the runtime's driver entry point (the library does not link libcuda, so it still
@@ -846,7 +847,8 @@ int run_series_range(EspbResampleBatch *c, int series_first, int n_series, const
                              kChunkRows * row_bytes, ng, stream),
            "pad rows");
     CU_TRY(launch_biquad_tm(x_raw, x_new, rows, taps, n_in, n_series, pre->sections, *pre->params, pre->state,
-                            pre->block_rows, pre->warm_rows, stream, pre->blk_state, pre->mismatches),
+                            pre->block_rows, pre->warm_rows, stream, pre->blk_state, pre->mismatches,
+                            pre->chain_broken),
            "biquad kernel");
   } else {
     // Long float calls of the standard kernel: the transposition signals its progress per row tile and the resampler
@@ -1025,7 +1027,8 @@ int run_series_range(EspbResampleBatch *c, int series_first, int n_series, const
         blocks = post->block_rows;
       }
       CU_TRY(launch_biquad_tm(y_tm, y_f, c->yt_rows, 0, gen, n_series, post->sections, *post->params, post->state,
-                              blocks, post->warm_rows, stream, post->blk_state, post->mismatches),
+                              blocks, post->warm_rows, stream, post->blk_state, post->mismatches,
+                              post->chain_broken),
              "biquad kernel");
     }
     if (pcm_out) {  // resampler.cpp:152-153: float_to_quantized, fused with the way back to the caller's layout
@@ -1537,6 +1540,7 @@ struct EspbBiquadBatch {
   int block_rows = -1, warm_rows = 1024;
   bool one_pass = true;  // ESPB_BIQUAD_ONEPASS=0: always through time-major scratch (three passes)
   DevBuf blk_state;                      // (start, end) state of every block, for the verify kernel
+  DevBuf chain_broken;                   // [groups] scratch flags of the parallel hand-over check
   DevBuf mismatch_dev;                   // [1] blocks repaired so far in the call being enqueued
   unsigned int *mismatch_host = nullptr; // pinned copy of the previous call's count
   cudaEvent_t mismatch_ready = nullptr;
@@ -1561,6 +1565,8 @@ namespace {
 int biquad_prepare_blocks(EspbBiquadBatch *f, int n_rows, int block_rows, cudaStream_t stream) {
   const size_t floats = biquad_block_state_floats(f->num_series, f->num_sections, n_rows, block_rows);
   CU_TRY(f->blk_state.reserve(floats * sizeof(float)), "biquad block states");
+  CU_TRY(f->chain_broken.reserve((size_t) ((f->num_series + kSeriesPerRow - 1) / kSeriesPerRow) * sizeof(unsigned int)),
+         "biquad chain flags");
   if (!f->mismatch_dev.p) {
     CU_TRY(f->mismatch_dev.reserve(sizeof(unsigned int)), "biquad counter");
     CU_TRY(cudaMallocHost(&f->mismatch_host, sizeof(unsigned int)), "biquad counter");
@@ -1636,6 +1642,7 @@ void espb_biquad_free(EspbBiquadBatch *f) {
   f->tm2.release();
   f->state.release();
   f->blk_state.release();
+  f->chain_broken.release();
   f->mismatch_dev.release();
   if (f->mismatch_host)
     cudaFreeHost(f->mismatch_host);
@@ -1694,7 +1701,7 @@ int espb_biquad_apply_buffer(EspbBiquadBatch *f, float *buf, const EspbLayout *l
   }
   CU_TRY(launch_biquad_tm(f->tm.as<float>(), filtered, f->tm_rows, 0, num_samples, f->num_series, f->num_sections,
                           f->params, f->state.as<float>(), blocks, f->warm_rows, s, f->blk_state.as<float>(),
-                          f->mismatch_dev.as<unsigned int>()),
+                          f->mismatch_dev.as<unsigned int>(), blocks > 0 ? f->chain_broken.as<unsigned int>() : nullptr),
          "biquad kernel");
   if (blocks > 0)
     if (int rc = biquad_finish_blocks(f, s))
@@ -2104,6 +2111,7 @@ int wrapper_run_range(EspbResampler *r, int s0, int ns, const uint8_t *d_in, int
       flt.blk_state = lp->blk_state.as<float>() +
                       (size_t) (s0 * ch / kSeriesPerRow) * n_blocks * lp->num_sections * 2 * kSeriesPerRow * 4;
       flt.mismatches = lp->mismatch_dev.as<unsigned int>();
+      flt.chain_broken = lp->chain_broken.as<unsigned int>() + (size_t) (s0 * ch / kSeriesPerRow);
     }
   }
   (void) out_free;

@@ -182,7 +182,9 @@ cudaError_t launch_biquad_cl(float *buf, int64_t ss, int64_t cs, int64_t fs, int
 cudaError_t launch_biquad_tm(const float *src, float *dst, int64_t rows_cap, int row_first, int n_rows, int n_series,
                              int n_sections, BiquadParams c, float *state /* [series][section][4] */,
                              int block_rows, int warm_rows, cudaStream_t stream, float *blk_state = nullptr,
-                             unsigned int *mismatches = nullptr);
+                             unsigned int *mismatches = nullptr, unsigned int *chain_broken = nullptr);
+// (chain_broken: one scratch word per group of the launch; with it the hand-overs are compared in parallel first and
+//  the sequential walk is taken only by groups in which one differs)
 // mono streams: post-filter + float_to_quantized in one pass (biquad_kernel.cu); returns the frames written as PCM
 int launch_biquad_tm_pcm(float *buf, int64_t rows_cap, int row_first, int n_rows, int n_series, int n_sections,
                          BiquadParams c, float *state, uint8_t *out, int64_t out_row_bytes, int bits,
