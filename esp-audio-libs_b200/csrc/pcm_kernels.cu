@@ -205,10 +205,13 @@ __global__ void __launch_bounds__(PT_THREADS)
   }
   __syncthreads();
   float4 *dst = reinterpret_cast<float4 *>(tm + ((int64_t) g * rows_cap + row_first + j0) * SGN);
+  // (few series in the group: only the 16-byte units that hold series are written — see transpose_fast_tile)
+  const int units = (n_series - g * SGN + 3) / 4;
 #pragma unroll 4
   for (int i = tid; i < PT_ROWS * (SGN / 4); i += PT_THREADS) {
     const int t = i / (SGN / 4), c4 = i % (SGN / 4);
-    dst[i] = tile.vec(t, c4);
+    if (c4 < units)
+      dst[i] = tile.vec(t, c4);
   }
 }
 

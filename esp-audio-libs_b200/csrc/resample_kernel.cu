@@ -247,10 +247,14 @@ __device__ __forceinline__ void transpose_fast_tile(const SwzTile tile, int g, i
   }
   __syncthreads();
   float4 *dst = reinterpret_cast<float4 *>(xt + ((int64_t) g * rows_cap + row_first + j0) * SGN);
+  // (a group with few series — one stereo or 8-channel stream per context — only writes the 16-byte units that hold
+  //  series: the others were zeroed when the staging buffers were allocated and nobody reads them as data)
+  const int units = (n_series - g * SGN + 3) / 4;
 #pragma unroll 4
   for (int i = tid; i < ROWS * (SGN / 4); i += TF_THREADS) {
     const int t = i / (SGN / 4), c4 = i % (SGN / 4);
-    dst[i] = tile.vec(t, c4);
+    if (c4 < units)
+      dst[i] = tile.vec(t, c4);
   }
 }
 
