@@ -183,8 +183,12 @@ __global__ void __launch_bounds__(PT_THREADS)
   const int g = blockIdx.x, j0 = blockIdx.y * PT_ROWS, tid = threadIdx.x;
   constexpr int UNITS = SGN / CH;            // streams per group
   constexpr int GROUPS = PT_ROWS * CH / 4;   // 4-sample groups per stream per tile
+  // 16-byte units of a row that hold series of this group (all 32 but in the last group), and the streams they span:
+  // a group with few series neither fills nor stores the rest of the tile
+  const int units = (n_series - g * SGN + 3) / 4 < SGN / 4 ? (n_series - g * SGN + 3) / 4 : SGN / 4;
+  const int streams_here = (units * 4 + CH - 1) / CH < UNITS ? (units * 4 + CH - 1) / CH : UNITS;
 #pragma unroll 2
-  for (int v = tid; v < UNITS * GROUPS; v += PT_THREADS) {
+  for (int v = tid; v < streams_here * GROUPS; v += PT_THREADS) {
     const int unit = v / GROUPS, grp = v % GROUPS;
     const int q0 = g * SGN + unit * CH;
     int32_t s[4] = {0, 0, 0, 0};
@@ -205,8 +209,6 @@ __global__ void __launch_bounds__(PT_THREADS)
   }
   __syncthreads();
   float4 *dst = reinterpret_cast<float4 *>(tm + ((int64_t) g * rows_cap + row_first + j0) * SGN);
-  // (few series in the group: only the 16-byte units that hold series are written — see transpose_fast_tile)
-  const int units = (n_series - g * SGN + 3) / 4;
 #pragma unroll 4
   for (int i = tid; i < PT_ROWS * (SGN / 4); i += PT_THREADS) {
     const int t = i / (SGN / 4), c4 = i % (SGN / 4);

@@ -212,8 +212,13 @@ __device__ __forceinline__ void transpose_fast_tile(const SwzTile tile, int g, i
   const int tid = threadIdx.x;
   constexpr int UNITS = SGN / CH;              // contiguous runs per group (streams, or series when planar)
   constexpr int V_PER_UNIT = ROWS * CH / VEC;  // vectors per run
+  // 16-byte units of a row that hold series of this group (all 32 but in the last group), and the runs they span:
+  // a group with few series — one stereo or 8-channel stream per context — neither fills nor stores the rest of
+  // the tile (those units of xt were zeroed when the staging buffers were allocated; nobody reads them as data)
+  const int units = (n_series - g * SGN + 3) / 4 < SGN / 4 ? (n_series - g * SGN + 3) / 4 : SGN / 4;
+  const int runs_here = (units * 4 + CH - 1) / CH < UNITS ? (units * 4 + CH - 1) / CH : UNITS;
 #pragma unroll 4
-  for (int v = tid; v < UNITS * V_PER_UNIT; v += TF_THREADS) {
+  for (int v = tid; v < runs_here * V_PER_UNIT; v += TF_THREADS) {
     const int unit = v / V_PER_UNIT, off4 = v % V_PER_UNIT;  // powers of two: shifts
     const int q0 = g * SGN + unit * CH;                       // first series of the run
     float xv[VEC];
@@ -247,9 +252,6 @@ __device__ __forceinline__ void transpose_fast_tile(const SwzTile tile, int g, i
   }
   __syncthreads();
   float4 *dst = reinterpret_cast<float4 *>(xt + ((int64_t) g * rows_cap + row_first + j0) * SGN);
-  // (a group with few series — one stereo or 8-channel stream per context — only writes the 16-byte units that hold
-  //  series: the others were zeroed when the staging buffers were allocated and nobody reads them as data)
-  const int units = (n_series - g * SGN + 3) / 4;
 #pragma unroll 4
   for (int i = tid; i < ROWS * (SGN / 4); i += TF_THREADS) {
     const int t = i / (SGN / 4), c4 = i % (SGN / 4);
