@@ -225,16 +225,20 @@ __global__ void __launch_bounds__(PT_THREADS)
   const SwzTile tile{tile_s};
   const int g = blockIdx.x, j0 = blockIdx.y * PT_ROWS, tid = threadIdx.x;
   const float4 *src = reinterpret_cast<const float4 *>(tm + ((int64_t) g * rows_cap + row_first + j0) * SGN);
+  constexpr int UNITS = SGN / CH;
+  constexpr int GROUPS = PT_ROWS * CH / 4;
+  // (a group with few series reads and converts only the 16-byte units that hold series: espb_pcm_to_tm_kernel)
+  const int units = (n_series - g * SGN + 3) / 4 < SGN / 4 ? (n_series - g * SGN + 3) / 4 : SGN / 4;
+  const int streams_here = (units * 4 + CH - 1) / CH < UNITS ? (units * 4 + CH - 1) / CH : UNITS;
 #pragma unroll 4
   for (int i = tid; i < PT_ROWS * (SGN / 4); i += PT_THREADS) {
     const int t = i / (SGN / 4), c4 = i % (SGN / 4);
-    tile.vec(t, c4) = __ldg(src + i);
+    if (c4 < units)
+      tile.vec(t, c4) = __ldg(src + i);
   }
   __syncthreads();
-  constexpr int UNITS = SGN / CH;
-  constexpr int GROUPS = PT_ROWS * CH / 4;
 #pragma unroll 2
-  for (int v = tid; v < UNITS * GROUPS; v += PT_THREADS) {
+  for (int v = tid; v < streams_here * GROUPS; v += PT_THREADS) {
     const int unit = v / GROUPS, grp = v % GROUPS;
     const int q0 = g * SGN + unit * CH;
     if (q0 >= n_series)

@@ -493,16 +493,20 @@ __global__ void __launch_bounds__(TF_THREADS)
   const int j0 = blockIdx.y * TF_ROWS;
   const int tid = threadIdx.x;
   const float4 *src = reinterpret_cast<const float4 *>(tm + ((int64_t) g * rows_cap + row_first + j0) * SGN);
+  constexpr int UNITS = SGN / CH;
+  constexpr int V_PER_UNIT = TF_ROWS * CH / 4;
+  // (a group with few series reads and lays out only the 16-byte units that hold series: transpose_fast_tile)
+  const int units = (n_series - g * SGN + 3) / 4 < SGN / 4 ? (n_series - g * SGN + 3) / 4 : SGN / 4;
+  const int runs_here = (units * 4 + CH - 1) / CH < UNITS ? (units * 4 + CH - 1) / CH : UNITS;
 #pragma unroll 4
   for (int i = tid; i < TF_ROWS * (SGN / 4); i += TF_THREADS) {
     const int t = i / (SGN / 4), c4 = i % (SGN / 4);
-    tile.vec(t, c4) = __ldg(src + i);
+    if (c4 < units)
+      tile.vec(t, c4) = __ldg(src + i);
   }
   __syncthreads();
-  constexpr int UNITS = SGN / CH;
-  constexpr int V_PER_UNIT = TF_ROWS * CH / 4;
 #pragma unroll 4
-  for (int v = tid; v < UNITS * V_PER_UNIT; v += TF_THREADS) {
+  for (int v = tid; v < runs_here * V_PER_UNIT; v += TF_THREADS) {
     const int unit = v / V_PER_UNIT, off4 = v % V_PER_UNIT;
     const int q0 = g * SGN + unit * CH;
     if (q0 >= n_series)
