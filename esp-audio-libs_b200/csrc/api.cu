@@ -1547,13 +1547,14 @@ struct EspbBiquadBatch {
   bool mismatch_pending = false;
   uint64_t repaired_total = 0;
   static constexpr int kAutoBlockRows = 8192, kAutoMaxGroups = 32, kMaxWarmRows = 1 << 16;
+  static constexpr int kAutoBlockRowsFew = 2048;  // (espb_biquad_tm_few_kernel: nothing is staged, short blocks pay)
   int n_groups() const { return (num_series + kSeriesPerRow - 1) / kSeriesPerRow; }
   // rows per block for a call over n_rows rows (0: sequential)
   int blocks_for(int n_rows) const {
     if (block_rows > 0)
       return n_rows > block_rows ? block_rows : 0;
     if (block_rows < 0 && n_groups() <= kAutoMaxGroups && n_rows >= 2 * kAutoBlockRows)
-      return kAutoBlockRows;
+      return num_series <= kBiquadFewSeries ? kAutoBlockRowsFew : kAutoBlockRows;
     return 0;
   }
 };

@@ -354,6 +354,66 @@ __device__ __forceinline__ bool same_bits(const float4 &a, const float4 &b) {
          __float_as_uint(a.z) == __float_as_uint(b.z) && __float_as_uint(a.w) == __float_as_uint(b.w);
 }
 
+// Time blocks of ONE group with few series (a single stereo or 8-channel stream: C4).  The kernel above would run one
+// CTA per block with 8 of its 128 threads holding a series and move whole 512-byte rows through its ring, 15/16 of
+// them padding.  Here a thread is a (block, series) pair — 128 / lanes blocks per CTA — that reads only its own
+// column (the lanes of a block share one 32-byte sector per row, 16 rows of loads in flight ahead of the recurrence)
+// and writes only its own results.  Same recurrence, same warm-up, same state record (so the chain check, the
+// verify kernel and the repairs are shared); since nothing is staged the blocks can be shorter, which is where the
+// parallelism for a single stream comes from.
+template <int NSEC, bool FIRST_ORDER>
+__global__ void __launch_bounds__(SGN)
+    espb_biquad_tm_few_kernel(const float *__restrict__ src, float *__restrict__ dst, int row_first, int n_rows,
+                              BiquadParams c, const float *__restrict__ state, int n_series, int lanes, int block_rows,
+                              int warm_rows, int n_blocks, float4 *__restrict__ blk_state) {
+  const int gid = blockIdx.x * SGN + threadIdx.x;
+  const int blk = gid / lanes, q = gid - blk * lanes;
+  if (blk >= n_blocks || q >= n_series)
+    return;
+  const int blk_lo = blk * block_rows;
+  const int blk_hi = blk_lo + block_rows < n_rows ? blk_lo + block_rows : n_rows;
+  const int run_lo = (blk == 0 || blk_lo < warm_rows) ? 0 : blk_lo - warm_rows;
+  Section sec[NSEC];
+#pragma unroll
+  for (int k = 0; k < NSEC; ++k) {
+    float4 v = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    if (run_lo == 0)
+      v = *reinterpret_cast<const float4 *>(state + ((int64_t) q * NSEC + k) * 4);
+    sec[k].in_d1 = v.x, sec[k].in_d2 = v.y, sec[k].out_d1 = v.z, sec[k].out_d2 = v.w;
+  }
+  const float *ps = src + (int64_t) (row_first + run_lo) * SGN + q;
+  float *pd = dst + (int64_t) (row_first + run_lo) * SGN + q;
+  float4 *rec = blk_state + ((size_t) blk * NSEC * 2) * SGN + q;  // (group 0)
+  const int n = blk_hi - run_lo, store_from = blk_lo - run_lo;
+  constexpr int U = 16;
+  for (int r0 = 0; r0 < n; r0 += U) {
+    float x[U];
+#pragma unroll
+    for (int i = 0; i < U; ++i)
+      x[i] = r0 + i < n ? __ldg(ps + (int64_t) (r0 + i) * SGN) : 0.0f;
+#pragma unroll
+    for (int i = 0; i < U; ++i) {
+      const int r = r0 + i;
+      if (r < n) {
+        if (r == store_from) {  // the state this block's own rows start from, for the chain check
+#pragma unroll
+          for (int s2 = 0; s2 < NSEC; ++s2)
+            rec[(s2 * 2) * SGN] = make_float4(sec[s2].in_d1, sec[s2].in_d2, sec[s2].out_d1, sec[s2].out_d2);
+        }
+        float v = x[i];
+#pragma unroll
+        for (int s2 = 0; s2 < NSEC; ++s2)
+          v = section_step<FIRST_ORDER>(sec[s2], v, c);
+        if (r >= store_from)
+          pd[(int64_t) r * SGN] = v;
+      }
+    }
+  }
+#pragma unroll
+  for (int s2 = 0; s2 < NSEC; ++s2)
+    rec[(s2 * 2 + 1) * SGN] = make_float4(sec[s2].in_d1, sec[s2].in_d2, sec[s2].out_d1, sec[s2].out_d2);
+}
+
 // The comparisons of the chain check do not depend on each other — only a repair does — so they run first, one
 // thread per (series, block), and leave one flag per group: unbroken chains (the normal case) then cost the verify
 // kernel one load per series instead of a sequential walk over all blocks (C4, 352 blocks: 378 us -> a few us).
@@ -684,7 +744,18 @@ cudaError_t launch_tm(const float *src, float *dst, int64_t rows_cap, int row_fi
     if (e != cudaSuccess)
       return e;
   }
-  if (c.first_order)
+  if (rec && n_series <= kBiquadFewSeries) {  // one group, few series: threads are (block, series) pairs
+    int lanes = 4;
+    while (lanes < n_series)
+      lanes *= 2;
+    const int ctas = (n_blocks * lanes + SGN - 1) / SGN;
+    if (c.first_order)
+      espb_biquad_tm_few_kernel<NSEC, true><<<ctas, SGN, 0, stream>>>(src, dst, row_first, n_rows, c, state, n_series,
+                                                                     lanes, block_rows, warm_rows, n_blocks, rec);
+    else
+      espb_biquad_tm_few_kernel<NSEC, false><<<ctas, SGN, 0, stream>>>(src, dst, row_first, n_rows, c, state, n_series,
+                                                                      lanes, block_rows, warm_rows, n_blocks, rec);
+  } else if (c.first_order)
     espb_biquad_tm_kernel<NSEC, true><<<grid, SGN, smem, stream>>>(src, dst, rows_cap, row_first, n_rows, c, state,
                                                                    n_series, block_rows, warm_rows, rec);
   else

@@ -176,6 +176,8 @@ struct BiquadParams {
 // at its end, which espb_biquad_verify_kernel compares — and repairs where they differ — before committing the final
 // state) and may be given a counter of repaired blocks.
 size_t biquad_block_state_floats(int n_series, int n_sections, int n_rows, int block_rows);
+// banks of at most this many series (one group) run their time blocks as (block, series) threads: shorter blocks pay
+constexpr int kBiquadFewSeries = 32;
 // the same filter in ONE pass on the caller's layout (interleaved or frame-contiguous; cudaErrorNotSupported else)
 cudaError_t launch_biquad_cl(float *buf, int64_t ss, int64_t cs, int64_t fs, int channels, int n_series, int n_frames,
                              int n_sections, BiquadParams c, float *state, cudaStream_t stream);
